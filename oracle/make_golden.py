@@ -1,0 +1,215 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference classes
+(/root/reference, via oracle/ref_harness.py) on small seeded inputs.
+
+Run in the authoring container only:  python oracle/make_golden.py
+The fixtures (inputs + reference outputs) are committed; the GPU box and CI never need
+/root/reference.  Re-running must reproduce the committed files bit for bit (all inputs
+come from seeded generators).
+"""
+from __future__ import annotations
+
+import io
+import os
+import sys
+import warnings
+from contextlib import redirect_stdout
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+from oracle import np_oracle, ref_harness  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def quiet(fn, *a, **k):
+    with redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return fn(*a, **k)
+
+
+def ref_dsa(ref, xtr, ytr, xte, pte, **kw):
+    sa = quiet(ref.surprise.DSA, xtr, ytr, **kw)
+    import tqdm
+
+    real = tqdm.tqdm
+    try:
+        tqdm.tqdm = lambda it, **_: it          # silence the progress bar only
+        dsa = quiet(sa, xte, pte)
+    finally:
+        tqdm.tqdm = real
+    # per-class distances straight from the reference's _dsa_distances (surprise.py:615-631)
+    da = np.zeros(xte.shape[0], dtype=sa.train_activations.dtype)
+    db = np.zeros_like(da)
+    for c in range(sa.num_classes):
+        rows = np.argwhere(np.asarray(pte) == c).flatten()
+        for chunk in np.array_split(rows, max(1, int(np.ceil(rows.size / 64)))):
+            if chunk.size:
+                a, b = sa._dsa_distances(np_oracle.flatten_rows(np.asarray(xte))[chunk], c)
+                da[chunk], db[chunk] = a, b
+    return dsa, da, db
+
+
+def dsa_cases(ref):
+    cases = {}
+    # g1: float32 Gaussian clusters
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(600, 100, 16, 4, seed=11)
+    cases["f32_clusters"] = (xtr, ytr, xte, pte, {})
+    # g2: the reference's own plausibility inputs (tests/test_surprise.py:141-151), float64
+    rng = np.random.RandomState(42)
+    act = rng.random((100, 10))
+    lab = rng.randint(0, 3, size=100)
+    cases["f64_plausibility_id"] = (act, lab, act[:10], lab[:10], {})
+    cases["f64_plausibility_ood"] = (act, lab, act[:10] + 10, lab[:10], {})
+    # g3: exact ties — small-integer valued float32 traces, duplicated train rows
+    rng = np.random.default_rng(12)
+    base = rng.integers(0, 3, size=(60, 12)).astype(np.float32)
+    xtr = np.concatenate([base, base[:20], base[5:25]])
+    ytr = np.concatenate([np.arange(60) % 3, np.arange(20) % 3, (np.arange(20) + 5) % 3]).astype(np.int64)
+    xte = np.concatenate([base[:15], rng.integers(0, 3, size=(25, 12)).astype(np.float32)])
+    pte = rng.integers(0, 3, size=40).astype(np.int64)
+    cases["f32_ties"] = (xtr, ytr, xte, pte, {})
+    # g4: the study's configuration: subsampling=0.3 (handler_surprise.py:24)
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(1000, 64, 32, 5, seed=13)
+    cases["f32_subsample"] = (xtr, ytr, xte, pte, {"subsampling": 0.3})
+    # g5/g6: D > 128 (recursive pairwise split) and D < 8 (sequential sum)
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(300, 40, 300, 3, seed=14)
+    cases["f32_d300"] = (xtr, ytr, xte, pte, {})
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(200, 30, 5, 2, seed=15)
+    cases["f32_d5"] = (xtr, ytr, xte, pte, {})
+    # g7: ragged — one class absent from the test predictions, badge_size 7, 3-D traces
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(240, 33, 24, 4, seed=16)
+    pte[pte == 2] = 1
+    cases["f32_ragged_3d"] = (xtr.reshape(240, 2, 12), ytr, xte.reshape(33, 2, 12), pte, {"badge_size": 7})
+    out = {}
+    for name, (xtr, ytr, xte, pte, kw) in cases.items():
+        dsa, da, db = ref_dsa(ref, xtr, ytr, xte, pte, **kw)
+        out[f"{name}.xtr"], out[f"{name}.ytr"], out[f"{name}.xte"], out[f"{name}.pte"] = xtr, ytr, xte, pte
+        out[f"{name}.dsa"], out[f"{name}.dist_a"], out[f"{name}.dist_b"] = dsa, da, db
+        out[f"{name}.kw"] = np.array(repr(kw))
+    np.savez_compressed(os.path.join(OUT, "dsa_reference.npz"), **out)
+    print("dsa:", list(cases))
+
+
+def lsa_cases(ref):
+    out = {}
+    rng = np.random.RandomState(42)
+    # the reference's plausibility inputs (tests/test_surprise.py:141-151): finite ID, inf OOD
+    act = rng.random((100, 10))
+    sa = quiet(ref.surprise.LSA, act)
+    out["plaus.xtr"], out["plaus.xte"] = act, np.concatenate([act[:10], act[:10] + 10])
+    out["plaus.lsa"] = quiet(sa, out["plaus.xte"])
+    # unit cube 2000 x 10
+    a = rng.random((2000, 10)).astype(np.float32)
+    t = rng.random((100, 10)).astype(np.float32)
+    out["cube.xtr"], out["cube.xte"] = a, t
+    out["cube.lsa"] = quiet(quiet(ref.surprise.LSA, a), t)
+    # clusters with column removal (max_features=30 of 40)
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(3000, 120, 40, 4, seed=21)
+    sa = quiet(ref.surprise.LSA, xtr, max_features=30)
+    out["mf30.xtr"], out["mf30.xte"] = xtr, xte
+    out["mf30.lsa"] = quiet(sa, xte)
+    out["mf30.removed"] = np.array(sa.removed_neurons, dtype=np.int64)
+    # pc-lsa (MultiModalSA.build_by_class, handler_surprise.py:26)
+    mm = quiet(ref.surprise.MultiModalSA.build_by_class, xtr, ytr, lambda x, y: ref.surprise.LSA(x))
+    out["pclsa.ytr"], out["pclsa.pte"] = ytr, pte
+    out["pclsa.lsa"] = quiet(mm, xte, pte)
+    # singular covariance (duplicated column) -> _stabilize_covariance replaces the diagonal
+    base = rng.random((500, 6))
+    sing = np.concatenate([base, base[:, :1]], axis=1)
+    sa = quiet(ref.surprise.LSA, sing)
+    out["singular.xtr"], out["singular.xte"] = sing, sing[:20] + 0.01
+    out["singular.lsa"] = quiet(sa, out["singular.xte"])
+    out["singular.prepare_failed"] = np.array(bool(sa.kde.prepare_failed))
+    # moderately far points: finite but large values (log-domain stress)
+    out["far.xtr"], out["far.xte"] = a, (t * 3.0 + 0.5).astype(np.float32)
+    out["far.lsa"] = quiet(quiet(ref.surprise.LSA, a), out["far.xte"])
+    np.savez_compressed(os.path.join(OUT, "lsa_reference.npz"), **out)
+    print("lsa: plaus cube mf30 pclsa singular far;",
+          "inf count", int(np.isinf(out["plaus.lsa"]).sum()), int(np.isinf(out["far.lsa"]).sum()),
+          "singular prepare_failed", bool(sa.kde.prepare_failed))
+
+
+def coverage_cases(ref):
+    out = {}
+    rng = np.random.default_rng(31)
+    for name, dt_act, dt_stat, sections, n, d in [
+        ("k2_f32", np.float32, np.float32, 2, 17, 29),
+        ("k10_f32", np.float32, np.float32, 10, 33, 64),
+        ("k1000_f32", np.float32, np.float32, 1000, 9, 40),
+        ("k7_f64stat", np.float32, np.float64, 7, 12, 21),
+        ("k5_f64", np.float64, np.float64, 5, 10, 16),
+    ]:
+        stat = np.maximum(rng.normal(size=(200, d)), 0).astype(dt_stat)
+        mins, maxs = stat.min(axis=0), stat.max(axis=0)
+        maxs[::9] = mins[::9]                      # constant neurons: jumps == 0
+        act = np.maximum(rng.normal(size=(n, d)) * 1.3, 0).astype(dt_act)
+        act[0, 1] = maxs[1]                        # a == max hits no bucket (half-open)
+        act[1, 2] = mins[2]                        # a == min hits bucket 0
+        act[2, 3] = -0.5                           # below range
+        # split into two "layers" like the handlers pass them (neuron_coverage.py:25-28)
+        cut = d // 3
+        km = ref.neuron_coverage.KMNC([mins[:cut], mins[cut:]], [maxs[:cut], maxs[cut:]], sections)
+        score, prof = km([act[:, :cut], act[:, cut:]])
+        out[f"{name}.mins"], out[f"{name}.maxs"], out[f"{name}.act"] = mins, maxs, act
+        out[f"{name}.cut"], out[f"{name}.sections"] = np.array(cut), np.array(sections)
+        out[f"{name}.score"] = score
+        out[f"{name}.bucket"] = np.where(prof.any(axis=2), prof.argmax(axis=2), -1).astype(np.int32)
+        out[f"{name}.hits"] = prof.sum(axis=2).astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "kmnc_reference.npz"), **out)
+    print("kmnc ok")
+
+
+def gini_apfd_cases(ref):
+    out = {}
+    for name, dt in (("c1_f32", np.float32), ("c1_f64", np.float64)):
+        p, truth = np_oracle.synth_softmax(2000, 10, seed=1, dtype=dt)
+        pred, gini = ref.deepgini.DeepGini.calculate(p)
+        order = np.argsort(-gini)                                  # eval_apfd_table.py:86
+        fault = (pred != truth)
+        out[f"{name}.p"], out[f"{name}.truth"] = p, truth
+        out[f"{name}.pred"], out[f"{name}.gini"] = pred, gini
+        out[f"{name}.apfd"] = np.array(ref.apfd.apfd_from_order(fault, order))
+    p, _ = np_oracle.synth_softmax(64, 1000, seed=2, dtype=np.float32)   # wide rows: n > 128 path
+    pred, gini = ref.deepgini.DeepGini.calculate(p)
+    out["wide.p"], out["wide.pred"], out["wide.gini"] = p, pred, gini
+    rng = np.random.default_rng(41)
+    for i in range(4):
+        n = int(rng.integers(5, 400))
+        fault = rng.random(n) < 0.3
+        fault[0] = True
+        order = rng.permutation(n)
+        out[f"apfd{i}.fault"], out[f"apfd{i}.order"] = fault, order
+        out[f"apfd{i}.value"] = np.array(ref.apfd.apfd_from_order(fault, order))
+    np.savez_compressed(os.path.join(OUT, "gini_apfd_reference.npz"), **out)
+    print("gini/apfd ok")
+
+
+def prioritizer_cases(ref):
+    out = {}
+    rng = np.random.default_rng(51)
+    for i, (n, w, dens) in enumerate([(12, 9, 0.3), (40, 64, 0.1), (30, 20, 0.6), (25, 50, 0.0)]):
+        prof = rng.random((n, w)) < dens
+        scores = prof.sum(axis=1).astype(np.int64) if i % 2 == 0 else rng.random(n)
+        out[f"cam{i}.profiles"], out[f"cam{i}.scores"] = prof, scores
+        out[f"cam{i}.order"] = np.array(list(ref.prioritizers.cam(scores, prof.copy())), dtype=np.int64)
+        out[f"cam{i}.ctm"] = np.array(list(ref.prioritizers.ctm(scores)), dtype=np.int64)
+    m = ref.surprise.SurpriseCoverageMapper(10, 2.5)
+    vals = rng.random(50) * 3
+    out["scm.values"], out["scm.profile"] = vals, m.get_coverage_profile(vals)
+    m = ref.surprise.SurpriseCoverageMapper(10, 2.5, overflow_bucket=True)
+    out["scm.profile_overflow"] = m.get_coverage_profile(vals)
+    np.savez_compressed(os.path.join(OUT, "prioritizers_reference.npz"), **out)
+    print("prioritizers ok")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_harness.load()
+    dsa_cases(ref)
+    lsa_cases(ref)
+    coverage_cases(ref)
+    gini_apfd_cases(ref)
+    prioritizer_cases(ref)
+    print("sizes:", {f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))})
