@@ -1,0 +1,163 @@
+/*
+ * b200tip.h — C ABI of libb200tip.so, the B200 (sm_100a) scoring engine behind the
+ * reference's `src.core` prioritizer API (testingautomated-usi/simple-tip).
+ *
+ * The reference has no FFI layer: its boundary is the Python class API of src/core
+ * (SURVEY.md §8b).  The host mirror in simple_tip_b200/core keeps those classes and calls
+ * the entry points below through ctypes.  Every array argument is a DEVICE pointer to a
+ * contiguous row-major buffer owned by the caller (PyTorch on the Python side); the library
+ * never frees caller memory and keeps no state between calls.  `stream` is a cudaStream_t
+ * passed as void*; launches are asynchronous on it.  Every function returns 0 on success or
+ * a negative tip_status; tip_last_error() returns a thread-local message.
+ *
+ * Which reference arithmetic each entry point replaces (paths relative to the reference):
+ *   tip_deepgini        src/core/deepgini.py:31-35     argmax + 1 - sum(p*p)
+ *   tip_kmnc            src/core/neuron_coverage.py:82-94 (+ sum_score :8-22)
+ *   tip_pair_prep       (new) operand packing for the tensor-core pass
+ *   tip_nn_filter       src/core/surprise.py:638-647   the B x M x D difference/norm/min, as a
+ *                       tcgen05 pass that yields a per-query candidate set provably containing
+ *                       NumPy's argmin
+ *   tip_nn_rerank       src/core/surprise.py:640-648   exact np.linalg.norm / np.min / np.argmin
+ *                       on the candidates, in NumPy's summation order (bit-identical)
+ *   tip_gather_rows     src/core/surprise.py:648       to_ats[closest_position]
+ *   tip_whiten          scipy==1.4.1 gaussian_kernel_estimate: points . cholesky(inv_cov)
+ *   tip_kde_lse         scipy==1.4.1 gaussian_kernel_estimate pair loop (called from
+ *                       src/core/stable_kde.py:101), in the log domain
+ *   tip_kde_combine     merge of per-column-chunk (max, sum) partials
+ */
+#ifndef B200TIP_H
+#define B200TIP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIP_VERSION 100
+
+typedef enum tip_status {
+  TIP_OK = 0,
+  TIP_ERR_INVALID = -1,    /* bad argument (shape, dtype, alignment) */
+  TIP_ERR_CUDA = -2,       /* CUDA runtime / driver error, see tip_last_error() */
+  TIP_ERR_UNSUPPORTED = -3 /* not an sm_100 device */
+} tip_status;
+
+typedef enum tip_dtype {
+  TIP_F32 = 0,
+  TIP_F64 = 1,
+  TIP_BF16 = 2,
+  TIP_I16 = 3,
+  TIP_I32 = 4
+} tip_dtype;
+
+/* operand roles / packing modes for tip_pair_prep */
+#define TIP_ROLE_QUERY 0 /* rows become TMEM lanes (test traces / stage-2 winners)    */
+#define TIP_ROLE_TRAIN 1 /* rows become accumulator columns (training traces)         */
+
+/* row selection for tip_nn_rerank */
+#define TIP_RANGE_SAME_CLASS 0   /* columns [off[c], off[c+1])                      */
+#define TIP_RANGE_OTHER_CLASSES 1 /* columns [0, off[c]) U [off[c+1], off[C])       */
+
+/* One unit of work of the tensor-core pass: 128 query rows x a span of train rows. */
+typedef struct tip_work_item {
+  int32_t q_row0;  /* first query row of the 128-row tile                          */
+  int32_t q_rows;  /* valid rows in the tile (1..128); others are computed, not stored */
+  int32_t col0;    /* first train row of the span                                   */
+  int32_t col1;    /* one past the last train row of the span                       */
+  int32_t slot;    /* tip_kde_lse: partial-result slot of this span; unused otherwise */
+  int32_t reserved;
+} tip_work_item;
+
+int tip_version(void);
+const char* tip_last_error(void);
+/* sm count and compute capability of the current device */
+int tip_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched in this process (bench.py: gpu_launches) */
+uint64_t tip_launch_count(void);
+
+/* ---- DeepGini (deepgini.py:31-35) ----------------------------------------------------
+ * probs: n x c (TIP_F32 or TIP_F64).  pred[n] = first argmax, gini[n] = 1 - sum(p*p) in the
+ * input dtype, summed in NumPy's pairwise order (bit-identical to np.sum(p*p, axis=1)). */
+int tip_deepgini(const void* probs, int dtype, int64_t n, int64_t c, int32_t* pred, void* gini,
+                 void* stream);
+
+/* ---- KMNC (neuron_coverage.py:65-94) -------------------------------------------------
+ * act: n x d (TIP_F32/TIP_F64); mins, jumps: d values of stat_dtype, jumps = (max-min)/k
+ * computed by the caller with the reference's NumPy expression.  Thresholds are
+ * t_i = min + jumps*i evaluated on the fly in stat_dtype (same rounding as NumPy).
+ * bucket[n*d] (TIP_I16 or TIP_I32) = the i with t_i <= a < t_{i+1}, or -1; score[n] = number of
+ * neurons with a bucket (== sum of the reference's dense profile). bucket may be NULL. */
+int tip_kmnc(const void* act, int act_dtype, int64_t n, int64_t d, const void* mins,
+             const void* jumps, int stat_dtype, int32_t sections, void* bucket, int bucket_dtype,
+             int32_t* score, void* stream);
+
+/* ---- operand packing for the tensor-core pass ----------------------------------------
+ * Packed row (bf16), D16 = round_up(d,16), one 16-wide tail block:
+ *   segments == 1:  [ s*h(v) | tail ]                 v = fl32(x - center)
+ *   segments == 3:  query: [ h | l | h | tail ]       h = bf16(v), l = bf16(v - h)
+ *                   train: [ s*h | s*h | s*l | tail ]
+ *   tail(query) = [1,1,1,0...]; tail(train) = bf16 3-way split of norm_coef*|v|^2
+ * so that one K-loop accumulates  norm_coef*|y|^2 + s * <x, y>  in fp32 TMEM.
+ * sqnorm[rows] receives |h(v)|^2 (segments==1) or |v|^2 (segments==3) as fp32.
+ * tip_pair_pitch returns the packed row pitch in elements (multiple of 64). */
+int64_t tip_pair_pitch(int64_t d, int segments);
+int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d, const float* center,
+                  int role, int segments, float scale, float norm_coef, void* dst_bf16,
+                  float* sqnorm, void* stream);
+
+/* ---- nearest-neighbour candidate filter (tcgen05 + TMA) ------------------------------
+ * q_pack: m x pitch, t_pack: n x pitch (tip_pair_prep, scale=-2, norm_coef=1).
+ * For every query row and every work item covering it, scans the item's train span and
+ * appends to cand_idx[row*cap + k] every train row whose approximate squared distance is
+ * within the proven error window of the running minimum; cand_cnt[row]
+ * counts appends (may exceed cap: overflow -> tip_nn_rerank falls back to an exact scan).
+ * row_min_bits[m] (uint32 float bits, initialised to +inf = 0x7f800000 by the caller) carries
+ * the running minimum across items/CTAs.  t_rmax = max_j |h(y_j)| over the train rows. */
+int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const void* t_pack,
+                  int64_t n, int64_t d, int64_t pitch, const tip_work_item* items,
+                  int32_t n_items, float t_rmax, uint32_t* row_min_bits, int32_t* cand_idx,
+                  int32_t* cand_cnt, int32_t cap, void* stream);
+
+/* ---- exact re-rank (NumPy-order distances, first-occurrence argmin) -------------------
+ * q, t: original-dtype (TIP_F32/TIP_F64) matrices m x d and n x d; train rows are grouped by
+ * class (class_off[C+1]); q_class[m] gives each query's class, mode the column range.
+ * Rows with 1..cap candidates are re-ranked over their candidates; rows with 0 or > cap
+ * candidates (or cand_cnt == NULL) are scanned exhaustively over their range.
+ * out_dist[m] (dtype) = sqrt(pairwise_sum((x-y)^2)) of the winner, out_pos[m] = its train row
+ * (ties: lowest t_gid), stats[0] += exhaustive rows, stats[1] += candidates evaluated. */
+int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n, int64_t d,
+                  const int32_t* cand_idx, const int32_t* cand_cnt, int32_t cap,
+                  const int32_t* q_class, const int32_t* class_off, int32_t n_classes, int mode,
+                  const int32_t* t_gid, void* out_dist, int32_t* out_pos, int64_t* stats,
+                  void* stream);
+
+/* dst[i,:] = src[pos[i],:]  (rows of `row_bytes` bytes; pos < 0 -> zero row) */
+int tip_gather_rows(const void* src, int64_t row_bytes, const int32_t* pos, int64_t m, void* dst,
+                    void* stream);
+
+/* ---- LSA: whitening and the fused Gaussian-KDE log-sum-exp ---------------------------
+ * out[m x d_out] (fp32) = (x[:, cols] - mu) . w, x: m x d_in (TIP_F32/TIP_F64), cols[d_out] the kept
+ * columns (NULL = all), mu: d_out doubles, w: d_out x d_out fp32 row-major. */
+int tip_whiten(const void* x, int dtype, int64_t m, int64_t d_in, const int32_t* cols,
+               int64_t d_out, const double* mu, const float* w, float* out, void* stream);
+
+/* q_pack / t_pack from tip_pair_prep(segments=3, scale=1, norm_coef=-0.5 on the train side).
+ * For every work item writes the partial (max_i a_ij, sum_i exp(a_ij - max)) of
+ * a_ij = <p_i, q_j> - |p_i|^2/2 over the item's span into part_max/part_sum[slot*m + row]. */
+int tip_kde_lse(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d,
+                int64_t pitch, const tip_work_item* items, int32_t n_items, float* part_max,
+                float* part_sum, void* stream);
+/* merges `slots` partials per row in ascending slot order: out_max, out_sum (fp32) */
+int tip_kde_combine(const float* part_max, const float* part_sum, int64_t m, int32_t slots,
+                    float* out_max, float* out_sum, void* stream);
+
+/* ---- bring-up / validation: plain accumulator dump of one 128 x 256 tile --------------
+ * out[128*256] (fp32) = tail-augmented dot products of q rows [0,128) with t rows [0,256). */
+int tip_pair_probe(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d,
+                   int segments, int64_t pitch, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TIP_H */

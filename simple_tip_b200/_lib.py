@@ -1,0 +1,87 @@
+"""ctypes binding of libb200tip.so (the C ABI declared in include/b200tip.h).
+
+There is no CPU fallback: if the shared library or a CUDA device is missing, every scoring
+call raises.  `symbols()` lists what include/b200tip.h declares, so the CPU test-suite can
+verify the export table without touching a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200tip.so")
+
+TIP_F32, TIP_F64, TIP_BF16, TIP_I16, TIP_I32 = 0, 1, 2, 3, 4
+ROLE_QUERY, ROLE_TRAIN = 0, 1
+RANGE_SAME_CLASS, RANGE_OTHER_CLASSES = 0, 1
+ROW_TILE, COL_TILE = 128, 256
+
+
+class WorkItem(C.Structure):
+    _fields_ = [("q_row0", C.c_int32), ("q_rows", C.c_int32), ("col0", C.c_int32), ("col1", C.c_int32),
+                ("slot", C.c_int32), ("reserved", C.c_int32)]
+
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); mirrors include/b200tip.h one to one
+_SIGNATURES = {
+    "tip_version": (C.c_int, []),
+    "tip_last_error": (C.c_char_p, []),
+    "tip_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "tip_launch_count": (C.c_uint64, []),
+    "tip_deepgini": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, _vp]),
+    "tip_kmnc": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, C.c_int, _i32, _vp, C.c_int, _vp, _vp]),
+    "tip_pair_pitch": (_i64, [_i64, C.c_int]),
+    "tip_pair_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, C.c_int, C.c_int, _f32, _f32, _vp, _vp, _vp]),
+    "tip_nn_filter": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _f32, _vp, _vp, _vp, _i32, _vp]),
+    "tip_nn_rerank": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, C.c_int,
+                                _vp, _vp, _vp, _vp, _vp]),
+    "tip_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "tip_whiten": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "tip_kde_lse": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "tip_kde_combine": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "tip_pair_probe": (C.c_int, [_vp, _i64, _vp, _i64, _i64, C.c_int, _i64, _vp, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def symbols():
+    return sorted(_SIGNATURES)
+
+
+def load() -> C.CDLL:
+    """Loads libb200tip.so; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(nvcc, sm_100a).  simple_tip_b200 has no CPU fallback.")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+class TipError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().tip_last_error().decode(errors="replace")
+        raise TipError(f"{what} failed with status {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().tip_launch_count())

@@ -1,0 +1,157 @@
+"""Gaussian KDE with the reference's covariance "stabilisation", evaluated on the GPU.
+
+Mirror of `/root/reference/src/core/stable_kde.py` (a subclass of scipy==1.4.1's
+`gaussian_kde`).  The fit is the reference's float64 host arithmetic, restated line by line:
+Scott factor n^(-1/(d+4)); `np.cov(bias=False, aweights=1/n)`; while any eigenvalue of
+cov*factor^2 is <= 0 REPLACE the diagonal by 1e-10 * 2^k, giving up past 1e-5
+(`prepare_failed` -> every density 0, stable_kde.py:55-77,99-100); inverse; Cholesky of
+2*pi*covariance (raises LinAlgError like the reference when not positive definite).
+
+evaluate() is scipy 1.4.1's `gaussian_kernel_estimate`:
+    density_j = (1/n) * (2 pi)^(-d/2) * prod(diag(W)) * sum_i exp(-|p_i - q_j|^2 / 2),
+    W = cholesky(inv_cov), p = data . W, q = x . W
+computed by libb200tip.so in the log domain (split-bf16 tensor-core dot products, fused
+online log-sum-exp) and converted back to a float64 density here, so underflow to exactly 0
+(-> LSA = +inf, surprise.py:495) happens where the reference's float64 sum underflows.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Optional
+
+import numpy as np
+
+
+class StableGaussianKDE:
+    MAX_INCREMENT = 1e-5
+
+    def __init__(self, dataset, bw_method=None, weights=None, source_columns: Optional[np.ndarray] = None):
+        if bw_method is not None or weights is not None:
+            raise NotImplementedError("only the reference's usage (scott bandwidth, uniform weights) is supported")
+        self.dataset = np.atleast_2d(np.asarray(dataset)).astype(np.float64)     # stable_kde.py:22
+        if not self.dataset.size > 1:
+            raise ValueError("`dataset` input should have multiple elements.")
+        self.d, self.n = self.dataset.shape
+        self.weights = np.ones(self.n) / self.n
+        self.neff = 1.0 / np.sum(self.weights ** 2)
+        self.source_columns = None if source_columns is None else np.asarray(source_columns, dtype=np.int32)
+        self._engine = None
+        self._compute_covariance()
+        if not self.prepare_failed:
+            self._upload()
+
+    def scotts_factor(self):
+        return np.power(self.neff, -1.0 / (self.d + 4))
+
+    covariance_factor = scotts_factor
+
+    # -- fit (host, float64) ---------------------------------------------------------------
+    def _compute_covariance(self):
+        self.factor = self.covariance_factor()
+        cov = np.atleast_2d(np.cov(self.dataset, rowvar=1, bias=False, aweights=self.weights))
+        cov = self._stabilize_covariance(cov)
+        if self.prepare_failed:
+            self._data_inv_cov = None
+            return
+        self._data_covariance = cov
+        try:
+            self._data_inv_cov = np.linalg.inv(cov)
+        except np.linalg.LinAlgError:
+            self.prepare_failed = True
+            self._data_inv_cov = None
+            return
+        self.covariance = cov * self.factor ** 2
+        self.inv_cov = self._data_inv_cov / self.factor ** 2
+        chol = np.linalg.cholesky(self.covariance * 2 * np.pi)
+        self.log_det = 2 * np.log(np.diag(chol)).sum()
+        self._norm_factor = np.sqrt(np.linalg.det(2 * np.pi * self.covariance))
+
+    def _stabilize_covariance(self, covariance):
+        increment = 1e-10
+        while np.any(np.linalg.eigh(covariance * self.factor ** 2)[0] <= 0):
+            np.fill_diagonal(covariance, increment)
+            if increment > self.MAX_INCREMENT:
+                warnings.warn("Was not able to fix numerical imprecision in covariance matrix."
+                              "Failing silently. All likelihoods will be reported as 0.")
+                self.prepare_failed = True
+                return None
+            increment += increment
+        self.prepare_failed = False
+        return covariance
+
+    # -- device state ----------------------------------------------------------------------
+    def _upload(self):
+        import torch
+
+        from .. import engine as E
+
+        self.whitening = np.linalg.cholesky(self.inv_cov)                 # scipy 1.4.1: cholesky(precision)
+        self.mean = self.dataset.mean(axis=1)
+        norm = math.pow(2 * math.pi, -self.d / 2.0)
+        for i in range(self.d):
+            norm *= self.whitening[i, i]
+        self.norm = norm
+        self.log_norm = -self.d / 2.0 * math.log(2 * math.pi) + float(np.sum(np.log(np.diag(self.whitening))))
+        # squared distances are translation invariant: centre before whitening so the split-bf16
+        # operands carry the spread, not the offset, of the traces
+        p = (self.dataset.T - self.mean) @ self.whitening
+        self._engine = E.KdeEngine(p)
+        dev = self._engine.dev
+        self._w_dev = torch.from_numpy(self.whitening.astype(np.float32)).to(dev)
+        self._mu_dev = torch.from_numpy(self.mean).to(dev)
+        self._cols_dev = None if self.source_columns is None else torch.from_numpy(self.source_columns).to(dev)
+
+    # -- score -----------------------------------------------------------------------------
+    def evaluate(self, points) -> np.ndarray:
+        """scipy convention: points is (d, m) (or (d,) for one point)."""
+        points = np.atleast_2d(np.asarray(points))
+        d, m = points.shape
+        if d != self.d:
+            if d == 1 and m == self.d:
+                points = np.reshape(points, (self.d, 1))
+                m = 1
+            else:
+                raise ValueError(f"points have dimension {d}, dataset has dimension {self.d}")
+        if self.prepare_failed:
+            return np.zeros(m)
+        return self._density(np.ascontiguousarray(points.T), preselected=True)
+
+    __call__ = evaluate
+
+    def evaluate_rows(self, rows: np.ndarray) -> np.ndarray:
+        """rows: (m, all source columns); the kept columns are gathered on the GPU."""
+        if self.prepare_failed:
+            return np.zeros(rows.shape[0])
+        return self._density(rows, preselected=self.source_columns is None)
+
+    def _density(self, rows: np.ndarray, preselected: bool) -> np.ndarray:
+        import torch
+
+        from .. import engine as E
+
+        eng = self._engine
+        if rows.dtype not in (np.float32, np.float64):
+            rows = rows.astype(np.float64)
+        m = rows.shape[0]
+        if m == 0:
+            return np.zeros(0)
+        x = E.to_device(rows, eng.dev)
+        q = E.whiten(x, None if preselected else self._cols_dev, self._mu_dev, self._w_dev)
+        mx, sm, qsq = eng.log_kernel_sum(q)
+        mx = mx.to(torch.float64) - 0.5 * qsq.to(torch.float64)
+        packed = torch.stack([mx, sm.to(torch.float64)]).cpu().numpy()
+        return self._finish(packed[0], packed[1])
+
+    def _finish(self, log_max: np.ndarray, rel_sum: np.ndarray) -> np.ndarray:
+        """float64 density from the log-domain partials, with the reference's underflow:
+        in gaussian_kernel_estimate every term is fl(fl(exp(-arg/2)*norm)*w); if the largest
+        term is 0 all are, and the density is exactly 0."""
+        weight = 1.0 / self.n
+        with np.errstate(under="ignore", divide="ignore", invalid="ignore"):
+            log_density = self.log_norm + math.log(weight) + log_max + np.log(rel_sum)
+            density = np.exp(log_density)
+            largest_term = (np.exp(log_max) * self.norm) * weight
+        density[largest_term == 0] = 0.0
+        density[~np.isfinite(log_max)] = 0.0
+        return density

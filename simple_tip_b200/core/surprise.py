@@ -1,0 +1,378 @@
+"""Surprise adequacies behind the reference's `src.core.surprise` API, scored on a B200.
+
+Drop-in for `/root/reference/src/core/surprise.py`: same class names, constructor = fit,
+`__call__` = score, same argument meaning, same assertion / error messages
+(tests/test_surprise.py of the reference runs against this module through the `src/core`
+overlay).  The pair arithmetic of DSA and LSA runs in libb200tip.so (tcgen05 filter + exact
+re-rank, fused KDE log-sum-exp); everything that decides WHICH rows are compared (flattening,
+label validation, seeded sub-sampling, class grouping, column selection, the float64 KDE fit)
+stays host NumPy with the reference's expressions.  `fit` / `score` are additive aliases.
+"""
+from __future__ import annotations
+
+import abc
+import math
+import os
+import warnings
+from concurrent.futures import ThreadPoolExecutor
+from typing import Callable, Dict, Iterable, List, Optional, Tuple, Union
+
+import numpy as np
+
+from .stable_kde import StableGaussianKDE
+
+Activations = Union[List[np.ndarray], np.ndarray]
+Predictions = Union[List[Union[int, float]], np.ndarray]
+Discriminator = Callable[[Activations, Predictions], np.ndarray]
+
+
+# ------------------------------------------------------------------------------------------
+# input normalisation (reference: surprise.py:55-87, 136-183) — host side, bit-for-bit
+# ------------------------------------------------------------------------------------------
+def _subsample_arrays(subsampling: Union[int, float], arrays: Tuple[np.ndarray, ...], seed: int
+                      ) -> Tuple[np.ndarray, ...]:
+    """Same rows for every array; `RandomState(seed).choice(arange(n), k, replace=False)`
+    exactly as surprise.py:84-86 so that the SAME training rows enter the kernel."""
+    n = arrays[0].shape[0]
+    assert all(a.shape[0] == n for a in arrays), "All arrays must have the same number of samples"
+    if subsampling == 1.0:
+        return arrays
+    if isinstance(subsampling, int) and subsampling > 0:
+        k = min(subsampling, n)
+    elif 0 < subsampling < 1:
+        k = int(subsampling * n)
+    else:
+        raise ValueError(
+            "subsampling must be a float between 0 and 1 (share of training data),"
+            "or a positive int declaring the number of samples")
+    picked = np.random.RandomState(seed).choice(np.arange(n), k, replace=False)
+    return tuple(a[picked] for a in arrays)
+
+
+def _subsample_array(subsampling, array: np.ndarray, seed: int) -> np.ndarray:
+    return _subsample_arrays(subsampling, (array,), seed=seed)[0]
+
+
+def _class_predictions(predictions: Predictions, num_classes: int = None) -> np.ndarray:
+    """1-D integer class ids; messages pinned by the reference's tests/test_surprise.py:33-45."""
+    if isinstance(predictions, list):
+        predictions = np.array(predictions)
+    assert predictions.ndim == 1, (
+        "Class predictions must be one-dimensional. "
+        "If your predictions are one_hot encoded, use eg `np.argmax(softmax_outputs, axis=1)`")
+    if predictions.dtype != np.dtype(int):
+        np.testing.assert_almost_equal(predictions, predictions.astype(int), decimal=5,
+                                       err_msg="Predictions must be integers")
+        predictions = predictions.astype(int)
+    assert np.all(predictions >= 0), "Class predictions must be >= 0"
+    assert num_classes is None or np.all(predictions < num_classes), "Class predictions must be < num_classes"
+    return predictions
+
+
+def _flatten_layers(layers: Activations) -> np.ndarray:
+    if isinstance(layers, np.ndarray):
+        return layers if layers.ndim == 2 else layers.reshape((layers.shape[0], -1))
+    return np.concatenate([np.reshape(l, (l.shape[0], -1)) for l in layers], axis=1)
+
+
+def _flatten_predictions(predictions: Predictions) -> Optional[np.ndarray]:
+    if predictions is None:
+        return None
+    return predictions if isinstance(predictions, np.ndarray) else np.array(predictions)
+
+
+def _by_class_discriminator(activations: Activations, predictions: Predictions) -> np.ndarray:
+    return _class_predictions(predictions)
+
+
+class _KmeansDiscriminator:
+    """k-means modal assignment with silhouette model selection (surprise.py:102-133);
+    sklearn on the host — outside the accelerated path."""
+
+    def __init__(self, training_data: Activations, potential_k: Iterable[int], subsampling=1.0,
+                 subsampling_seed: int = 0, n_init: int = 10, max_iter: int = 300):
+        from sklearn.cluster import KMeans
+        from sklearn.metrics import silhouette_score
+
+        data = _subsample_array(subsampling, _flatten_layers(training_data), seed=subsampling_seed)
+        self.best_score, self.best_k, self.best_clusterer = -np.inf, None, None
+        for k in potential_k:
+            km = KMeans(n_clusters=k, n_init=n_init, max_iter=max_iter)
+            score = silhouette_score(data, km.fit_predict(data))
+            if score > self.best_score:
+                self.best_score, self.best_k, self.best_clusterer = score, k, km
+
+    def __call__(self, activations: Activations, predictions: Predictions) -> np.ndarray:
+        return self.best_clusterer.predict(_flatten_layers(activations))
+
+
+class SurpriseCoverageMapper:
+    """SA value -> one-hot bucket profile over [0, upper_bound] (surprise.py:186-209)."""
+
+    def __init__(self, sections: int, upper_bound: float, overflow_bucket: bool = False):
+        self.sections, self.upper_bound = sections, upper_bound
+        edges = np.linspace(start=0, stop=upper_bound, num=sections if overflow_bucket else sections + 1,
+                            dtype=np.float64)
+        self.thresholds = np.concatenate((edges, [np.inf])) if overflow_bucket else edges
+
+    def get_coverage_profile(self, surprise_values: np.ndarray) -> np.ndarray:
+        lo, hi = self.thresholds[:-1], self.thresholds[1:]
+        v = np.asarray(surprise_values)[..., None]
+        return np.logical_and(lo <= v, v < hi)
+
+
+class SA(abc.ABC):
+    def __init__(self):
+        super().__init__()
+
+    @abc.abstractmethod
+    def __call__(self, activations: Activations, predictions: Predictions, num_threads: int = 1) -> np.ndarray:
+        ...
+
+    def score(self, activations, predictions=None, **kw) -> np.ndarray:
+        return self(activations, predictions, **kw)
+
+    @classmethod
+    def fit(cls, *args, **kw):
+        return cls(*args, **kw)
+
+
+class MultiModalSA(SA):
+    """Routes every sample to the SA of its modal (surprise.py:226-371)."""
+
+    def __init__(self, discriminator: Discriminator, modal_sa: Dict[int, SA]):
+        super().__init__()
+        self.discriminator, self.modal_sa = discriminator, modal_sa
+
+    @staticmethod
+    def build_by_class(activations, predictions, sa_constructor) -> "MultiModalSA":
+        return MultiModalSA.build(activations, predictions, _by_class_discriminator, sa_constructor)
+
+    @staticmethod
+    def build_with_kmeans(activations, predictions, sa_constructor, potential_k: Iterable[int], n_init: int = 10,
+                          max_iter: int = 300, subsampling=1.0, subsampling_seed: int = 0) -> "MultiModalSA":
+        disc = _KmeansDiscriminator(activations, potential_k, n_init=n_init, max_iter=max_iter,
+                                    subsampling=subsampling, subsampling_seed=subsampling_seed)
+        return MultiModalSA.build(activations, predictions, disc, sa_constructor)
+
+    @staticmethod
+    def build(activations, predictions, discriminator: Discriminator, sa_constructor) -> "MultiModalSA":
+        acts = _flatten_layers(activations)
+        preds = _flatten_predictions(predictions)
+        modal = discriminator(acts, preds)
+        fitted: Dict[int, SA] = {}
+        for mid in np.unique(modal):
+            rows = modal == mid
+            fitted[mid] = sa_constructor(acts[rows], None if preds is None else preds[rows])
+        return MultiModalSA(discriminator=discriminator, modal_sa=fitted)
+
+    def _get_sa_for_modal_id(self, modal_id: int) -> SA:
+        try:
+            return self.modal_sa[modal_id]
+        except KeyError:
+            raise ValueError(f"No modal found for modal id {modal_id}. Check your discriminator")
+
+    def __call__(self, activations, predictions, num_threads: int = 1) -> np.ndarray:
+        modal = self.discriminator(activations, predictions)
+        acts = _flatten_layers(activations)
+        preds = _flatten_predictions(predictions)
+        assert len(modal) == acts.shape[0], (
+            f"The discriminator returned an invalid number ({len(modal)}) of modal indexes."
+            f"Expected: {acts.shape[0]} indexes.")
+        if len(modal) == 0:
+            return np.ndarray(shape=(0,))
+        present = np.unique(modal)
+        # One CUDA stream serves all modals; the per-modal calls are issued in order (the
+        # reference's thread pool, surprise.py:345, only overlapped CPU work).
+        per_modal = []
+        for mid in present:
+            sa = self._get_sa_for_modal_id(mid)
+            rows = modal == mid
+            per_modal.append(sa(acts[rows], None if preds is None else preds[rows], num_threads=num_threads))
+        res = np.full(fill_value=-np.inf, shape=modal.shape, dtype=per_modal[0].dtype)
+        for mid, vals in zip(present, per_modal):
+            res[modal == mid] = vals
+        return res
+
+
+class MDSA(SA):
+    """Mahalanobis distance (surprise.py:374-393): sklearn call, host."""
+
+    def __init__(self, activations: Activations):
+        super().__init__()
+        from sklearn.covariance import EmpiricalCovariance
+
+        self.covariance_matrix = EmpiricalCovariance()
+        self.covariance_matrix.fit(_flatten_layers(activations))
+
+    def __call__(self, activations, predictions=None, num_threads=None) -> np.ndarray:
+        return self.covariance_matrix.mahalanobis(_flatten_layers(activations))
+
+
+class MLSA(SA):
+    """GMM negative log-likelihood (surprise.py:498-520): sklearn call, host."""
+
+    def __init__(self, activations: Activations, num_components: int = 2):
+        super().__init__()
+        from sklearn.mixture import GaussianMixture
+
+        self.gmm = GaussianMixture(n_components=num_components)
+        self.gmm.fit(_flatten_layers(activations))
+
+    def __call__(self, activations, predictions=None, num_threads=0) -> np.ndarray:
+        return -self.gmm.score_samples(_flatten_layers(activations))
+
+
+# ------------------------------------------------------------------------------------------
+# LSA
+# ------------------------------------------------------------------------------------------
+class LSA(SA):
+    """Likelihood-based surprise adequacy (surprise.py:396-495).
+
+    fit: highest-variance column selection (:417-434) and the float64 KDE fit of
+    `StableGaussianKDE` on the host; score: whitening + fused Gaussian-KDE log-sum-exp on the
+    GPU, then `-np.log(density)` (:494-495; +inf where the float64 density underflows to 0)."""
+
+    def __init__(self, activations: Activations, var_threshold: Optional[float] = None,
+                 max_features: Optional[Union[int, float]] = 300):
+        super().__init__()
+        activations = _flatten_layers(activations)
+        assert var_threshold is None or max_features is None, (
+            "Both var_threshold and max_features cannot be specified at the same time."
+            "We recommend using the max_features arg to dynamically keep the features"
+            "with the highest variance.")
+        self.removed_neurons: List[int]
+        if var_threshold is not None and var_threshold > 0:
+            self.removed_neurons = np.where(np.var(activations, axis=0) < var_threshold)[0]
+        if max_features is not None:
+            width = activations.shape[1]
+            keep = min(max_features * width, width) if max_features < 1 else min(max_features, width)
+            self.removed_neurons = [int(c) for c in np.argsort(np.var(activations, axis=0))[:-keep]]
+        self.kde = self._create_gaussian_kde(activations)
+
+    def _create_gaussian_kde(self, activations: np.ndarray):
+        cleaned = self._remove_unused_columns(activations)
+        if cleaned.shape[1] == 0:
+            warnings.warn("All activation traces were removed (variance filter); this LSA instance "
+                          "will always report density 0", UserWarning)
+            self.kde = None
+            return None
+        try:
+            kept = np.delete(np.arange(activations.shape[1]), self.removed_neurons) \
+                if len(self.removed_neurons) > 0 else None
+            return StableGaussianKDE(cleaned.transpose(), source_columns=kept)
+        except (np.linalg.LinAlgError, ValueError) as e:
+            # surprise.py:456-476: only two message patterns trigger drop-a-neuron-and-retry;
+            # NumPy's "Matrix is not positive definite" matches neither, so this re-raises.
+            import re
+
+            text = str(e)
+            if ("-th leading minor of the array is not positive definite" in text
+                    or "numerical imprecision in covariance matrix" in text):
+                bad_row = int(re.findall("\\d*", text)[0]) - 1
+                bad = np.delete(np.arange(activations.shape[1]), self.removed_neurons)[bad_row]
+                warnings.warn(f"Dropping AT {bad}, as leading to numerical error.", UserWarning, 1)
+                self.removed_neurons.append(bad)
+                return self._create_gaussian_kde(activations)
+            warnings.warn("Problem regarding KDE fitting", UserWarning)
+            raise e
+
+    def _remove_unused_columns(self, tr_activations):
+        if self.removed_neurons is not None and len(self.removed_neurons) > 0:
+            return np.delete(tr_activations, self.removed_neurons, axis=1)
+        return tr_activations
+
+    def __call__(self, activations, predictions=None, num_threads: int = 0) -> np.ndarray:
+        activations = _flatten_layers(activations)
+        if self.kde is None:
+            return np.zeros(shape=(activations.shape[0],))
+        # column removal happens on the GPU (the kde knows which source columns it was fitted on)
+        density = self.kde.evaluate_rows(activations)
+        with np.errstate(divide="ignore"):
+            return -np.log(density)
+
+
+# ------------------------------------------------------------------------------------------
+# DSA
+# ------------------------------------------------------------------------------------------
+class DSA(SA):
+    """Distance-based surprise adequacy (surprise.py:523-691).
+
+    dsa = dist_a / dist_b with dist_a the distance from the test trace to the nearest training
+    trace of its predicted class and dist_b the distance from THAT TRAINING TRACE to the nearest
+    training trace of any other class (surprise.py:615-631).  Distances and the winner are
+    bit-identical to the reference's NumPy (`np.linalg.norm(axis=2)`, `np.argmin`)."""
+
+    def __init__(self, activations: Activations, predictions: Predictions, badge_size: int = 10,
+                 subsampling: Union[int, float] = 1.0, subsampling_seed: int = 0, *, comm=None):
+        super().__init__()
+        self.train_activations: np.ndarray = _flatten_layers(activations)
+        self.train_predictions: np.ndarray = _class_predictions(predictions)
+        self.train_activations, self.train_predictions = _subsample_arrays(
+            subsampling, (self.train_activations, self.train_predictions), subsampling_seed)
+        self.num_classes = np.max(self.train_predictions) + 1
+        self.class_matrix = self._class_matrix()
+        self.badge_size = badge_size          # kept for API compatibility; tiles replace badges
+        self.use_filter = os.environ.get("B200TIP_DSA_EXHAUSTIVE", "0") != "1"
+        self._comm = comm
+        self._engine = None
+        self._build_engine()
+
+    def _class_matrix(self) -> List[np.ndarray]:
+        return [np.argwhere(self.train_predictions == c).flatten() for c in range(self.num_classes)]
+
+    def _build_engine(self):
+        from .. import engine as E
+
+        train = self.train_activations
+        if train.dtype not in (np.float32, np.float64):
+            train = train.astype(np.result_type(train.dtype, np.float32))
+        self._compute_dtype = train.dtype
+        labels = self.train_predictions
+        gids = np.arange(train.shape[0])
+        if self._comm is not None and self._comm.world > 1:
+            keep = E.shard_rows(labels, int(self.num_classes), self._comm.rank, self._comm.world)
+            train, labels, gids = train[keep], labels[keep], gids[keep]
+        self._engine = E.NnEngine.from_host(train, labels, int(self.num_classes), gids)
+
+    def __call__(self, activations: Activations, predictions: Predictions, num_threads: int = None) -> np.ndarray:
+        import torch
+
+        from .. import engine as E
+
+        target_pred = _class_predictions(predictions)
+        target_ats = _flatten_layers(activations)
+        if target_ats.dtype != self._compute_dtype:
+            target_ats = target_ats.astype(np.result_type(target_ats.dtype, self._compute_dtype))
+            if target_ats.dtype != self._compute_dtype:
+                raise TypeError("test traces need the dtype of the training traces "
+                                f"({self._compute_dtype}), got {target_ats.dtype}")
+        eng = self._engine
+        # class-grouped order; rows labelled >= num_classes are never scored by the reference
+        # (its result buffer is np.empty there, surprise.py:576-580) -> NaN here.
+        order, q_off = E.class_layout(target_pred, int(self.num_classes))
+        for c in range(int(self.num_classes)):
+            if q_off[c + 1] > q_off[c]:
+                if len(self.class_matrix[c]) == 0:
+                    raise ValueError("zero-size array to reduction operation minimum which has no identity")
+                if len(self.class_matrix[c]) == self.train_predictions.shape[0]:
+                    raise ValueError("zero-size array to reduction operation minimum which has no identity")
+        dsa = np.full(shape=target_pred.shape[0], fill_value=np.nan)
+        if order.size == 0:
+            return dsa
+        dev = eng.dev
+        x_all = E.to_device(target_ats, dev)
+        idx = torch.from_numpy(order).to(dev, non_blocking=True)
+        x = x_all.index_select(0, idx)
+        q_class = torch.from_numpy(target_pred[order].astype(np.int32)).to(dev, non_blocking=True)
+        dist_a, dist_b, gid = E.dsa_distances(eng, x, q_class, q_off, self._comm, self.use_filter)
+        a = dist_a.cpu().numpy()
+        b = dist_b.cpu().numpy()
+        self.last_winner_index = np.full(target_pred.shape[0], -1, dtype=np.int64)
+        self.last_winner_index[order] = gid.cpu().numpy()
+        self.last_dist_a = np.full(target_pred.shape[0], np.nan, dtype=a.dtype)
+        self.last_dist_b = np.full(target_pred.shape[0], np.nan, dtype=a.dtype)
+        self.last_dist_a[order], self.last_dist_b[order] = a, b
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dsa[order] = a / b                 # input dtype, widened on store (surprise.py:595,611)
+        return dsa

@@ -1,0 +1,141 @@
+// common.cuh — shared helpers for libb200tip.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200tip.h"
+
+namespace tip {
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define TIP_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      tip::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return TIP_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define TIP_REQUIRE(cond, msg)                                                            \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      tip::set_error("%s:%d invalid argument: %s (%s)", __FILE__, __LINE__, msg, #cond);  \
+      return TIP_ERR_INVALID;                                                             \
+    }                                                                                     \
+  } while (0)
+
+#define TIP_LAUNCH_CHECK()                                                                \
+  do {                                                                                    \
+    tip::count_launch();                                                                  \
+    TIP_CHECK_CUDA(cudaGetLastError());                                                   \
+  } while (0)
+
+int sm_count();
+
+// ---- IEEE arithmetic without FMA contraction (NumPy never fuses) --------------------------
+template <typename T> struct Rn;
+template <> struct Rn<float> {
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <> struct Rn<double> {
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+  static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+
+// One leaf (n <= 128) of NumPy's pairwise summation applied to (x-y)^2 (or x^2 if y == nullptr):
+// n < 8 sequential from 0; else eight stride-8 accumulators, tree-combined, tail sequential.
+template <typename T>
+__device__ __forceinline__ T np_leaf_sumsq(const T* __restrict__ x, const T* __restrict__ y, int n) {
+  using R = Rn<T>;
+  auto term = [&](int i) -> T {
+    T d = y ? R::sub(x[i], y[i]) : x[i];
+    return R::mul(d, d);
+  };
+  if (n < 8) {
+    T res = (T)0;
+    for (int i = 0; i < n; i++) res = R::add(res, term(i));
+    return res;
+  }
+  T r0 = term(0), r1 = term(1), r2 = term(2), r3 = term(3);
+  T r4 = term(4), r5 = term(5), r6 = term(6), r7 = term(7);
+  int i = 8;
+  const int lim = n - (n % 8);
+  for (; i < lim; i += 8) {
+    r0 = R::add(r0, term(i + 0));
+    r1 = R::add(r1, term(i + 1));
+    r2 = R::add(r2, term(i + 2));
+    r3 = R::add(r3, term(i + 3));
+    r4 = R::add(r4, term(i + 4));
+    r5 = R::add(r5, term(i + 5));
+    r6 = R::add(r6, term(i + 6));
+    r7 = R::add(r7, term(i + 7));
+  }
+  T res = R::add(R::add(R::add(r0, r1), R::add(r2, r3)), R::add(R::add(r4, r5), R::add(r6, r7)));
+  for (; i < n; i++) res = R::add(res, term(i));
+  return res;
+}
+
+// Full NumPy pairwise sum of (x-y)^2 over n elements: blocks > 128 are split at
+// n2 = n/2 - (n/2)%8 recursively; done here with an explicit stack (depth <= 32).
+template <typename T>
+__device__ T np_sumsq(const T* __restrict__ x, const T* __restrict__ y, int n) {
+  if (n <= 128) return np_leaf_sumsq<T>(x, y, n);
+  int off[32], len[32];
+  unsigned char phase[32];
+  T vals[32];
+  int sp = 0, vp = 0;
+  off[0] = 0; len[0] = n; phase[0] = 0; sp = 1;
+  while (sp > 0) {
+    const int top = sp - 1;
+    const int o = off[top], l = len[top];
+    if (l <= 128) {
+      vals[vp++] = np_leaf_sumsq<T>(x + o, y ? y + o : nullptr, l);
+      sp--;
+    } else {
+      int n2 = l / 2;
+      n2 -= n2 % 8;
+      if (phase[top] == 0) {
+        phase[top] = 1;
+        off[sp] = o; len[sp] = n2; phase[sp] = 0; sp++;
+      } else if (phase[top] == 1) {
+        phase[top] = 2;
+        off[sp] = o + n2; len[sp] = l - n2; phase[sp] = 0; sp++;
+      } else {
+        const T r = vals[--vp];
+        const T lft = vals[--vp];
+        vals[vp++] = Rn<T>::add(lft, r);
+        sp--;
+      }
+    }
+  }
+  return vals[0];
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace tip

@@ -1,0 +1,480 @@
+// pair_tc.cu — the tensor-core pass over (query, train) activation-trace pairs (sm_100a).
+//
+// One persistent, warp-specialised kernel computes, for 128 query rows x 256 train rows at a
+// time, the fp32 accumulator
+//        acc[i][j] = norm_coef*|y_j|^2 + scale*<x_i, y_j>
+// (both terms come out of the same tcgen05.mma K-loop: the packed operands carry a 16-wide tail
+// block with a 3-way bf16 split of the norm on the train side and ones on the query side, see
+// tip_pair_prep) and reduces it on the fly — no N_test x N_train intermediate ever leaves the SM:
+//   MODE_NN   per-row running minimum + candidate emission (DSA, surprise.py:638-647)
+//   MODE_LSE  per-row online log-sum-exp (LSA / Gaussian KDE, scipy 1.4.1 gaussian_kernel_estimate)
+//   MODE_DUMP raw accumulator tile (bring-up / validation)
+//
+// Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one
+// lane), warps 2..5 = epilogue (TMEM lane quadrant = warp % 4, one query row per thread).
+// Pipelines: 4-stage smem ring (full/empty mbarriers, TMA -> MMA) and a 2-deep TMEM accumulator
+// ring (2 x 256 columns, MMA -> epilogue).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include "common.cuh"
+
+namespace tip {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // bf16 elements per smem row = one 128-byte swizzle atom
+constexpr int kStages = 4;
+constexpr int kABytes = BM * BK * 2;
+constexpr int kBBytes = BN * BK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kThreads = 192;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t kTmemCols = 512;
+
+enum { MODE_NN = 0, MODE_LSE = 1, MODE_DUMP = 2 };
+
+struct PairArgs {
+  const tip_work_item* items;
+  int n_items;
+  int k16;  // number of K=16 MMA steps per tile (packed width / 16)
+  int64_t m;
+  // MODE_NN
+  const float* q_sqnorm;
+  float rmax, eps2, gamma;  // error-window constants
+  uint32_t* row_min_bits;
+  int32_t* cand_idx;
+  int32_t* cand_cnt;
+  int cap;
+  // MODE_LSE
+  float* part_max;
+  float* part_sum;
+  // MODE_DUMP
+  float* dump;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > 200000000u) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO=1<<16 | SBO=64<<32 | version=1<<46 | SWIZZLE_128B=2<<61).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// Acceptance threshold (accumulator space) for a query whose smallest approximate squared
+// distance so far is s: every train row whose exact NumPy distance could still be the minimum
+// has acc <= thr.  r = |x_b| + max|y_b|, e2 = 2*eps'*r, g = gamma*r^2.
+__device__ __forceinline__ float nn_threshold(float s, float nx, float e2, float g) {
+  float r = sqrtf(s + g) + e2;
+  r *= 1.00004f;
+  float thr = fmaf(r, r, g) - nx;
+  return thr + fabsf(thr) * 1e-6f + 1e-30f;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PairArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar0 = base + kStages * kStageBytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kStages + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int k16 = args.k16;
+  const int nchunks = (k16 + 3) >> 2;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+        const tip_work_item it = args.items[w];
+        const int ntiles = (it.col1 - it.col0 + BN - 1) / BN;
+        for (int t = 0; t < ntiles; t++) {
+          for (int c = 0; c < nchunks; c++) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), kStageBytes);
+            const uint32_t a_dst = base + stage * kStageBytes;
+            tma_load_2d(a_dst, &tmA, full_bar(stage), c * BK, it.q_row0);
+            tma_load_2d(a_dst + kABytes, &tmB, full_bar(stage), c * BK, it.col0 + t * BN);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+        const tip_work_item it = args.items[w];
+        const int ntiles = (it.col1 - it.col0 + BN - 1) / BN;
+        for (int t = 0; t < ntiles; t++) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+          for (int c = 0; c < nchunks; c++) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_addr = base + stage * kStageBytes;
+            const uint64_t adesc = smem_desc(a_addr);
+            const uint64_t bdesc = smem_desc(a_addr + kABytes);
+            const int nm = min(4, k16 - 4 * c);
+            for (int k = 0; k < nm; k++) {
+              // +32 bytes (one K=16 slice) inside the 128-byte swizzle row = +2 in the >>4 field
+              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, (uint32_t)((c | k) != 0));
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(tfull_bar(acc));
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (one query row per thread) =================
+    const int quad = warp & 3;
+    const int row_local = quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const float kInf = __int_as_float(0x7f800000);
+    for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+      const tip_work_item it = args.items[w];
+      const int ntiles = (it.col1 - it.col0 + BN - 1) / BN;
+      const bool valid_row = row_local < it.q_rows;
+      const int64_t row = (int64_t)it.q_row0 + row_local;
+
+      // ---- per-item state ----
+      float nx = 0.f, e2 = 0.f, g = 0.f, best = kInf, thr = kInf;  // MODE_NN
+      float run_max = -kInf, run_sum = 0.f;                          // MODE_LSE
+      if (MODE == MODE_NN && valid_row) {
+        nx = args.q_sqnorm[row];
+        const float r = sqrtf(nx) + args.rmax;
+        e2 = args.eps2 * r;
+        g = args.gamma * r * r;
+        const float s0 = __uint_as_float(*(volatile uint32_t*)(args.row_min_bits + row));
+        thr = nn_threshold(s0, nx, e2, g);
+      }
+
+      for (int t = 0; t < ntiles; t++) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const int tile_col0 = it.col0 + t * BN;
+        const bool partial = tile_col0 + BN > it.col1;
+#pragma unroll 1
+        for (int qd = 0; qd < BN / 32; qd++) {
+          uint32_t r[32];
+          tmem_ld32(lane_addr + (uint32_t)(acc * BN + qd * 32), r);
+          tmem_wait_ld();
+          const int cbase = tile_col0 + qd * 32;
+          if (MODE == MODE_DUMP) {
+            if (w == 0 && t == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) args.dump[(int64_t)row_local * BN + qd * 32 + j] = __uint_as_float(r[j]);
+            }
+          } else if (MODE == MODE_NN) {
+            float mn = kInf;
+            if (partial) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                const float v = (cbase + j < it.col1) ? __uint_as_float(r[j]) : kInf;
+                r[j] = __float_as_uint(v);
+                mn = fminf(mn, v);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) mn = fminf(mn, fminf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+            }
+            if (valid_row && mn <= thr) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                const float v = __uint_as_float(r[j]);
+                if (v <= thr) {
+                  const int pos = atomicAdd(args.cand_cnt + row, 1);
+                  if (pos < args.cap) args.cand_idx[row * args.cap + pos] = cbase + j;
+                  if (v < best) {
+                    best = v;
+                    thr = nn_threshold(fmaxf(best + nx, 0.f), nx, e2, g);
+                  }
+                }
+              }
+            }
+          } else {  // MODE_LSE
+            constexpr float kL2e = 1.4426950408889634f;
+            float mx = -kInf;
+            if (partial) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                const float v = (cbase + j < it.col1) ? __uint_as_float(r[j]) : -kInf;
+                r[j] = __float_as_uint(v);
+                mx = fmaxf(mx, v);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+            }
+            if (mx > run_max) {
+              run_sum *= exp2f((run_max - mx) * kL2e);  // run_max = -inf -> factor 0
+              run_max = mx;
+            }
+            if (run_max > -kInf) {
+              const float off = -run_max * kL2e;
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                s0 += exp2f(fmaf(__uint_as_float(r[j + 0]), kL2e, off));
+                s1 += exp2f(fmaf(__uint_as_float(r[j + 1]), kL2e, off));
+                s2 += exp2f(fmaf(__uint_as_float(r[j + 2]), kL2e, off));
+                s3 += exp2f(fmaf(__uint_as_float(r[j + 3]), kL2e, off));
+              }
+              run_sum += (s0 + s1) + (s2 + s3);
+            }
+          }
+        }
+        // accumulator drained: hand the TMEM stage back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+
+      if (MODE == MODE_NN) {
+        if (valid_row && best < kInf)
+          atomicMin(args.row_min_bits + row, __float_as_uint(fmaxf(best + nx, 0.f)));
+      } else if (MODE == MODE_LSE) {
+        if (valid_row) {
+          args.part_max[(int64_t)it.slot * args.m + row] = run_max;
+          args.part_sum[(int64_t)it.slot * args.m + row] = run_sum;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* basep, int64_t rows, int64_t pitch, int box_rows) {
+  auto fn = get_encode();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return TIP_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(basep), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return TIP_ERR_CUDA; }
+  return TIP_OK;
+}
+
+static int check_device() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      set_error("no CUDA device");
+      return TIP_ERR_CUDA;
+    }
+    ok = (major == 10) ? 1 : 0;
+  }
+  if (!ok) { set_error("libb200tip tensor-core kernels need an sm_100 device"); return TIP_ERR_UNSUPPORTED; }
+  return TIP_OK;
+}
+
+template <int MODE>
+static int launch_pair(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t pitch, PairArgs args,
+                       cudaStream_t st) {
+  int rc = check_device();
+  if (rc != TIP_OK) return rc;
+  TIP_REQUIRE(((uintptr_t)q_pack & 127) == 0 && ((uintptr_t)t_pack & 127) == 0, "packed operands must be 128-byte aligned");
+  TIP_REQUIRE(pitch % 64 == 0 && args.k16 * 16 <= pitch, "pitch");
+  TIP_REQUIRE(m >= 1 && n >= 1 && m < (1LL << 31) && n < (1LL << 31), "shape");
+  CUtensorMap ma, mb;
+  rc = make_map(&ma, q_pack, m, pitch, BM);
+  if (rc != TIP_OK) return rc;
+  rc = make_map(&mb, t_pack, n, pitch, BN);
+  if (rc != TIP_OK) return rc;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[MODE]) {
+    TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set[MODE] = true;
+  }
+  const int grid = min(args.n_items, sm_count());
+  pair_kernel<MODE><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, args);
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
+}
+
+static int k16_of(int64_t d, int segments) {
+  const int64_t d16 = (d + 15) & ~(int64_t)15;
+  return (int)((segments * d16 + 16) / 16);
+}
+
+}  // namespace tip
+
+using namespace tip;
+
+extern "C" int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const void* t_pack, int64_t n,
+                             int64_t d, int64_t pitch, const tip_work_item* items, int32_t n_items, float t_rmax,
+                             uint32_t* row_min_bits, int32_t* cand_idx, int32_t* cand_cnt, int32_t cap,
+                             void* stream) {
+  TIP_REQUIRE(q_pack && q_sqnorm && t_pack && items && row_min_bits && cand_idx && cand_cnt, "null pointer");
+  TIP_REQUIRE(cap >= 1 && n_items >= 0, "cap / n_items");
+  TIP_REQUIRE(pitch == tip_pair_pitch(d, 1), "pitch does not match tip_pair_pitch(d, 1)");
+  if (n_items == 0) return TIP_OK;
+  PairArgs a{};
+  a.items = items; a.n_items = n_items; a.k16 = k16_of(d, 1); a.m = m;
+  a.q_sqnorm = q_sqnorm; a.rmax = t_rmax;
+  // eps' = (2^-9 + 2^-23)/(1 - that): bf16 rounding of the centred traces (triangle inequality);
+  // gamma: fp32 accumulation over K products + norm rounding, assuming nothing better than
+  // truncating adds inside the tensor core.
+  a.eps2 = 2.0f * 1.96e-3f;
+  a.gamma = (float)(a.k16 * 16 + 16) * 1.1920929e-7f;
+  a.row_min_bits = row_min_bits; a.cand_idx = cand_idx; a.cand_cnt = cand_cnt; a.cap = cap;
+  return launch_pair<MODE_NN>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
+}
+
+extern "C" int tip_kde_lse(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d, int64_t pitch,
+                           const tip_work_item* items, int32_t n_items, float* part_max, float* part_sum,
+                           void* stream) {
+  TIP_REQUIRE(q_pack && t_pack && items && part_max && part_sum, "null pointer");
+  TIP_REQUIRE(pitch == tip_pair_pitch(d, 3), "pitch does not match tip_pair_pitch(d, 3)");
+  if (n_items == 0) return TIP_OK;
+  PairArgs a{};
+  a.items = items; a.n_items = n_items; a.k16 = k16_of(d, 3); a.m = m;
+  a.part_max = part_max; a.part_sum = part_sum;
+  return launch_pair<MODE_LSE>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
+}
+
+extern "C" int tip_pair_probe(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d, int segments,
+                              int64_t pitch, float* out, void* stream) {
+  TIP_REQUIRE(q_pack && t_pack && out, "null pointer");
+  TIP_REQUIRE(pitch == tip_pair_pitch(d, segments), "pitch does not match tip_pair_pitch");
+  static tip_work_item* d_item = nullptr;
+  if (!d_item) TIP_CHECK_CUDA(cudaMalloc(&d_item, sizeof(tip_work_item)));
+  tip_work_item h{0, (int32_t)std::min<int64_t>(m, BM), 0, (int32_t)std::min<int64_t>(n, BN), 0, 0};
+  TIP_CHECK_CUDA(cudaMemcpyAsync(d_item, &h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  PairArgs a{};
+  a.items = d_item; a.n_items = 1; a.k16 = k16_of(d, segments); a.m = m; a.dump = out;
+  return launch_pair<MODE_DUMP>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
+}

@@ -1,0 +1,563 @@
+// simple.cu — bandwidth-bound kernels and small utilities of libb200tip.so:
+//   DeepGini (deepgini.py:31-35), KMNC (neuron_coverage.py:65-94), operand packing for the
+//   tensor-core pass, row gather, LSA whitening, LSE partial merge, and the C-ABI basics.
+#include <stdarg.h>
+#include <algorithm>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace tip {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+// =============================================================================================
+// DeepGini
+// =============================================================================================
+// Narrow rows (c <= kGiniSmallC): a block stages 128 rows in shared memory with coalesced
+// 16-byte-agnostic loads, then one thread per row walks its row in NumPy's pairwise order.
+constexpr int kGiniRows = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(kGiniRows) gini_small_kernel(const T* __restrict__ p, int64_t n, int c,
+                                                               int32_t* __restrict__ pred,
+                                                               T* __restrict__ gini) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);
+  const int stride = c + 1;  // +1 padding: thread r reads tile[r*stride + k], conflict-free for odd strides
+  for (int64_t row0 = (int64_t)blockIdx.x * kGiniRows; row0 < n; row0 += (int64_t)gridDim.x * kGiniRows) {
+    const int rows = (int)min((int64_t)kGiniRows, n - row0);
+    const T* src = p + row0 * c;
+    const int total = rows * c;
+    for (int i = threadIdx.x; i < total; i += kGiniRows) {
+      const int r = i / c, k = i - r * c;
+      tile[r * stride + k] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < rows) {
+      const T* row = tile + threadIdx.x * stride;
+      int best = 0;
+      T bv = row[0];
+      for (int k = 1; k < c; k++) {
+        const T v = row[k];
+        if (v > bv) { bv = v; best = k; }
+      }
+      const T ss = np_sumsq<T>(row, nullptr, c);
+      pred[row0 + threadIdx.x] = best;
+      gini[row0 + threadIdx.x] = Rn<T>::sub((T)1, ss);
+    }
+    __syncthreads();
+  }
+}
+
+// Wide rows: one warp per row.  Lanes evaluate the <=128-element leaves of NumPy's pairwise
+// tree round-robin (each leaf is contiguous, so all fetched sectors are used), lane 0 then
+// combines the leaf sums in tree order.
+constexpr int kGiniMaxLeaves = 1024;
+
+template <typename T>
+__device__ int walk_leaves(int n, int lane, const T* row, T* leaf_sums, bool combine, T* result) {
+  int off[32], len[32];
+  unsigned char phase[32];
+  T vals[32];
+  int sp = 1, vp = 0, leaf = 0;
+  off[0] = 0; len[0] = n; phase[0] = 0;
+  while (sp > 0) {
+    const int top = sp - 1;
+    const int o = off[top], l = len[top];
+    if (l <= 128) {
+      if (combine) vals[vp++] = leaf_sums[leaf];
+      else if ((leaf & 31) == lane) leaf_sums[leaf] = np_leaf_sumsq<T>(row + o, nullptr, l);
+      leaf++;
+      sp--;
+    } else {
+      int n2 = l / 2;
+      n2 -= n2 % 8;
+      if (phase[top] == 0) { phase[top] = 1; off[sp] = o; len[sp] = n2; phase[sp] = 0; sp++; }
+      else if (phase[top] == 1) { phase[top] = 2; off[sp] = o + n2; len[sp] = l - n2; phase[sp] = 0; sp++; }
+      else {
+        if (combine) { const T r = vals[--vp]; const T a = vals[--vp]; vals[vp++] = Rn<T>::add(a, r); }
+        sp--;
+      }
+    }
+  }
+  if (combine) *result = vals[0];
+  return leaf;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) gini_wide_kernel(const T* __restrict__ p, int64_t n, int c,
+                                                        int32_t* __restrict__ pred, T* __restrict__ gini) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  T* leaf_sums = reinterpret_cast<T*>(smem_raw) + warp * kGiniMaxLeaves;
+  for (int64_t row = (int64_t)blockIdx.x * 4 + warp; row < n; row += (int64_t)gridDim.x * 4) {
+    const T* src = p + row * c;
+    // argmax, first occurrence
+    T bv = src[0];
+    int bi = 0;
+    for (int k = lane; k < c; k += 32) {
+      const T v = src[k];
+      if (v > bv || (v == bv && k < bi)) { bv = v; bi = k; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const T ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    T dummy;
+    walk_leaves<T>(c, lane, src, leaf_sums, false, &dummy);
+    __syncwarp();
+    if (lane == 0) {
+      T ss;
+      walk_leaves<T>(c, 0, src, leaf_sums, true, &ss);
+      pred[row] = bi;
+      gini[row] = Rn<T>::sub((T)1, ss);
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T>
+static int launch_gini(const T* p, int64_t n, int64_t c, int32_t* pred, T* gini, cudaStream_t st) {
+  const int sms = sm_count();
+  const size_t small_bytes = (size_t)kGiniRows * (size_t)(c + 1) * sizeof(T);
+  if (small_bytes <= 96 * 1024) {
+    TIP_CHECK_CUDA(cudaFuncSetAttribute(gini_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)small_bytes));
+    const int64_t blocks = (n + kGiniRows - 1) / kGiniRows;
+    const int grid = (int)std::min<int64_t>(blocks, (int64_t)sms * 8);
+    gini_small_kernel<T><<<grid, kGiniRows, small_bytes, st>>>(p, n, (int)c, pred, gini);
+  } else {
+    TIP_REQUIRE(c <= (int64_t)kGiniMaxLeaves * 64, "row too wide");
+    const size_t bytes = 4 * kGiniMaxLeaves * sizeof(T);
+    const int grid = (int)std::min<int64_t>((n + 3) / 4, (int64_t)sms * 16);
+    gini_wide_kernel<T><<<grid, 128, bytes, st>>>(p, n, (int)c, pred, gini);
+  }
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
+}
+
+// =============================================================================================
+// KMNC
+// =============================================================================================
+template <typename TA, typename TS> struct CmpType { using type = double; };
+template <> struct CmpType<float, float> { using type = float; };
+
+template <typename TA, typename TS>
+__device__ __forceinline__ int kmnc_bucket(TA a_in, TS lo, TS jump, int k) {
+  using TC = typename CmpType<TA, TS>::type;
+  using R = Rn<TS>;
+  if (!(jump > (TS)0)) return -1;  // constant / inverted / NaN range: never covered
+  const TC a = (TC)a_in;
+  auto t = [&](int i) -> TC { return (TC)R::add(lo, R::mul(jump, (TS)i)); };  // NumPy: min + jumps*i
+  if (!(a >= t(0)) || !(a < t(k))) return -1;
+  double est = ((double)a_in - (double)lo) / (double)jump;
+  int i = est >= (double)(k - 1) ? k - 1 : (est <= 0.0 ? 0 : (int)est);
+  while (i > 0 && a < t(i)) i--;
+  while (i < k - 1 && a >= t(i + 1)) i++;
+  return i;
+}
+
+template <typename TA, typename TS, typename TB>
+__global__ void __launch_bounds__(256) kmnc_kernel(const TA* __restrict__ act, int64_t n, int64_t d,
+                                                   const TS* __restrict__ mins, const TS* __restrict__ jumps,
+                                                   int k, TB* __restrict__ bucket, int32_t* __restrict__ score) {
+  __shared__ int warp_cnt[8];
+  for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
+    const TA* a = act + row * d;
+    TB* b = bucket ? bucket + row * d : nullptr;
+    int cnt = 0;
+    for (int64_t j = threadIdx.x; j < d; j += 256) {
+      const int i = kmnc_bucket<TA, TS>(a[j], mins[j], jumps[j], k);
+      cnt += (i >= 0);
+      if (b) b[j] = (TB)i;
+    }
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int s = 0;
+      for (int w = 0; w < 8; w++) s += warp_cnt[w];
+      score[row] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// float traces, float statistics, d % 4 == 0, 16-byte aligned: 128-bit loads, 64-bit stores.
+template <typename TB>
+__global__ void __launch_bounds__(256) kmnc_vec4_kernel(const float* __restrict__ act, int64_t n, int64_t d,
+                                                        const float* __restrict__ mins,
+                                                        const float* __restrict__ jumps, int k,
+                                                        TB* __restrict__ bucket, int32_t* __restrict__ score) {
+  __shared__ int warp_cnt[8];
+  const int64_t d4 = d >> 2;
+  for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
+    const float4* a4 = reinterpret_cast<const float4*>(act + row * d);
+    int cnt = 0;
+    for (int64_t j = threadIdx.x; j < d4; j += 256) {
+      float4 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "l"(a4 + j));
+      const float4 lo = __ldg(reinterpret_cast<const float4*>(mins) + j);
+      const float4 jp = __ldg(reinterpret_cast<const float4*>(jumps) + j);
+      const int i0 = kmnc_bucket<float, float>(v.x, lo.x, jp.x, k);
+      const int i1 = kmnc_bucket<float, float>(v.y, lo.y, jp.y, k);
+      const int i2 = kmnc_bucket<float, float>(v.z, lo.z, jp.z, k);
+      const int i3 = kmnc_bucket<float, float>(v.w, lo.w, jp.w, k);
+      cnt += (i0 >= 0) + (i1 >= 0) + (i2 >= 0) + (i3 >= 0);
+      if (bucket) {
+        TB* b = bucket + row * d + (j << 2);
+        if (sizeof(TB) == 2) {
+          short4 o = make_short4((short)i0, (short)i1, (short)i2, (short)i3);
+          *reinterpret_cast<short4*>(b) = o;
+        } else {
+          int4 o = make_int4(i0, i1, i2, i3);
+          *reinterpret_cast<int4*>(b) = o;
+        }
+      }
+    }
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int s = 0;
+      for (int w = 0; w < 8; w++) s += warp_cnt[w];
+      score[row] = s;
+    }
+    __syncthreads();
+  }
+}
+
+template <typename TA, typename TS>
+static int launch_kmnc(const void* act, int64_t n, int64_t d, const void* mins, const void* jumps, int k,
+                       void* bucket, int bucket_dtype, int32_t* score, cudaStream_t st) {
+  const int grid = (int)std::min<int64_t>(n, (int64_t)sm_count() * 8);
+  if (bucket == nullptr || bucket_dtype == TIP_I16) {
+    kmnc_kernel<TA, TS, int16_t><<<grid, 256, 0, st>>>((const TA*)act, n, d, (const TS*)mins, (const TS*)jumps,
+                                                       k, (int16_t*)bucket, score);
+  } else {
+    kmnc_kernel<TA, TS, int32_t><<<grid, 256, 0, st>>>((const TA*)act, n, d, (const TS*)mins, (const TS*)jumps,
+                                                       k, (int32_t*)bucket, score);
+  }
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
+}
+
+// =============================================================================================
+// Operand packing for the tensor-core pass (layout documented in b200tip.h)
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) pair_prep_kernel(const T* __restrict__ src, int64_t rows, int d,
+                                                        const float* __restrict__ center, int role,
+                                                        int segments, float scale, float norm_coef,
+                                                        __nv_bfloat16* __restrict__ dst, int64_t pitch,
+                                                        float* __restrict__ sqnorm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int d16 = (d + 15) & ~15;
+  const T* x = src + row * (int64_t)d;
+  __nv_bfloat16* out = dst + row * pitch;
+  double acc = 0.0;
+  for (int c = lane; c < d16; c += 32) {
+    float v = 0.f;
+    if (c < d) {
+      const float ctr = center ? center[c] : 0.f;
+      v = sizeof(T) == 8 ? (float)((double)x[c] - (double)ctr) : __fsub_rn((float)x[c], ctr);
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float hf = __bfloat162float(h);
+    if (segments == 1) {
+      acc += (double)hf * (double)hf;
+      out[c] = role == TIP_ROLE_TRAIN ? __float2bfloat16_rn(scale * hf) : h;
+    } else {
+      const __nv_bfloat16 l = __float2bfloat16_rn(__fsub_rn(v, hf));
+      acc += (double)v * (double)v;
+      if (role == TIP_ROLE_TRAIN) {
+        const __nv_bfloat16 sh = __float2bfloat16_rn(scale * hf);
+        out[c] = sh;
+        out[d16 + c] = sh;
+        out[2 * d16 + c] = __float2bfloat16_rn(scale * __bfloat162float(l));
+      } else {
+        out[c] = h;
+        out[d16 + c] = l;
+        out[2 * d16 + c] = h;
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  const float nrm = (float)acc;
+  const int tail = segments * d16;
+  // tail block + zero padding up to the pitch
+  for (int c = tail + lane; c < pitch; c += 32) {
+    float v = 0.f;
+    const int t = c - tail;
+    if (t < 3) {
+      if (role == TIP_ROLE_TRAIN) {
+        const float cv = norm_coef * nrm;
+        const float c0 = __bfloat162float(__float2bfloat16_rn(cv));
+        const float c1 = __bfloat162float(__float2bfloat16_rn(cv - c0));
+        const float c2 = __bfloat162float(__float2bfloat16_rn(cv - c0 - c1));
+        v = t == 0 ? c0 : (t == 1 ? c1 : c2);
+      } else {
+        v = 1.f;
+      }
+    }
+    out[c] = __float2bfloat16_rn(v);
+  }
+  if (lane == 0 && sqnorm) sqnorm[row] = nrm;
+}
+
+// =============================================================================================
+// gather / whiten / combine
+// =============================================================================================
+__global__ void __launch_bounds__(256) gather_rows_kernel(const unsigned char* __restrict__ src,
+                                                          int64_t row_bytes, const int32_t* __restrict__ pos,
+                                                          int64_t m, unsigned char* __restrict__ dst) {
+  for (int64_t row = blockIdx.x; row < m; row += gridDim.x) {
+    const int32_t p = pos[row];
+    unsigned char* o = dst + row * row_bytes;
+    if ((row_bytes & 15) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+      const int64_t n16 = row_bytes >> 4;
+      const uint4* s = reinterpret_cast<const uint4*>(src + (int64_t)(p < 0 ? 0 : p) * row_bytes);
+      uint4* o4 = reinterpret_cast<uint4*>(o);
+      for (int64_t i = threadIdx.x; i < n16; i += 256) o4[i] = p < 0 ? make_uint4(0, 0, 0, 0) : s[i];
+    } else {
+      const unsigned char* s = src + (int64_t)(p < 0 ? 0 : p) * row_bytes;
+      for (int64_t i = threadIdx.x; i < row_bytes; i += 256) o[i] = p < 0 ? 0 : s[i];
+    }
+  }
+}
+
+// out[m x dn] = (x[:, cols] - mu) . w   (fp32 FFMA, 64x64 tiles, 4x4 per thread)
+template <typename T>
+__global__ void __launch_bounds__(256) whiten_kernel(const T* __restrict__ x, int64_t m, int64_t d_in,
+                                                     const int32_t* __restrict__ cols, int dn,
+                                                     const double* __restrict__ mu, const float* __restrict__ w,
+                                                     float* __restrict__ out) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t row0 = (int64_t)blockIdx.y * 64;
+  const int col0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < dn; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, k = i & 15;
+      float v = 0.f;
+      if (row0 + r < m && k0 + k < dn) {
+        const int src_col = cols ? cols[k0 + k] : (k0 + k);
+        v = (float)((double)x[(row0 + r) * d_in + src_col] - mu[k0 + k]);
+      }
+      As[k][r] = v;
+    }
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int k = i >> 6, c = i & 63;
+      Bs[k][c] = (k0 + k < dn && col0 + c < dn) ? w[(int64_t)(k0 + k) * dn + col0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; i++) {
+    const int64_t r = row0 + ty * 4 + i;
+    if (r >= m) continue;
+    for (int j = 0; j < 4; j++) {
+      const int c = col0 + tx * 4 + j;
+      if (c < dn) out[r * dn + c] = acc[i][j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) kde_combine_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
+                                                          int64_t m, int slots, float* __restrict__ om,
+                                                          float* __restrict__ os) {
+  const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (row >= m) return;
+  float mx = -INFINITY;
+  for (int s = 0; s < slots; s++) mx = fmaxf(mx, pm[(int64_t)s * m + row]);
+  float sum = 0.f;
+  if (mx > -INFINITY)
+    for (int s = 0; s < slots; s++) {
+      const float v = pm[(int64_t)s * m + row];
+      if (v > -INFINITY) sum += ps[(int64_t)s * m + row] * __expf(v - mx);
+    }
+  om[row] = mx;
+  os[row] = sum;
+}
+
+}  // namespace tip
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace tip;
+
+extern "C" int tip_version(void) { return TIP_VERSION; }
+extern "C" const char* tip_last_error(void) { return g_err; }
+extern "C" uint64_t tip_launch_count(void) { return g_launches.load(); }
+
+extern "C" int tip_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  TIP_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  TIP_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sms) *sms = prop.multiProcessorCount;
+  if (major) *major = prop.major;
+  if (minor) *minor = prop.minor;
+  return TIP_OK;
+}
+
+extern "C" int tip_deepgini(const void* probs, int dtype, int64_t n, int64_t c, int32_t* pred, void* gini,
+                            void* stream) {
+  TIP_REQUIRE(probs && pred && gini, "null pointer");
+  TIP_REQUIRE(n >= 0 && c >= 1 && c < (1 << 30), "shape");
+  if (n == 0) return TIP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TIP_F32) return launch_gini<float>((const float*)probs, n, c, pred, (float*)gini, st);
+  if (dtype == TIP_F64) return launch_gini<double>((const double*)probs, n, c, pred, (double*)gini, st);
+  TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
+}
+
+extern "C" int tip_kmnc(const void* act, int act_dtype, int64_t n, int64_t d, const void* mins, const void* jumps,
+                        int stat_dtype, int32_t sections, void* bucket, int bucket_dtype, int32_t* score,
+                        void* stream) {
+  TIP_REQUIRE(act && mins && jumps && score, "null pointer");
+  TIP_REQUIRE(n >= 0 && d >= 1, "shape");
+  TIP_REQUIRE(sections >= 1, "sections");
+  TIP_REQUIRE(bucket == nullptr || bucket_dtype == TIP_I16 || bucket_dtype == TIP_I32, "bucket dtype");
+  TIP_REQUIRE(!(bucket && bucket_dtype == TIP_I16) || sections <= 32767, "sections exceed int16 bucket ids");
+  if (n == 0) return TIP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act_dtype == TIP_F32 && stat_dtype == TIP_F32) {
+    const bool aligned = (d % 4 == 0) && (((uintptr_t)act | (uintptr_t)mins | (uintptr_t)jumps) & 15) == 0 &&
+                         (bucket == nullptr || ((uintptr_t)bucket & 15) == 0);
+    if (aligned) {
+      const int grid = (int)std::min<int64_t>(n, (int64_t)sm_count() * 8);
+      if (bucket == nullptr || bucket_dtype == TIP_I16)
+        kmnc_vec4_kernel<int16_t><<<grid, 256, 0, st>>>((const float*)act, n, d, (const float*)mins,
+                                                        (const float*)jumps, sections, (int16_t*)bucket, score);
+      else
+        kmnc_vec4_kernel<int32_t><<<grid, 256, 0, st>>>((const float*)act, n, d, (const float*)mins,
+                                                        (const float*)jumps, sections, (int32_t*)bucket, score);
+      TIP_LAUNCH_CHECK();
+      return TIP_OK;
+    }
+    return launch_kmnc<float, float>(act, n, d, mins, jumps, sections, bucket, bucket_dtype, score, st);
+  }
+  if (act_dtype == TIP_F32 && stat_dtype == TIP_F64)
+    return launch_kmnc<float, double>(act, n, d, mins, jumps, sections, bucket, bucket_dtype, score, st);
+  if (act_dtype == TIP_F64 && stat_dtype == TIP_F32)
+    return launch_kmnc<double, float>(act, n, d, mins, jumps, sections, bucket, bucket_dtype, score, st);
+  if (act_dtype == TIP_F64 && stat_dtype == TIP_F64)
+    return launch_kmnc<double, double>(act, n, d, mins, jumps, sections, bucket, bucket_dtype, score, st);
+  TIP_REQUIRE(false, "dtypes must be TIP_F32 / TIP_F64");
+}
+
+extern "C" int64_t tip_pair_pitch(int64_t d, int segments) {
+  if (d < 1 || (segments != 1 && segments != 3)) return -1;
+  const int64_t d16 = (d + 15) & ~(int64_t)15;
+  return (segments * d16 + 16 + 63) & ~(int64_t)63;
+}
+
+extern "C" int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d, const float* center, int role,
+                             int segments, float scale, float norm_coef, void* dst, float* sqnorm, void* stream) {
+  TIP_REQUIRE(src && dst, "null pointer");
+  TIP_REQUIRE(segments == 1 || segments == 3, "segments must be 1 or 3");
+  TIP_REQUIRE(role == TIP_ROLE_QUERY || role == TIP_ROLE_TRAIN, "role");
+  TIP_REQUIRE(d >= 1 && d <= (1 << 20), "d");
+  TIP_REQUIRE(rows >= 0, "rows");
+  if (rows == 0) return TIP_OK;
+  const int64_t pitch = tip_pair_pitch(d, segments);
+  const int64_t blocks = (rows + 7) / 8;
+  TIP_REQUIRE(blocks < (1LL << 31), "too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TIP_F32)
+    pair_prep_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)src, rows, (int)d, center, role, segments,
+                                                             scale, norm_coef, (__nv_bfloat16*)dst, pitch, sqnorm);
+  else if (dtype == TIP_F64)
+    pair_prep_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double*)src, rows, (int)d, center, role,
+                                                              segments, scale, norm_coef, (__nv_bfloat16*)dst, pitch,
+                                                              sqnorm);
+  else
+    TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
+}
+
+extern "C" int tip_gather_rows(const void* src, int64_t row_bytes, const int32_t* pos, int64_t m, void* dst,
+                               void* stream) {
+  TIP_REQUIRE(src && pos && dst, "null pointer");
+  TIP_REQUIRE(row_bytes > 0 && m >= 0, "shape");
+  if (m == 0) return TIP_OK;
+  const int grid = (int)std::min<int64_t>(m, (int64_t)sm_count() * 16);
+  gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)src, row_bytes, pos, m,
+                                                            (unsigned char*)dst);
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
+}
+
+extern "C" int tip_whiten(const void* x, int dtype, int64_t m, int64_t d_in, const int32_t* cols, int64_t d_out,
+                          const double* mu, const float* w, float* out, void* stream) {
+  TIP_REQUIRE(x && mu && w && out, "null pointer");
+  TIP_REQUIRE(m >= 0 && d_in >= 1 && d_out >= 1 && d_out <= 65535 * 64, "shape");
+  if (m == 0) return TIP_OK;
+  dim3 grid((unsigned)((d_out + 63) / 64), (unsigned)((m + 63) / 64));
+  TIP_REQUIRE((m + 63) / 64 <= 65535, "too many rows for one launch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TIP_F32)
+    whiten_kernel<float><<<grid, 256, 0, st>>>((const float*)x, m, d_in, cols, (int)d_out, mu, w, out);
+  else if (dtype == TIP_F64)
+    whiten_kernel<double><<<grid, 256, 0, st>>>((const double*)x, m, d_in, cols, (int)d_out, mu, w, out);
+  else
+    TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
+}
+
+extern "C" int tip_kde_combine(const float* pm, const float* ps, int64_t m, int32_t slots, float* om, float* os,
+                               void* stream) {
+  TIP_REQUIRE(pm && ps && om && os, "null pointer");
+  TIP_REQUIRE(m >= 0 && slots >= 1, "shape");
+  if (m == 0) return TIP_OK;
+  kde_combine_kernel<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pm, ps, m, slots, om, os);
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
+}

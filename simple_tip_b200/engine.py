@@ -1,0 +1,361 @@
+"""Device-side orchestration of the scoring kernels (PyTorch = memory, streams, NCCL plumbing).
+
+Two engines sit under the reference-compatible classes in `simple_tip_b200.core`:
+
+* `NnEngine`  — class-grouped training traces resident in HBM (original dtype for the exact
+  re-rank + packed bf16 operand for the tensor-core filter); `search()` runs
+  filter -> re-rank for a batch of class-sorted queries.  Used twice per DSA call
+  (surprise.py:615-631: same-class nearest neighbour, then other-class nearest neighbour
+  of the winning TRAIN row).
+* `KdeEngine` — whitened training traces as a 3-segment split-bf16 operand; `log_kernel_sum()`
+  returns per-query (max, sum) of exp(-|p_i - q_j|^2 / 2) in the log domain
+  (scipy 1.4.1 gaussian_kernel_estimate, called from stable_kde.py:101).
+
+The pure-host planning helpers (`class_layout`, `build_items`, `shard_rows`) and the
+cross-rank reduction protocol (`TrainShardComm`) contain no CUDA calls and are unit-tested on
+CPU (gloo, world_size 2).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+DEFAULT_CAP = 64
+
+
+# ------------------------------------------------------------------------------------------
+# plumbing
+# ------------------------------------------------------------------------------------------
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("simple_tip_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def tip_dtype(dt) -> int:
+    if dt in (torch.float32, np.float32, np.dtype("float32")):
+        return _lib.TIP_F32
+    if dt in (torch.float64, np.float64, np.dtype("float64")):
+        return _lib.TIP_F64
+    raise TypeError(f"activation traces must be float32 or float64, got {dt}")
+
+
+def to_device(a: np.ndarray, dev: torch.device) -> torch.Tensor:
+    """Host -> HBM.  Pinned sources (e.g. views of torch pinned tensors) copy asynchronously."""
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+
+
+# ------------------------------------------------------------------------------------------
+# host-side planning (no CUDA)
+# ------------------------------------------------------------------------------------------
+def class_layout(labels: np.ndarray, num_classes: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Stable grouping by class.  Returns (order, offsets[num_classes+1]); `order` lists the
+    positions of rows with 0 <= label < num_classes, grouped by class, ascending position inside
+    a class (the order `np.argwhere(pred == label)` gives, surprise.py:554,581)."""
+    labels = np.asarray(labels)
+    valid = np.flatnonzero((labels >= 0) & (labels < num_classes))
+    order = valid[np.argsort(labels[valid], kind="stable")]
+    counts = np.bincount(labels[valid].astype(np.int64), minlength=num_classes)[:num_classes]
+    offsets = np.zeros(num_classes + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    return order, offsets
+
+
+def shard_rows(labels: np.ndarray, num_classes: int, rank: int, world: int) -> np.ndarray:
+    """Rows of the training set kept by `rank`: every class is dealt round-robin, so each rank
+    holds ~N_c/world rows of every class in ascending original order."""
+    order, off = class_layout(labels, num_classes)
+    keep = []
+    for c in range(num_classes):
+        rows = order[off[c]:off[c + 1]]
+        keep.append(rows[rank::world])
+    return np.sort(np.concatenate(keep)) if keep else np.zeros(0, dtype=np.int64)
+
+
+def span_tiles_for(total_tile_pairs: int, sms: int) -> int:
+    """Column tiles per work item: aim for ~6 items per SM so the static round-robin balances."""
+    return int(min(32, max(2, round(total_tile_pairs / max(1, sms * 6)))))
+
+
+def build_items(q_off: np.ndarray, ranges_per_class: Sequence[Sequence[Tuple[int, int]]], span_tiles: int
+                ) -> Tuple[np.ndarray, int]:
+    """Work list of the tensor-core pass.  q_off[c]..q_off[c+1] are the (class-sorted) query rows
+    of class c; ranges_per_class[c] the train-row ranges they must be compared with.  Every item is
+    one 128-row query tile x one span of at most span_tiles*256 train rows.  Returns
+    (int32 array [n, 6] laid out as tip_work_item, max number of spans per class)."""
+    width = span_tiles * _lib.COL_TILE
+    out = []
+    max_slots = 1
+    for c, ranges in enumerate(ranges_per_class):
+        cnt = int(q_off[c + 1] - q_off[c])
+        if cnt <= 0:
+            continue
+        spans = []
+        for lo, hi in ranges:
+            for s in range(int(lo), int(hi), width):
+                spans.append((s, min(s + width, int(hi))))
+        if not spans:
+            continue
+        max_slots = max(max_slots, len(spans))
+        r0 = np.arange(int(q_off[c]), int(q_off[c + 1]), _lib.ROW_TILE, dtype=np.int64)
+        rows = np.minimum(_lib.ROW_TILE, int(q_off[c + 1]) - r0)
+        sp = np.asarray(spans, dtype=np.int64)
+        nt, ns = r0.shape[0], sp.shape[0]
+        item = np.zeros((nt * ns, 6), dtype=np.int32)
+        item[:, 0] = np.repeat(r0, ns)
+        item[:, 1] = np.repeat(rows, ns)
+        item[:, 2] = np.tile(sp[:, 0], nt)
+        item[:, 3] = np.tile(sp[:, 1], nt)
+        item[:, 4] = np.tile(np.arange(ns), nt)
+        out.append(item)
+    if not out:
+        return np.zeros((0, 6), dtype=np.int32), max_slots
+    return np.concatenate(out), max_slots
+
+
+def count_tile_pairs(q_off: np.ndarray, ranges_per_class) -> int:
+    total = 0
+    for c, ranges in enumerate(ranges_per_class):
+        cnt = int(q_off[c + 1] - q_off[c])
+        if cnt <= 0:
+            continue
+        cols = sum(max(0, int(hi) - int(lo)) for lo, hi in ranges)
+        total += math.ceil(cnt / _lib.ROW_TILE) * math.ceil(cols / _lib.COL_TILE)
+    return total
+
+
+# ------------------------------------------------------------------------------------------
+# cross-rank protocol (N_train sharded over the ranks of one NVSwitch box)
+# ------------------------------------------------------------------------------------------
+class TrainShardComm:
+    """All-reduces of per-shard results over a torch.distributed group (NCCL on GPUs, gloo in
+    the CPU tests).  All messages are O(N_test) scalars except the stage-2 query rows."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def min_(self, t: torch.Tensor) -> torch.Tensor:
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return t
+
+    def max_(self, t: torch.Tensor) -> torch.Tensor:
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def sum_(self, t: torch.Tensor) -> torch.Tensor:
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    # -- DSA stage 1: global (distance, lowest original index) and the winning rows -----------
+    def reduce_winners(self, dist_a: torch.Tensor, gid: torch.Tensor, rows: torch.Tensor
+                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """dist_a[m] local minima (NaN = this shard has no row of the class), gid[m] original
+        index of the local winner, rows[m, d] the local winner's trace.  Returns the global
+        minimum distance, the global winner's original index (lowest index among exact ties,
+        i.e. np.argmin's first occurrence) and its trace on every rank."""
+        big = torch.iinfo(torch.int64).max
+        local = torch.where(torch.isnan(dist_a), torch.full_like(dist_a, float("inf")), dist_a)
+        gmin = self.min_(local.clone())
+        cand = torch.where(local == gmin, gid.to(torch.int64), torch.full_like(gid, big, dtype=torch.int64))
+        ggid = self.min_(cand)
+        mine = (local == gmin) & (gid.to(torch.int64) == ggid) & torch.isfinite(gmin)
+        contrib = torch.where(mine[:, None], rows, torch.zeros_like(rows))
+        self.sum_(contrib)
+        gmin = torch.where(torch.isinf(gmin) & torch.isnan(dist_a), dist_a, gmin)  # nobody had the class
+        return gmin, ggid, contrib
+
+    def reduce_min_nan(self, d: torch.Tensor) -> torch.Tensor:
+        """min over ranks where NaN means 'empty range on this shard'."""
+        local = torch.where(torch.isnan(d), torch.full_like(d, float("inf")), d)
+        g = self.min_(local)
+        return torch.where(torch.isinf(g), torch.full_like(g, float("nan")), g)
+
+    # -- LSA: merge per-shard (max, sum) -------------------------------------------------------
+    def reduce_lse(self, mx: torch.Tensor, sm: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        g = self.max_(mx.clone())
+        scale = torch.where(torch.isinf(mx) & (mx < 0), torch.zeros_like(mx), torch.exp(mx - g))
+        s = self.sum_((sm * scale).to(torch.float64))
+        return g, s
+
+
+# ------------------------------------------------------------------------------------------
+# nearest-neighbour engine (DSA)
+# ------------------------------------------------------------------------------------------
+class NnEngine:
+    def __init__(self, t_sorted: torch.Tensor, class_off: np.ndarray, t_gid: torch.Tensor, cap: int = DEFAULT_CAP):
+        """t_sorted: [n, d] float32/float64 on the GPU, rows grouped by class (offsets class_off,
+        ascending original index inside a class); t_gid[n] int32 original indices."""
+        self.dev = require_cuda()
+        self.lib = _lib.load()
+        self.t = t_sorted.contiguous()
+        self.n, self.d = self.t.shape
+        self.dtype = tip_dtype(self.t.dtype)
+        self.class_off = np.asarray(class_off, dtype=np.int64)
+        self.num_classes = self.class_off.shape[0] - 1
+        self.class_off_dev = torch.from_numpy(self.class_off.astype(np.int32)).to(self.dev)
+        self.t_gid = t_gid.to(torch.int32).contiguous()
+        self.cap = int(cap)
+        self.pitch = int(self.lib.tip_pair_pitch(self.d, 1))
+        sms = C.c_int(0)
+        _lib.check(self.lib.tip_device_info(C.byref(sms), None, None), "tip_device_info")
+        self.sms = sms.value
+        self.stats = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        if self.n > 0:
+            self.center = self.t.mean(dim=0, dtype=torch.float64).to(torch.float32).contiguous()
+            self.t_pack = torch.empty((self.n, self.pitch), dtype=torch.bfloat16, device=self.dev)
+            sq = torch.empty(self.n, dtype=torch.float32, device=self.dev)
+            _lib.check(self.lib.tip_pair_prep(_p(self.t), self.dtype, self.n, self.d, _p(self.center), _lib.ROLE_TRAIN,
+                                              1, -2.0, 1.0, _p(self.t_pack), _p(sq), _stream()), "tip_pair_prep")
+            self.rmax = float(torch.sqrt(sq.max()).item()) * (1.0 + 1e-6)
+        else:
+            self.center = torch.zeros(self.d, dtype=torch.float32, device=self.dev)
+            self.t_pack, self.rmax = None, 0.0
+
+    @classmethod
+    def from_host(cls, train: np.ndarray, labels: np.ndarray, num_classes: int, gids: Optional[np.ndarray] = None,
+                  cap: int = DEFAULT_CAP) -> "NnEngine":
+        dev = require_cuda()
+        order, off = class_layout(labels, num_classes)
+        t = to_device(train, dev)
+        idx = torch.from_numpy(order).to(dev)
+        gid = idx if gids is None else torch.from_numpy(np.asarray(gids)[order]).to(dev)
+        return cls(t.index_select(0, idx), off, gid, cap)
+
+    def ranges(self, mode: int):
+        off = self.class_off
+        if mode == _lib.RANGE_SAME_CLASS:
+            return [[(off[c], off[c + 1])] for c in range(self.num_classes)]
+        return [[(0, off[c]), (off[c + 1], off[-1])] for c in range(self.num_classes)]
+
+    def search(self, q: torch.Tensor, q_class: torch.Tensor, q_off: np.ndarray, mode: int, use_filter: bool = True
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """q: [m, d] queries grouped by class (q_off), q_class[m] int32.  Returns, per query, the
+        exact NumPy-order distance to its nearest train row in the range selected by `mode`
+        (NaN when the range is empty on this shard) and that row's position (-1 when empty)."""
+        m = q.shape[0]
+        out_dist = torch.empty(m, dtype=q.dtype, device=self.dev)
+        out_pos = torch.empty(m, dtype=torch.int32, device=self.dev)
+        if m == 0:
+            return out_dist, out_pos
+        lib = self.lib
+        cand_idx = cand_cnt = None
+        if use_filter and self.n > 0:
+            ranges = self.ranges(mode)
+            pairs = count_tile_pairs(q_off, ranges)
+            items, _ = build_items(q_off, ranges, span_tiles_for(pairs, self.sms))
+            if items.shape[0] > 0:
+                q_pack = torch.empty((m, self.pitch), dtype=torch.bfloat16, device=self.dev)
+                q_sq = torch.empty(m, dtype=torch.float32, device=self.dev)
+                _lib.check(lib.tip_pair_prep(_p(q), tip_dtype(q.dtype), m, self.d, _p(self.center), _lib.ROLE_QUERY, 1,
+                                             1.0, 0.0, _p(q_pack), _p(q_sq), _stream()), "tip_pair_prep")
+                items_dev = torch.from_numpy(items).to(self.dev, non_blocking=True)
+                row_min = torch.full((m,), 0x7F800000, dtype=torch.int32, device=self.dev)
+                cand_cnt = torch.zeros(m, dtype=torch.int32, device=self.dev)
+                cand_idx = torch.empty((m, self.cap), dtype=torch.int32, device=self.dev)
+                _lib.check(lib.tip_nn_filter(_p(q_pack), _p(q_sq), m, _p(self.t_pack), self.n, self.d, self.pitch,
+                                             _p(items_dev), items.shape[0], self.rmax, _p(row_min), _p(cand_idx),
+                                             _p(cand_cnt), self.cap, _stream()), "tip_nn_filter")
+        _lib.check(lib.tip_nn_rerank(_p(q), _p(self.t), tip_dtype(q.dtype), m, self.n, self.d, _p(cand_idx),
+                                     _p(cand_cnt), self.cap, _p(q_class), _p(self.class_off_dev), self.num_classes,
+                                     mode, _p(self.t_gid), _p(out_dist), _p(out_pos), _p(self.stats), _stream()),
+                   "tip_nn_rerank")
+        self.last_cand_cnt = cand_cnt
+        return out_dist, out_pos
+
+    def gather(self, pos: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((pos.shape[0], self.d), dtype=self.t.dtype, device=self.dev)
+        if pos.shape[0]:
+            _lib.check(self.lib.tip_gather_rows(_p(self.t), self.d * self.t.element_size(), _p(pos), pos.shape[0],
+                                                _p(out), _stream()), "tip_gather_rows")
+        return out
+
+
+def dsa_distances(engine: NnEngine, x: torch.Tensor, q_class: torch.Tensor, q_off: np.ndarray,
+                  comm: Optional[TrainShardComm] = None, use_filter: bool = True
+                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """surprise.py:615-631 for class-sorted queries x: (dist_a, dist_b, winner original index)."""
+    dist_a, pos_a = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter)
+    winners = engine.gather(pos_a)
+    gid = torch.where(pos_a >= 0, engine.t_gid[pos_a.clamp(min=0).long()], torch.full_like(pos_a, -1))
+    if comm is not None and comm.world > 1:
+        dist_a, gid64, winners = comm.reduce_winners(dist_a, gid, winners)
+        gid = gid64
+    dist_b, _ = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter)
+    if comm is not None and comm.world > 1:
+        dist_b = comm.reduce_min_nan(dist_b)
+    return dist_a, dist_b, gid
+
+
+# ------------------------------------------------------------------------------------------
+# Gaussian-KDE engine (LSA)
+# ------------------------------------------------------------------------------------------
+class KdeEngine:
+    def __init__(self, p_whitened: np.ndarray):
+        """p_whitened: [n, d] float64 whitened, centred training traces (host)."""
+        self.dev = require_cuda()
+        self.lib = _lib.load()
+        self.n, self.d = p_whitened.shape
+        self.pitch = int(self.lib.tip_pair_pitch(self.d, 3))
+        sms = C.c_int(0)
+        _lib.check(self.lib.tip_device_info(C.byref(sms), None, None), "tip_device_info")
+        self.sms = sms.value
+        p32 = to_device(p_whitened.astype(np.float32), self.dev)
+        self.t_pack = torch.empty((self.n, self.pitch), dtype=torch.bfloat16, device=self.dev)
+        _lib.check(self.lib.tip_pair_prep(_p(p32), _lib.TIP_F32, self.n, self.d, None, _lib.ROLE_TRAIN, 3, 1.0, -0.5,
+                                          _p(self.t_pack), None, _stream()), "tip_pair_prep")
+        torch.cuda.current_stream().synchronize()
+
+    def log_kernel_sum(self, q: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """q: [m, d] fp32 whitened, centred queries on the GPU.  Returns (mx, sm, qsq) with
+        sum_i exp(-|p_i - q_j|^2/2) = exp(mx_j - qsq_j/2) * sm_j."""
+        m = q.shape[0]
+        lib = self.lib
+        q_pack = torch.empty((m, self.pitch), dtype=torch.bfloat16, device=self.dev)
+        q_sq = torch.empty(m, dtype=torch.float32, device=self.dev)
+        _lib.check(lib.tip_pair_prep(_p(q), _lib.TIP_F32, m, self.d, None, _lib.ROLE_QUERY, 3, 1.0, 0.0, _p(q_pack),
+                                     _p(q_sq), _stream()), "tip_pair_prep")
+        q_off = np.array([0, m], dtype=np.int64)
+        ranges = [[(0, self.n)]]
+        items, slots = build_items(q_off, ranges, span_tiles_for(count_tile_pairs(q_off, ranges), self.sms))
+        items_dev = torch.from_numpy(items).to(self.dev, non_blocking=True)
+        part_max = torch.full((slots, m), float("-inf"), dtype=torch.float32, device=self.dev)
+        part_sum = torch.zeros((slots, m), dtype=torch.float32, device=self.dev)
+        _lib.check(lib.tip_kde_lse(_p(q_pack), m, _p(self.t_pack), self.n, self.d, self.pitch, _p(items_dev),
+                                   items.shape[0], _p(part_max), _p(part_sum), _stream()), "tip_kde_lse")
+        mx = torch.empty(m, dtype=torch.float32, device=self.dev)
+        sm = torch.empty(m, dtype=torch.float32, device=self.dev)
+        _lib.check(lib.tip_kde_combine(_p(part_max), _p(part_sum), m, slots, _p(mx), _p(sm), _stream()),
+                   "tip_kde_combine")
+        return mx, sm, q_sq
+
+
+def whiten(x: torch.Tensor, cols: Optional[torch.Tensor], mu: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """(x[:, cols] - mu) @ w in fp32 on the GPU (scipy 1.4.1: points . cholesky(inv_cov))."""
+    lib = _lib.load()
+    m, d_in = x.shape
+    d_out = w.shape[0]
+    out = torch.empty((m, d_out), dtype=torch.float32, device=x.device)
+    _lib.check(lib.tip_whiten(_p(x), tip_dtype(x.dtype), m, d_in, _p(cols), d_out, _p(mu), _p(w), _p(out), _stream()),
+               "tip_whiten")
+    return out

@@ -1,0 +1,347 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the
+reference-facing overlay (`src.core.*`) or the C ABI; the oracle (NumPy / C ports of the
+reference, pinned in test_oracle_golden.py) is the checker.
+
+Tolerances: DSA distances, winners, scores — bit-exact.  KMNC bucket ids and scores, DeepGini
+predictions and scores — bit-exact.  LSA — rtol 1e-4 (north_star) with an absolute floor of
+2e-4 on the log-density (values cross zero), inf <-> inf.
+"""
+import ast
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, np_oracle
+from tests.conftest import case_names
+
+pytestmark = pytest.mark.gpu
+
+LSA_RTOL, LSA_ATOL = 1e-4, 2e-4
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+# ------------------------------------------------------------------------------------------
+# tensor-core pass: raw accumulator tile vs an fp32 matmul of the packed operands
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,segments", [(16, 1), (128, 1), (100, 1), (300, 1), (2048, 1), (10, 3), (256, 3), (40, 3)])
+def test_pair_probe_matches_packed_matmul(d, segments):
+    torch = _torch()
+    from simple_tip_b200 import _lib
+    from simple_tip_b200 import engine as E
+
+    lib = _lib.load()
+    dev = E.require_cuda()
+    rng = np.random.default_rng(d * 7 + segments)
+    q = torch.from_numpy(rng.normal(size=(128, d)).astype(np.float32)).to(dev)
+    t = torch.from_numpy(rng.normal(size=(256, d)).astype(np.float32) * 1.5).to(dev)
+    center = torch.from_numpy(rng.normal(size=d).astype(np.float32) * 0.1).to(dev)
+    pitch = int(lib.tip_pair_pitch(d, segments))
+    qp = torch.empty((128, pitch), dtype=torch.bfloat16, device=dev)
+    tp = torch.empty((256, pitch), dtype=torch.bfloat16, device=dev)
+    qs = torch.empty(128, dtype=torch.float32, device=dev)
+    ts = torch.empty(256, dtype=torch.float32, device=dev)
+    scale, coef = (-2.0, 1.0) if segments == 1 else (1.0, -0.5)
+    _lib.check(lib.tip_pair_prep(E._p(q), _lib.TIP_F32, 128, d, E._p(center), _lib.ROLE_QUERY, segments, 1.0, 0.0,
+                                 E._p(qp), E._p(qs), E._stream()), "prep q")
+    _lib.check(lib.tip_pair_prep(E._p(t), _lib.TIP_F32, 256, d, E._p(center), _lib.ROLE_TRAIN, segments, scale, coef,
+                                 E._p(tp), E._p(ts), E._stream()), "prep t")
+    out = torch.empty((128, 256), dtype=torch.float32, device=dev)
+    _lib.check(lib.tip_pair_probe(E._p(qp), 128, E._p(tp), 256, d, segments, pitch, E._p(out), E._stream()), "probe")
+    torch.cuda.synchronize()
+    want = qp.to(torch.float64) @ tp.to(torch.float64).T
+    scale_ref = float((qp.to(torch.float64).abs() @ tp.to(torch.float64).abs().T).max())
+    err = float((out.to(torch.float64) - want).abs().max())
+    assert err <= 4e-6 * scale_ref + 1e-6, (err, scale_ref)
+    # and the packed operands mean what tip_pair_prep documents
+    vq = (q - center).to(torch.float64)
+    vt = (t - center).to(torch.float64)
+    if segments == 1:
+        d2 = ((vq[:, None, :] - vt[None, :, :]) ** 2).sum(-1)
+        approx = out.to(torch.float64) + qs.to(torch.float64)[:, None]
+        rel = float(((approx - d2).abs() / d2.clamp(min=1.0)).max())
+        assert rel < 3e-2, rel                                   # single bf16 pass
+    else:
+        a = vq @ vt.T - 0.5 * (vt ** 2).sum(-1)[None, :]
+        err3 = float((out.to(torch.float64) - a).abs().max())
+        bound = 2e-5 * float(vq.norm(dim=1).max() * vt.norm(dim=1).max()) + 1e-4
+        assert err3 < bound, (err3, bound)                       # split-bf16 (3 segments)
+
+
+# ------------------------------------------------------------------------------------------
+# DeepGini / KMNC
+# ------------------------------------------------------------------------------------------
+def test_deepgini_golden_and_known_answers(golden):
+    from src.core.deepgini import DeepGini
+
+    g = golden("gini_apfd_reference.npz")
+    for name in ("c1_f32", "c1_f64", "wide"):
+        pred, gini = DeepGini.calculate(g[f"{name}.p"])
+        assert np.array_equal(pred, g[f"{name}.pred"]), name
+        assert gini.dtype == g[f"{name}.gini"].dtype and np.array_equal(gini, g[f"{name}.gini"]), name
+    batch = np.array([[0.1, 0.2, 0.3, 0.4], [0.5, 0.1, 0.1, 0.3], [0.25] * 4, [1.0, 0, 0, 0], [0, 1.0, 0, 0]])
+    pred, unc = DeepGini.calculate(batch)          # reference tests/test_deepgini.py:15-38
+    assert np.all(pred == [3, 0, 0, 0, 1]) and np.all(unc == np.array([0.7, 0.64, 0.75, 0, 0]))
+    assert DeepGini.takes_samples() is False and DeepGini.is_confidence() is False
+    assert all(a.startswith("custom") for a in DeepGini.aliases())
+
+
+@pytest.mark.parametrize("n,c,dt", [(10000, 10, np.float32), (3, 1, np.float32), (777, 7, np.float64),
+                                    (300, 129, np.float32), (50, 5000, np.float32), (1, 1000, np.float64)])
+def test_deepgini_shapes_and_apfd(n, c, dt):
+    from src.core.apfd import apfd_from_order
+    from src.core.deepgini import DeepGini
+
+    p, truth = np_oracle.synth_softmax(n, c, seed=n + c, dtype=dt)
+    pred, gini = DeepGini.calculate(p)
+    wp, wg = np_oracle.deepgini_oracle(p)
+    assert np.array_equal(pred, wp) and np.array_equal(gini, wg)
+    fault = wp != truth
+    if fault.any():
+        assert apfd_from_order(fault, np.argsort(-gini)) == np_oracle.apfd_oracle(fault, np.argsort(-wg))
+
+
+def test_kmnc_golden(golden):
+    from src.core.neuron_coverage import KMNC
+
+    g = golden("kmnc_reference.npz")
+    for name in case_names(g, "score"):
+        mins, maxs, act = g[f"{name}.mins"], g[f"{name}.maxs"], g[f"{name}.act"]
+        cut, k = int(g[f"{name}.cut"]), int(g[f"{name}.sections"])
+        km = KMNC([mins[:cut], mins[cut:]], [maxs[:cut], maxs[cut:]], k)
+        score, bucket = km.buckets([act[:, :cut], act[:, cut:]])
+        assert np.array_equal(bucket, g[f"{name}.bucket"]), name
+        assert np.array_equal(score, g[f"{name}.score"]), name
+        s2, prof = km([act[:, :cut], act[:, cut:]])
+        assert s2.dtype == g[f"{name}.score"].dtype and np.array_equal(s2, g[f"{name}.score"])
+        assert prof.shape == (act.shape[0], act.shape[1], k) and prof.dtype == bool
+        assert np.array_equal(prof.sum(axis=2), g[f"{name}.hits"])
+        assert np.array_equal(np.where(prof.any(axis=2), prof.argmax(axis=2), -1), g[f"{name}.bucket"])
+
+
+def test_kmnc_known_answer_from_reference_tests():
+    from src.core.neuron_coverage import KMNC
+
+    acts = [np.array([[0.1, 0.4, 0.9, 0.4], [0.1, 0.9, 0.9, 0.4]]),
+            np.array([[0.3, 0.2, 0.1, 0.6, 0.8], [0.3, 0.9, 0.1, 0.6, 0.8]]),
+            np.array([[0.2, 0.3, 0.4, 0.4], [0.2, 0.9, 0.4, 0.4]])]
+    mins = [np.array([0] * 4), np.array([0] * 5), np.array([0.1] * 4)]
+    maxs = [np.array([1] * 4), np.array([1] * 5), np.array([0.95] * 4)]
+    score, profile = KMNC(mins, maxs, 2)(acts)
+    assert np.all(score == np.array([13, 13]))
+    assert np.all(profile[0] == np.concatenate([
+        [[True, False], [True, False], [False, True], [True, False]],
+        [[True, False], [True, False], [True, False], [False, True], [False, True]],
+        [[True, False], [True, False], [True, False], [True, False]]]))
+    out = [a.copy() for a in acts]
+    out[0][0][0], out[1][0][0] = -0.5, 1.5
+    assert np.all(KMNC(mins, maxs, 2)(out)[0] == np.array([11, 13]))
+
+
+@pytest.mark.parametrize("n,d,k", [(2000, 4096, 1000), (513, 1001, 50), (64, 4096, 10000)])
+def test_kmnc_large_vs_c_oracle(n, d, k):
+    from src.core.neuron_coverage import KMNC
+
+    act, mins, maxs = np_oracle.synth_relu(n, d, seed=4)
+    km = KMNC([mins], [maxs], k)
+    score, bucket = km.buckets([act])
+    sub = np.random.default_rng(0).choice(n, size=min(n, 24), replace=False)
+    thresh = np.stack(km.thresh)
+    cb, cs = c_oracle.kmnc(act[sub], thresh)
+    assert np.array_equal(bucket[sub], cb) and np.array_equal(score[sub], cs)
+    # size-independent properties on the full output
+    assert np.array_equal(score, (bucket >= 0).sum(axis=1))
+    inside = (act >= mins) & (act < thresh[-1]) & (km._jumps > 0)
+    assert np.array_equal(bucket >= 0, inside)
+    lo = mins + km._jumps * np.maximum(bucket, 0)
+    hi = mins + km._jumps * (np.maximum(bucket, 0) + 1)
+    ok = bucket < 0
+    assert np.all(ok | ((lo <= act) & (act < hi)))
+
+
+# ------------------------------------------------------------------------------------------
+# DSA
+# ------------------------------------------------------------------------------------------
+def test_dsa_golden_bit_exact(golden):
+    from src.core.surprise import DSA
+
+    g = golden("dsa_reference.npz")
+    for name in case_names(g, "dsa"):
+        kw = ast.literal_eval(str(g[f"{name}.kw"]))
+        xtr, ytr, xte, pte = (g[f"{name}.{k}"] for k in ("xtr", "ytr", "xte", "pte"))
+        sa = DSA(xtr, ytr, **kw)
+        got = sa(xte, pte)
+        assert got.dtype == np.float64 and got.shape == (xte.shape[0],)
+        assert np.array_equal(got, g[f"{name}.dsa"], equal_nan=True), name
+        assert np.array_equal(sa.last_dist_a, g[f"{name}.dist_a"]), name
+        assert np.array_equal(sa.last_dist_b, g[f"{name}.dist_b"]), name
+        want = np_oracle.dsa_oracle(xtr, ytr, xte, pte, **kw)
+        assert np.array_equal(sa.last_winner_index, want["idx_a"]), name      # argmin indices
+        # exhaustive (no tensor-core filter) path gives the same bits
+        sa.use_filter = False
+        assert np.array_equal(sa(xte, pte), g[f"{name}.dsa"], equal_nan=True), name
+
+
+@pytest.mark.parametrize("n_train,n_test,d,classes,dt,seed", [
+    (20000, 1500, 128, 10, np.float32, 2), (5000, 700, 64, 3, np.float32, 3), (3000, 257, 200, 7, np.float32, 4),
+    (4000, 300, 128, 10, np.float64, 5), (1500, 100, 1600, 4, np.float32, 6), (900, 130, 9, 2, np.float32, 7)])
+def test_dsa_random_vs_c_oracle(n_train, n_test, d, classes, dt, seed):
+    from src.core.surprise import DSA
+
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(n_train, n_test, d, classes, seed=seed, dtype=dt)
+    want = c_oracle.dsa(xtr, ytr, xte, pte)
+    sa = DSA(xtr, ytr)
+    got = sa(xte, pte)
+    assert np.array_equal(sa.last_winner_index, want["idx_a"])
+    assert np.array_equal(sa.last_dist_a, want["dist_a"]) and np.array_equal(sa.last_dist_b, want["dist_b"])
+    assert np.array_equal(got, want["dsa"])
+    # the filter, not the fallback, did the work
+    stats = sa._engine.stats.cpu().numpy()
+    assert stats[0] == 0, f"{stats[0]} rows fell back to the exhaustive scan"
+    assert stats[1] <= 2 * n_test * 40, f"candidate lists unexpectedly long: {stats[1]}"
+    # determinism (reference tests/test_surprise.py:165-171)
+    assert np.array_equal(sa(xte, pte), got)
+
+
+def test_dsa_heavy_ties_and_overflow_fallback():
+    """Many exactly tied distances (integer grid, duplicated rows): lowest original index must
+    win, also when the candidate list overflows and the exhaustive scan takes over."""
+    from src.core.surprise import DSA
+
+    rng = np.random.default_rng(9)
+    base = rng.integers(0, 2, size=(40, 16)).astype(np.float32)
+    xtr = np.tile(base, (30, 1))                       # every row 30 times
+    ytr = np.tile(np.arange(40) % 2, 30).astype(np.int64)
+    xte = rng.integers(0, 2, size=(300, 16)).astype(np.float32)
+    pte = rng.integers(0, 2, size=300).astype(np.int64)
+    want = c_oracle.dsa(xtr, ytr, xte, pte)
+    sa = DSA(xtr, ytr)
+    got = sa(xte, pte)
+    assert np.array_equal(sa.last_winner_index, want["idx_a"])
+    assert np.array_equal(got, want["dsa"], equal_nan=True)
+    sa._engine.cap = 4                                  # force overflow -> exhaustive rows
+    assert np.array_equal(sa(xte, pte), want["dsa"], equal_nan=True)
+    assert sa._engine.stats.cpu().numpy()[0] > 0
+
+
+def test_dsa_edge_cases():
+    from src.core.surprise import DSA
+
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(400, 50, 24, 4, seed=21)
+    sa = DSA(xtr, ytr)
+    assert sa(xte[:0], pte[:0]).shape == (0,)
+    one = sa(xte[:1], pte[:1])
+    assert np.array_equal(one, np_oracle.dsa_oracle(xtr, ytr, xte[:1], pte[:1])["dsa"])
+    # labels beyond the training classes are never scored by the reference (np.empty garbage): NaN here
+    p2 = pte.copy()
+    p2[:5] = 9
+    got = sa(xte, p2)
+    assert np.isnan(got[:5]).all()
+    assert np.array_equal(got[5:], np_oracle.dsa_oracle(xtr, ytr, xte, pte)["dsa"][5:])
+    # a class without training rows raises like np.min of an empty array (surprise.py:645)
+    y2 = ytr.copy()
+    y2[y2 == 1] = 0
+    with pytest.raises(ValueError):
+        DSA(xtr, y2)(xte, np.ones(50, dtype=np.int64))
+    with pytest.raises(AssertionError, match="must be one-dimensional"):
+        sa(xte, pte[None, :])
+    with pytest.raises(ValueError, match="subsampling"):
+        DSA(xtr, ytr, subsampling=-1)
+
+
+@pytest.mark.parametrize("subsampling", [1.0, 0.3])
+def test_dsa_config2_full_size_properties(subsampling):
+    """BASELINE config 2 (10k x 60k x 128 fp32): checked on a random row subset against the C
+    oracle (exhaustive over all 60k rows) and through size-independent properties."""
+    from src.core.surprise import DSA
+
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(60000, 10000, 128, 10, seed=2)
+    sa = DSA(xtr, ytr, subsampling=subsampling)
+    got = sa(xte, pte)
+    assert np.isfinite(got).all() and (got > 0).all()
+    rows = np.random.default_rng(0).choice(10000, size=96, replace=False)
+    want = c_oracle.dsa(sa.train_activations, sa.train_predictions, xte[rows], pte[rows])
+    assert np.array_equal(sa.last_winner_index[rows], want["idx_a"])
+    assert np.array_equal(got[rows], want["dsa"])
+    # properties: the winner has the predicted class; dist_a is the exact distance to it
+    w = sa.last_winner_index
+    assert np.array_equal(sa.train_predictions[w], pte)
+    sub = rows[:32]
+    exact = np.linalg.norm(xte[sub] - sa.train_activations[w[sub]], axis=1)
+    assert np.array_equal(exact.astype(np.float32), sa.last_dist_a[sub])
+    # train rows as queries: distance 0, winner = lowest index among identical rows
+    probe = sa.train_activations[:64]
+    z = sa(probe, sa.train_predictions[:64])
+    assert (z == 0).all() and np.array_equal(sa.last_winner_index, np.arange(64))
+    # idempotence / permutation equivariance
+    perm = np.random.default_rng(1).permutation(10000)
+    assert np.array_equal(sa(xte[perm], pte[perm]), got[perm])
+    assert sa._engine.stats.cpu().numpy()[0] == 0
+
+
+# ------------------------------------------------------------------------------------------
+# LSA
+# ------------------------------------------------------------------------------------------
+def _close(got, want):
+    assert np.array_equal(np.isinf(got), np.isinf(want)), (np.isinf(got).sum(), np.isinf(want).sum())
+    assert np.array_equal(np.sign(got[np.isinf(got)]), np.sign(want[np.isinf(want)]))
+    f = np.isfinite(want)
+    np.testing.assert_allclose(got[f], want[f], rtol=LSA_RTOL, atol=LSA_ATOL)
+
+
+def test_lsa_golden(golden):
+    from src.core.surprise import LSA, MultiModalSA
+
+    g = golden("lsa_reference.npz")
+    for name, kw in (("plaus", {}), ("cube", {}), ("mf30", {"max_features": 30}), ("far", {})):
+        sa = LSA(g[f"{name}.xtr"], **kw)
+        _close(sa(g[f"{name}.xte"]), g[f"{name}.lsa"])
+    assert np.array_equal(np.array(LSA(g["mf30.xtr"], max_features=30).removed_neurons), g["mf30.removed"])
+    with pytest.warns(UserWarning):
+        sing = LSA(g["singular.xtr"])
+    assert sing.kde.prepare_failed
+    assert np.isinf(sing(g["singular.xte"])).all()
+    mm = MultiModalSA.build_by_class(g["mf30.xtr"], g["pclsa.ytr"], lambda x, y: LSA(x))
+    _close(mm(g["mf30.xte"], g["pclsa.pte"]), g["pclsa.lsa"])
+
+
+@pytest.mark.parametrize("n_train,n_test,d,seed,dt", [(6000, 500, 256, 3, np.float32), (3000, 300, 20, 4, np.float32),
+                                                      (2500, 129, 300, 5, np.float32), (1000, 64, 10, 6, np.float64)])
+def test_lsa_random_vs_oracle(n_train, n_test, d, seed, dt):
+    from src.core.surprise import LSA
+
+    xtr, _, xte, _, _ = np_oracle.synth_clusters(n_train, n_test, d, 4, seed=seed, dtype=dt, spread=1.0)
+    want = np_oracle.lsa_oracle(xtr, xte)
+    got = LSA(xtr)(xte)
+    _close(got, want)
+    assert np.array_equal(LSA(xtr)(xte), got)            # deterministic across fits and calls
+
+
+def test_lsa_bf16_stored_traces_config3_shape():
+    """BASELINE config 3 shape at reduced N: traces stored in bf16; both sides see the same
+    bf16-rounded values."""
+    torch = _torch()
+    from src.core.surprise import LSA
+
+    xtr, _, xte, _, _ = np_oracle.synth_clusters(8000, 400, 256, 10, seed=3, spread=1.0)
+    r = lambda a: torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+    xtr, xte = r(xtr), r(xte)
+    _close(LSA(xtr)(xte), np_oracle.lsa_oracle(xtr, xte))
+
+
+def test_lsa_api_edges():
+    from src.core.surprise import LSA
+
+    rng = np.random.RandomState(0)
+    x = rng.random((500, 12))
+    with pytest.raises(AssertionError):
+        LSA(x, var_threshold=0.1, max_features=5)
+    sa = LSA(x)
+    assert sa(x[:0]).shape == (0,)
+    assert sa(x[:1]).shape == (1,)
+    _close(sa(x[:50].reshape(50, 3, 4)), np_oracle.lsa_oracle(x, x[:50]))

@@ -1,0 +1,180 @@
+"""CPU tests: host-side planning, the C-ABI export table, and the cross-rank protocol
+(world_size-2 gloo).  No compute call touches a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle
+from simple_tip_b200 import _lib
+from simple_tip_b200 import engine as E
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+
+
+def test_c_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "b200tip.h")).read()
+    declared = set(re.findall(r"\b(tip_[a-z0-9_]+)\s*\(", header))
+    declared -= {"tip_status", "tip_dtype", "tip_work_item"}
+    assert declared == set(_lib.symbols()), declared ^ set(_lib.symbols())
+    lib = _lib.load()                      # static cudart: loads without a GPU
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.tip_version() == 100
+    assert lib.tip_pair_pitch(128, 1) == 192 and lib.tip_pair_pitch(256, 3) == 832
+    assert lib.tip_pair_pitch(5, 1) == 64 and lib.tip_pair_pitch(0, 1) == -1
+    assert C.sizeof(_lib.WorkItem) == 24
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "simple_tip_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower().replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_scoring_fails_loudly_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from src.core.deepgini import DeepGini
+    from src.core.surprise import DSA
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DeepGini.calculate(np.ones((2, 2), dtype=np.float32) / 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DSA(np.zeros((4, 3), dtype=np.float32), np.array([0, 1, 0, 1]))
+
+
+def test_class_layout_and_subsampling_match_reference_semantics(golden):
+    labels = np.array([2, 0, 1, 2, 5, 0, 1, 1, -1, 2])
+    order, off = E.class_layout(labels, 3)
+    assert list(off) == [0, 2, 5, 8]
+    assert list(order) == [1, 5, 2, 6, 7, 0, 3, 9]          # ascending position inside each class
+    # sub-sampling picks the same rows as the reference (surprise.py:84-86)
+    from src.core.surprise import _subsample_arrays
+
+    a = np.arange(1000)
+    (got,) = _subsample_arrays(0.3, (a,), seed=0)
+    want = np_oracle.subsample_indexes(1000, 0.3, 0)
+    assert np.array_equal(got, want) and got.shape == (300,)
+    (got,) = _subsample_arrays(17, (a,), seed=3)
+    assert np.array_equal(got, np.random.RandomState(3).choice(np.arange(1000), 17, replace=False))
+    assert _subsample_arrays(1.0, (a,), seed=0)[0] is a
+    with pytest.raises(ValueError):
+        _subsample_arrays(0, (a,), seed=0)
+
+
+def test_work_items_cover_every_pair_exactly_once():
+    rng = np.random.default_rng(0)
+    q_off = np.array([0, 300, 300, 1000])                    # class 1 has no queries
+    t_off = np.array([0, 5000, 5600, 9000])
+    for mode in ("same", "other"):
+        ranges = [[(t_off[c], t_off[c + 1])] if mode == "same" else [(0, t_off[c]), (t_off[c + 1], t_off[-1])]
+                  for c in range(3)]
+        items, slots = E.build_items(q_off, ranges, span_tiles=3)
+        cover = np.zeros((1000, 9000), dtype=np.int32)
+        for q0, rows, c0, c1, slot, _ in items:
+            assert 1 <= rows <= 128 and c1 - c0 <= 3 * 256 and 0 <= slot < slots
+            cover[q0:q0 + rows, c0:c1] += 1
+        want = np.zeros_like(cover)
+        for c in range(3):
+            for lo, hi in ranges[c]:
+                want[q_off[c]:q_off[c + 1], lo:hi] = 1
+        assert np.array_equal(cover, want)
+        assert E.count_tile_pairs(q_off, ranges) >= items.shape[0]
+    assert E.build_items(np.array([0, 0]), [[(0, 10)]], 2)[0].shape == (0, 6)
+    assert 2 <= E.span_tiles_for(10, 148) <= 32 and E.span_tiles_for(10 ** 7, 148) == 32
+
+
+def test_shard_rows_partition_preserves_class_order():
+    labels = np.random.default_rng(1).integers(0, 5, size=1003)
+    parts = [E.shard_rows(labels, 5, r, 4) for r in range(4)]
+    allrows = np.sort(np.concatenate(parts))
+    assert np.array_equal(allrows, np.arange(1003))
+    for p in parts:
+        assert np.all(np.diff(p) > 0)
+        counts = np.bincount(labels[p], minlength=5)
+        assert np.all(np.abs(counts - np.bincount(labels, minlength=5) / 4) <= 1)
+
+
+# ------------------------------------------------------------------------------------------
+# world_size-2 gloo: the N_train-sharded protocol reproduces the single-shard oracle
+# ------------------------------------------------------------------------------------------
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = E.TrainShardComm()
+        xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(400, 60, 12, 3, seed=5)
+        xtr[200:210] = xtr[0:10]                         # exact duplicates: tie-break on index
+        ytr[200:210] = ytr[0:10]
+        xte[:10] = xtr[0:10]
+        pte[:10] = ytr[0:10]
+        ytr[ytr == 2][:0]                                 # no-op
+        keep = E.shard_rows(ytr, 3, rank, world)
+        full = np_oracle.dsa_oracle(xtr, ytr, xte, pte)
+        # per-shard stage 1 with the oracle (stands in for the CUDA search)
+        da = np.full(60, np.nan, dtype=np.float32)
+        gid = np.full(60, -1, dtype=np.int64)
+        rows = np.zeros((60, 12), dtype=np.float32)
+        for i in range(60):
+            cand = keep[ytr[keep] == pte[i]]
+            if cand.size:
+                d = np.linalg.norm(xte[i][None, None, :] - xtr[cand][None], axis=2)[0]
+                j = int(np.argmin(d))
+                da[i], gid[i], rows[i] = d[j], cand[j], xtr[cand[j]]
+        g_da, g_gid, g_rows = comm.reduce_winners(torch.from_numpy(da), torch.from_numpy(gid), torch.from_numpy(rows))
+        assert np.array_equal(g_da.numpy(), full["dist_a"])
+        assert np.array_equal(g_gid.numpy(), full["idx_a"])
+        assert np.array_equal(g_rows.numpy(), xtr[full["idx_a"]])
+        # stage 2 on the shard: distance from the winning TRAIN rows to other-class rows
+        db = np.full(60, np.nan, dtype=np.float32)
+        for i in range(60):
+            cand = keep[ytr[keep] != pte[i]]
+            if cand.size:
+                db[i] = np.linalg.norm(g_rows.numpy()[i][None, None, :] - xtr[cand][None], axis=2).min()
+        g_db = comm.reduce_min_nan(torch.from_numpy(db))
+        assert np.array_equal(g_db.numpy(), full["dist_b"])
+        assert np.array_equal((g_da / g_db).numpy().astype(np.float64), full["dsa"])
+        # LSE merge: per-shard (max, sum) -> global
+        vals = np.random.default_rng(7).normal(size=(60, 400)) * 30 - 200
+        mine = vals[:, rank::world]
+        mx = mine.max(axis=1)
+        sm = np.exp(mine - mx[:, None]).sum(axis=1)
+        gm, gs = comm.reduce_lse(torch.from_numpy(mx), torch.from_numpy(sm))
+        want = np.log(np.exp(vals - vals.max(axis=1, keepdims=True)).sum(axis=1)) + vals.max(axis=1)
+        np.testing.assert_allclose(gm.numpy() + np.log(gs.numpy()), want, rtol=1e-12)
+        # a class missing on one shard / everywhere
+        nan_case = comm.reduce_min_nan(torch.tensor([float("nan"), 1.0 + rank]))
+        assert np.isnan(nan_case[0].item()) and nan_case[1].item() == 1.0
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_train_shard_protocol_gloo_world2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(msg == "ok" for _, msg in results), results
