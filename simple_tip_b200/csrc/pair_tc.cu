@@ -30,7 +30,9 @@ constexpr int kABytes = BM * BK * 2;
 constexpr int kBBytes = BN * BK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kThreads = 192;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kCandSlots = 8;   // per-query staging slots for candidates (MODE_NN)
+constexpr int kCandBytes = kCandSlots * 128 * 8;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kCandBytes;
 constexpr uint32_t kTmemCols = 512;
 
 enum { MODE_NN = 0, MODE_LSE = 1, MODE_DUMP = 2 };
@@ -235,6 +237,9 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int quad = warp & 3;
     const int row_local = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int etid = threadIdx.x - 64;   // 0..127 among the epilogue threads
+    float* cand_val = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
+    int* cand_col = reinterpret_cast<int*>(cand_val + kCandSlots * 128);
     int acc = 0;
     uint32_t acc_phase = 0;
     const float kInf = __int_as_float(0x7f800000);
@@ -247,13 +252,15 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // ---- per-item state ----
       float nx = 0.f, e2 = 0.f, g = 0.f, best = kInf, thr = kInf;  // MODE_NN
       float run_max = -kInf, run_sum = 0.f;                          // MODE_LSE
+      float s_ref = kInf;   // smallest approximate squared distance known for this query (any CTA)
+      int n_staged = 0;
       if (MODE == MODE_NN && valid_row) {
         nx = args.q_sqnorm[row];
         const float r = sqrtf(nx) + args.rmax;
         e2 = args.eps2 * r;
         g = args.gamma * r * r;
-        const float s0 = __uint_as_float(*(volatile uint32_t*)(args.row_min_bits + row));
-        thr = nn_threshold(s0, nx, e2, g);
+        s_ref = __uint_as_float(*(volatile uint32_t*)(args.row_min_bits + row));
+        thr = nn_threshold(s_ref, nx, e2, g);
       }
 
       for (int t = 0; t < ntiles; t++) {
@@ -289,12 +296,31 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int j = 0; j < 32; j++) {
                 const float v = __uint_as_float(r[j]);
-                if (v <= thr) {
-                  const int pos = atomicAdd(args.cand_cnt + row, 1);
-                  if (pos < args.cap) args.cand_idx[row * args.cap + pos] = cbase + j;
+                if (v <= thr && v < kInf) {
                   if (v < best) {
                     best = v;
-                    thr = nn_threshold(fmaxf(best + nx, 0.f), nx, e2, g);
+                    s_ref = fminf(s_ref, fmaxf(best + nx, 0.f));
+                    thr = nn_threshold(s_ref, nx, e2, g);
+                  }
+                  if (n_staged == kCandSlots) {   // compact against the (tighter) current threshold
+                    int keep = 0;
+                    for (int k = 0; k < kCandSlots; k++) {
+                      const float sv = cand_val[k * 128 + etid];
+                      if (sv <= thr) {
+                        cand_val[keep * 128 + etid] = sv;
+                        cand_col[keep * 128 + etid] = cand_col[k * 128 + etid];
+                        keep++;
+                      }
+                    }
+                    n_staged = keep;
+                  }
+                  if (n_staged < kCandSlots) {
+                    cand_val[n_staged * 128 + etid] = v;
+                    cand_col[n_staged * 128 + etid] = cbase + j;
+                    n_staged++;
+                  } else {                        // staging full of live candidates: emit directly
+                    const int pos = atomicAdd(args.cand_cnt + row, 1);
+                    if (pos < args.cap) args.cand_idx[row * args.cap + pos] = cbase + j;
                   }
                 }
               }
@@ -331,6 +357,16 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
+        if (MODE == MODE_NN && valid_row) {
+          // share the running minimum across CTAs scanning other spans for the same query
+          const float mine = fmaxf(best + nx, 0.f);
+          const float seen = __uint_as_float(*(volatile uint32_t*)(args.row_min_bits + row));
+          if (mine < seen) atomicMin(args.row_min_bits + row, __float_as_uint(mine));
+          if (seen < s_ref) {
+            s_ref = seen;
+            thr = nn_threshold(s_ref, nx, e2, g);
+          }
+        }
         // accumulator drained: hand the TMEM stage back to the MMA warp
         tc_fence_before();
         __syncwarp();
@@ -340,8 +376,14 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
 
       if (MODE == MODE_NN) {
-        if (valid_row && best < kInf)
-          atomicMin(args.row_min_bits + row, __float_as_uint(fmaxf(best + nx, 0.f)));
+        if (valid_row) {
+          for (int k = 0; k < n_staged; k++) {
+            if (cand_val[k * 128 + etid] <= thr) {
+              const int pos = atomicAdd(args.cand_cnt + row, 1);
+              if (pos < args.cap) args.cand_idx[row * args.cap + pos] = cand_col[k * 128 + etid];
+            }
+          }
+        }
       } else if (MODE == MODE_LSE) {
         if (valid_row) {
           args.part_max[(int64_t)it.slot * args.m + row] = run_max;

@@ -174,12 +174,19 @@ __device__ __forceinline__ int kmnc_bucket(TA a_in, TS lo, TS jump, int k) {
   if (!(jump > (TS)0)) return -1;  // constant / inverted / NaN range: never covered
   const TC a = (TC)a_in;
   auto t = [&](int i) -> TC { return (TC)R::add(lo, R::mul(jump, (TS)i)); };  // NumPy: min + jumps*i
-  if (!(a >= t(0)) || !(a < t(k))) return -1;
-  double est = ((double)a_in - (double)lo) / (double)jump;
-  int i = est >= (double)(k - 1) ? k - 1 : (est <= 0.0 ? 0 : (int)est);
+  // cheap estimate of the section, then exact fix-up against the NumPy-rounded thresholds
+  int i;
+  if (sizeof(TA) == 4 && sizeof(TS) == 4) {
+    const float est = __fdividef((float)a_in - (float)lo, (float)jump);
+    i = est >= (float)(k - 1) ? k - 1 : (est > 0.f ? (int)est : 0);
+  } else {
+    const double est = ((double)a_in - (double)lo) / (double)jump;
+    i = est >= (double)(k - 1) ? k - 1 : (est > 0.0 ? (int)est : 0);
+  }
   while (i > 0 && a < t(i)) i--;
   while (i < k - 1 && a >= t(i + 1)) i++;
-  return i;
+  // i is now the only possible section; NaN / out-of-range values fail this test
+  return (a >= t(i) && a < t(i + 1)) ? i : -1;
 }
 
 template <typename TA, typename TS, typename TB>
@@ -209,48 +216,45 @@ __global__ void __launch_bounds__(256) kmnc_kernel(const TA* __restrict__ act, i
 }
 
 // float traces, float statistics, d % 4 == 0, 16-byte aligned: 128-bit loads, 64-bit stores.
+// One warp owns 128 consecutive neurons of one sample at a time (grid-stride over such chunks);
+// per-sample counts are accumulated with one atomic per chunk into a zeroed score array.
 template <typename TB>
 __global__ void __launch_bounds__(256) kmnc_vec4_kernel(const float* __restrict__ act, int64_t n, int64_t d,
                                                         const float* __restrict__ mins,
                                                         const float* __restrict__ jumps, int k,
                                                         TB* __restrict__ bucket, int32_t* __restrict__ score) {
-  __shared__ int warp_cnt[8];
+  const int lane = threadIdx.x & 31;
   const int64_t d4 = d >> 2;
-  for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
-    const float4* a4 = reinterpret_cast<const float4*>(act + row * d);
+  const int64_t cpr = (d4 + 31) >> 5;  // chunks per row
+  const int64_t total = n * cpr;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t chunk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); chunk < total; chunk += nwarps) {
+    const int64_t row = chunk / cpr;
+    const int64_t j = (chunk - row * cpr) * 32 + lane;
     int cnt = 0;
-    for (int64_t j = threadIdx.x; j < d4; j += 256) {
+    if (j < d4) {
       float4 v;
       asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                    : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                   : "l"(a4 + j));
+                   : "l"(reinterpret_cast<const float4*>(act + row * d) + j));
       const float4 lo = __ldg(reinterpret_cast<const float4*>(mins) + j);
       const float4 jp = __ldg(reinterpret_cast<const float4*>(jumps) + j);
       const int i0 = kmnc_bucket<float, float>(v.x, lo.x, jp.x, k);
       const int i1 = kmnc_bucket<float, float>(v.y, lo.y, jp.y, k);
       const int i2 = kmnc_bucket<float, float>(v.z, lo.z, jp.z, k);
       const int i3 = kmnc_bucket<float, float>(v.w, lo.w, jp.w, k);
-      cnt += (i0 >= 0) + (i1 >= 0) + (i2 >= 0) + (i3 >= 0);
+      cnt = (i0 >= 0) + (i1 >= 0) + (i2 >= 0) + (i3 >= 0);
       if (bucket) {
         TB* b = bucket + row * d + (j << 2);
         if (sizeof(TB) == 2) {
-          short4 o = make_short4((short)i0, (short)i1, (short)i2, (short)i3);
-          *reinterpret_cast<short4*>(b) = o;
+          *reinterpret_cast<short4*>(b) = make_short4((short)i0, (short)i1, (short)i2, (short)i3);
         } else {
-          int4 o = make_int4(i0, i1, i2, i3);
-          *reinterpret_cast<int4*>(b) = o;
+          *reinterpret_cast<int4*>(b) = make_int4(i0, i1, i2, i3);
         }
       }
     }
     cnt = warp_sum(cnt);
-    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int s = 0;
-      for (int w = 0; w < 8; w++) s += warp_cnt[w];
-      score[row] = s;
-    }
-    __syncthreads();
+    if (lane == 0 && cnt) atomicAdd(score + row, cnt);
   }
 }
 
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(256) kde_combine_kernel(const float* __restric
   if (mx > -INFINITY)
     for (int s = 0; s < slots; s++) {
       const float v = pm[(int64_t)s * m + row];
-      if (v > -INFINITY) sum += ps[(int64_t)s * m + row] * __expf(v - mx);
+      if (v > -INFINITY) sum += ps[(int64_t)s * m + row] * expf(v - mx);
     }
   om[row] = mx;
   os[row] = sum;
@@ -470,7 +474,9 @@ extern "C" int tip_kmnc(const void* act, int act_dtype, int64_t n, int64_t d, co
     const bool aligned = (d % 4 == 0) && (((uintptr_t)act | (uintptr_t)mins | (uintptr_t)jumps) & 15) == 0 &&
                          (bucket == nullptr || ((uintptr_t)bucket & 15) == 0);
     if (aligned) {
-      const int grid = (int)std::min<int64_t>(n, (int64_t)sm_count() * 8);
+      TIP_CHECK_CUDA(cudaMemsetAsync(score, 0, (size_t)n * sizeof(int32_t), st));
+      const int64_t chunks = n * (((d >> 2) + 31) >> 5);
+      const int grid = (int)std::min<int64_t>((chunks + 7) / 8, (int64_t)sm_count() * 8);
       if (bucket == nullptr || bucket_dtype == TIP_I16)
         kmnc_vec4_kernel<int16_t><<<grid, 256, 0, st>>>((const float*)act, n, d, (const float*)mins,
                                                         (const float*)jumps, sections, (int16_t*)bucket, score);

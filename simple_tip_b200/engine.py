@@ -28,6 +28,10 @@ from . import _lib
 
 DEFAULT_CAP = 64
 
+# bench.py sets this to a list to collect (kernel name, algorithmic flops, start event, end event)
+# around the tensor-core launches; None (default) records nothing.
+PROFILE = None
+
 
 # ------------------------------------------------------------------------------------------
 # plumbing
@@ -273,9 +277,19 @@ class NnEngine:
                 row_min = torch.full((m,), 0x7F800000, dtype=torch.int32, device=self.dev)
                 cand_cnt = torch.zeros(m, dtype=torch.int32, device=self.dev)
                 cand_idx = torch.empty((m, self.cap), dtype=torch.int32, device=self.dev)
+                ev = None
+                if PROFILE is not None:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
                 _lib.check(lib.tip_nn_filter(_p(q_pack), _p(q_sq), m, _p(self.t_pack), self.n, self.d, self.pitch,
                                              _p(items_dev), items.shape[0], self.rmax, _p(row_min), _p(cand_idx),
                                              _p(cand_cnt), self.cap, _stream()), "tip_nn_filter")
+                if ev is not None:
+                    ev[1].record()
+                    pairs = sum(int(q_off[c + 1] - q_off[c]) * sum(int(hi) - int(lo) for lo, hi in ranges[c])
+                                for c in range(self.num_classes))
+                    name = "nn_filter_same_class" if mode == _lib.RANGE_SAME_CLASS else "nn_filter_other_classes"
+                    PROFILE.append((name, 2.0 * self.d * pairs, ev[0], ev[1]))
         _lib.check(lib.tip_nn_rerank(_p(q), _p(self.t), tip_dtype(q.dtype), m, self.n, self.d, _p(cand_idx),
                                      _p(cand_cnt), self.cap, _p(q_class), _p(self.class_off_dev), self.num_classes,
                                      mode, _p(self.t_gid), _p(out_dist), _p(out_pos), _p(self.stats), _stream()),
@@ -297,7 +311,10 @@ def dsa_distances(engine: NnEngine, x: torch.Tensor, q_class: torch.Tensor, q_of
     """surprise.py:615-631 for class-sorted queries x: (dist_a, dist_b, winner original index)."""
     dist_a, pos_a = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter)
     winners = engine.gather(pos_a)
-    gid = torch.where(pos_a >= 0, engine.t_gid[pos_a.clamp(min=0).long()], torch.full_like(pos_a, -1))
+    if engine.n > 0:
+        gid = torch.where(pos_a >= 0, engine.t_gid[pos_a.clamp(min=0).long()], torch.full_like(pos_a, -1))
+    else:
+        gid = torch.full_like(pos_a, -1)
     if comm is not None and comm.world > 1:
         dist_a, gid64, winners = comm.reduce_winners(dist_a, gid, winners)
         gid = gid64
