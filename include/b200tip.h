@@ -109,9 +109,10 @@ int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d, const flo
 /* ---- nearest-neighbour candidate filter (tcgen05 + TMA) ------------------------------
  * q_pack: m x pitch, t_pack: n x pitch (tip_pair_prep, scale=-2, norm_coef=1).
  * For every query row and every work item covering it, scans the item's train span and
- * appends to cand_idx[row*cap + k] every train row whose approximate squared distance is
- * within the proven error window of the running minimum; cand_cnt[row]
- * counts appends (may exceed cap: overflow -> tip_nn_rerank falls back to an exact scan).
+ * appends to cand_idx[row*cap + k] the first row of every group of 8 consecutive train rows
+ * that contains a row whose approximate squared distance is within the proven error window of
+ * the running minimum; cand_cnt[row] counts appends (may exceed cap:
+ * overflow -> tip_nn_rerank falls back to an exact scan).
  * row_min_bits[m] (uint32 float bits, initialised to +inf = 0x7f800000 by the caller) carries
  * the running minimum across items/CTAs.  t_rmax = max_j |h(y_j)| over the train rows. */
 int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const void* t_pack,
@@ -122,7 +123,8 @@ int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const vo
 /* ---- exact re-rank (NumPy-order distances, first-occurrence argmin) -------------------
  * q, t: original-dtype (TIP_F32/TIP_F64) matrices m x d and n x d; train rows are grouped by
  * class (class_off[C+1]); q_class[m] gives each query's class, mode the column range.
- * Rows with 1..cap candidates are re-ranked over their candidates; rows with 0 or > cap
+ * Rows with 1..cap candidate groups (8 consecutive train rows each, clipped to the class range)
+ * are re-ranked over those rows; rows with 0 or > cap
  * candidates (or cand_cnt == NULL) are scanned exhaustively over their range.
  * out_dist[m] (dtype) = sqrt(pairwise_sum((x-y)^2)) of the winner, out_pos[m] = its train row
  * (ties: lowest t_gid), stats[0] += exhaustive rows, stats[1] += candidates evaluated. */
@@ -144,7 +146,9 @@ int tip_whiten(const void* x, int dtype, int64_t m, int64_t d_in, const int32_t*
 
 /* q_pack / t_pack from tip_pair_prep(segments=3, scale=1, norm_coef=-0.5 on the train side).
  * For every work item writes the partial (max_i a_ij, sum_i exp(a_ij - max)) of
- * a_ij = <p_i, q_j> - |p_i|^2/2 over the item's span into part_max/part_sum[slot*m + row]. */
+ * a_ij = <p_i, q_j> - |p_i|^2/2 over the item's span into part_max/part_sum[(2*slot+h)*m + row],
+ * h = 0/1 for the two 128-column halves of the 256-wide tiles (so 2*slots*m floats each, which
+ * the caller initialises to -inf / 0). */
 int tip_kde_lse(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d,
                 int64_t pitch, const tip_work_item* items, int32_t n_items, float* part_max,
                 float* part_sum, void* stream);

@@ -314,6 +314,7 @@ class DSA(SA):
         self.class_matrix = self._class_matrix()
         self.badge_size = badge_size          # kept for API compatibility; tiles replace badges
         self.use_filter = os.environ.get("B200TIP_DSA_EXHAUSTIVE", "0") != "1"
+        self.use_graphs = os.environ.get("B200TIP_GRAPHS", "1") != "0"   # CUDA-graph replay of the search
         self._comm = comm
         self._engine = None
         self._build_engine()
@@ -363,13 +364,24 @@ class DSA(SA):
         dev = eng.dev
         x_all = E.to_device(target_ats, dev)
         idx = torch.from_numpy(order).to(dev, non_blocking=True)
-        x = x_all.index_select(0, idx)
-        q_class = torch.from_numpy(target_pred[order].astype(np.int32)).to(dev, non_blocking=True)
-        dist_a, dist_b, gid = E.dsa_distances(eng, x, q_class, q_off, self._comm, self.use_filter)
-        a = dist_a.cpu().numpy()
-        b = dist_b.cpu().numpy()
+        sharded = self._comm is not None and self._comm.world > 1
+        if self.use_graphs and not sharded:
+            # steady state: gather straight into the captured graph's input, one replay, one D2H
+            plan = E.dsa_plan(eng, int(order.size), q_off, x_all.dtype, self.use_filter)
+            torch.index_select(x_all, 0, idx, out=plan.x)
+            res = plan.run().cpu().numpy()
+            a = res[0].astype(self._compute_dtype)
+            b = res[1].astype(self._compute_dtype)
+            gid_host = res[2].astype(np.int64)
+        else:
+            x = x_all.index_select(0, idx)
+            q_class = torch.from_numpy(target_pred[order].astype(np.int32)).to(dev, non_blocking=True)
+            dist_a, dist_b, gid = E.dsa_distances(eng, x, q_class, q_off, self._comm, self.use_filter)
+            a = dist_a.cpu().numpy()
+            b = dist_b.cpu().numpy()
+            gid_host = gid.cpu().numpy()
         self.last_winner_index = np.full(target_pred.shape[0], -1, dtype=np.int64)
-        self.last_winner_index[order] = gid.cpu().numpy()
+        self.last_winner_index[order] = gid_host
         self.last_dist_a = np.full(target_pred.shape[0], np.nan, dtype=a.dtype)
         self.last_dist_b = np.full(target_pred.shape[0], np.nan, dtype=a.dtype)
         self.last_dist_a[order], self.last_dist_b[order] = a, b

@@ -125,6 +125,64 @@ __device__ T np_sumsq(const T* __restrict__ x, const T* __restrict__ y, int n) {
   return vals[0];
 }
 
+// ---- the same sums, computed cooperatively by a group of 8 consecutive lanes ----------------
+// Lane `sub` (0..7) owns NumPy's stride-8 accumulator r[sub]; the tree
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is three xor-shuffles (IEEE addition is commutative, so
+// every lane of the group ends with the same bits).  All 32 lanes of the warp must call this
+// with the same n (four independent groups per warp).
+template <typename T>
+__device__ __forceinline__ T np_leaf_sumsq_g8(const T* __restrict__ x, const T* __restrict__ y, int n, int sub) {
+  using R = Rn<T>;
+  auto term = [&](int i) -> T {
+    T d = R::sub(x[i], y[i]);
+    return R::mul(d, d);
+  };
+  if (n < 8) {
+    T res = (T)0;
+    for (int i = 0; i < n; i++) res = R::add(res, term(i));
+    return res;
+  }
+  T r = term(sub);
+  int i = 8;
+  const int lim = n - (n % 8);
+  // loads/squares of four steps are independent of the (ordered) accumulation: batch them
+  for (; i + 24 < lim; i += 32) {
+    const T t0 = term(i + sub), t1 = term(i + 8 + sub), t2 = term(i + 16 + sub), t3 = term(i + 24 + sub);
+    r = R::add(R::add(R::add(R::add(r, t0), t1), t2), t3);
+  }
+  for (; i < lim; i += 8) r = R::add(r, term(i + sub));
+  r = R::add(r, __shfl_xor_sync(0xffffffffu, r, 1));
+  r = R::add(r, __shfl_xor_sync(0xffffffffu, r, 2));
+  r = R::add(r, __shfl_xor_sync(0xffffffffu, r, 4));
+  for (; i < n; i++) r = R::add(r, term(i));
+  return r;
+}
+
+template <typename T>
+__device__ T np_sumsq_g8(const T* __restrict__ x, const T* __restrict__ y, int n, int sub) {
+  if (n <= 128) return np_leaf_sumsq_g8<T>(x, y, n, sub);
+  int off[32], len[32];
+  unsigned char phase[32];
+  T vals[32];
+  int sp = 1, vp = 0;
+  off[0] = 0; len[0] = n; phase[0] = 0;
+  while (sp > 0) {
+    const int top = sp - 1;
+    const int o = off[top], l = len[top];
+    if (l <= 128) {
+      vals[vp++] = np_leaf_sumsq_g8<T>(x + o, y + o, l, sub);
+      sp--;
+    } else {
+      int n2 = l / 2;
+      n2 -= n2 % 8;
+      if (phase[top] == 0) { phase[top] = 1; off[sp] = o; len[sp] = n2; phase[sp] = 0; sp++; }
+      else if (phase[top] == 1) { phase[top] = 2; off[sp] = o + n2; len[sp] = l - n2; phase[sp] = 0; sp++; }
+      else { const T r = vals[--vp]; const T a = vals[--vp]; vals[vp++] = Rn<T>::add(a, r); sp--; }
+    }
+  }
+  return vals[0];
+}
+
 __device__ __forceinline__ float warp_min(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;

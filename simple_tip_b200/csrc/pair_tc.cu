@@ -10,8 +10,9 @@
 //   MODE_LSE  per-row online log-sum-exp (LSA / Gaussian KDE, scipy 1.4.1 gaussian_kernel_estimate)
 //   MODE_DUMP raw accumulator tile (bring-up / validation)
 //
-// Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one
-// lane), warps 2..5 = epilogue (TMEM lane quadrant = warp % 4, one query row per thread).
+// Roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one
+// lane), warps 2..9 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp-2)/4; one
+// query row x 128 columns per thread, TMEM loads software-pipelined against the reduction).
 // Pipelines: 4-stage smem ring (full/empty mbarriers, TMA -> MMA) and a 2-deep TMEM accumulator
 // ring (2 x 256 columns, MMA -> epilogue).
 #include <cuda.h>
@@ -29,9 +30,10 @@ constexpr int kStages = 4;
 constexpr int kABytes = BM * BK * 2;
 constexpr int kBBytes = BN * BK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kThreads = 192;
+constexpr int kEpiThreads = 256;             // 8 epilogue warps
+constexpr int kThreads = 64 + kEpiThreads;   // + TMA warp + MMA warp
 constexpr int kCandSlots = 8;   // per-query staging slots for candidates (MODE_NN)
-constexpr int kCandBytes = kCandSlots * 128 * 8;
+constexpr int kCandBytes = kCandSlots * 256 * 8;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kCandBytes;
 constexpr uint32_t kTmemCols = 512;
 
@@ -141,6 +143,127 @@ __device__ __forceinline__ float nn_threshold(float s, float nx, float e2, float
   return thr + fabsf(thr) * 1e-6f + 1e-30f;
 }
 
+struct EpiState {
+  bool valid_row;
+  int64_t row;
+  int col1;
+  float nx, e2, g, best, thr, s_ref;   // MODE_NN
+  int n_staged;
+  float run_max, run_sum;              // MODE_LSE
+};
+struct EpiShared {
+  float* cand_val;
+  int* cand_col;
+  int etid;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Reduce 32 accumulator columns [cbase, cbase+32) of one query row.
+template <int MODE>
+__device__ __forceinline__ void epi_chunk(const PairArgs& args, EpiState& st, const EpiShared& sh, uint32_t (&r)[32],
+                                          int cbase, bool partial, bool dump_tile, int row_local, int dump_col) {
+  const float kInf = __int_as_float(0x7f800000);
+  if (MODE == MODE_DUMP) {
+    if (dump_tile) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) args.dump[(int64_t)row_local * BN + dump_col + j] = __uint_as_float(r[j]);
+    }
+  } else if (MODE == MODE_NN) {
+    // Candidates are tracked per group of 8 consecutive train rows: one min per group, so the
+    // (frequent: 32 independent queries per warp) event path is a few dozen instructions.  The
+    // re-rank evaluates all rows of a surviving group exactly.
+    if (partial) {
+#pragma unroll
+      for (int j = 0; j < 32; j++)
+        if (cbase + j >= st.col1) r[j] = 0x7f800000u;
+    }
+    float gmin[4];
+#pragma unroll
+    for (int gi = 0; gi < 4; gi++) {
+      const float a0 = fminf(__uint_as_float(r[8 * gi + 0]), __uint_as_float(r[8 * gi + 1]));
+      const float a1 = fminf(__uint_as_float(r[8 * gi + 2]), __uint_as_float(r[8 * gi + 3]));
+      const float a2 = fminf(__uint_as_float(r[8 * gi + 4]), __uint_as_float(r[8 * gi + 5]));
+      const float a3 = fminf(__uint_as_float(r[8 * gi + 6]), __uint_as_float(r[8 * gi + 7]));
+      gmin[gi] = fminf(fminf(a0, a1), fminf(a2, a3));
+    }
+    const float mn = fminf(fminf(gmin[0], gmin[1]), fminf(gmin[2], gmin[3]));
+    if (st.valid_row && mn <= st.thr && mn < kInf) {
+      if (mn < st.best) {
+        st.best = mn;
+        st.s_ref = fminf(st.s_ref, fmaxf(st.best + st.nx, 0.f));
+        st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
+      }
+#pragma unroll 1
+      for (int gi = 0; gi < 4; gi++) {
+        const float v = gi == 0 ? gmin[0] : (gi == 1 ? gmin[1] : (gi == 2 ? gmin[2] : gmin[3]));
+        if (v <= st.thr) {
+          if (st.n_staged == kCandSlots) {   // compact against the (tighter) current threshold
+            int keep = 0;
+            for (int k = 0; k < kCandSlots; k++) {
+              const float sv = sh.cand_val[k * kEpiThreads + sh.etid];
+              if (sv <= st.thr) {
+                sh.cand_val[keep * kEpiThreads + sh.etid] = sv;
+                sh.cand_col[keep * kEpiThreads + sh.etid] = sh.cand_col[k * kEpiThreads + sh.etid];
+                keep++;
+              }
+            }
+            st.n_staged = keep;
+          }
+          if (st.n_staged < kCandSlots) {
+            sh.cand_val[st.n_staged * kEpiThreads + sh.etid] = v;
+            sh.cand_col[st.n_staged * kEpiThreads + sh.etid] = cbase + 8 * gi;
+            st.n_staged++;
+          } else {                           // staging full of live groups: emit directly
+            const int pos = atomicAdd(args.cand_cnt + st.row, 1);
+            if (pos < args.cap) args.cand_idx[st.row * args.cap + pos] = cbase + 8 * gi;
+          }
+        }
+      }
+    }
+  } else {  // MODE_LSE
+    constexpr float kL2e = 1.4426950408889634f;
+    float mx = -kInf;
+    if (partial) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const float v = (cbase + j < st.col1) ? __uint_as_float(r[j]) : -kInf;
+        r[j] = __float_as_uint(v);
+        mx = fmaxf(mx, v);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+    }
+    if (mx > st.run_max) {
+      st.run_sum *= fast_exp2((st.run_max - mx) * kL2e);  // run_max = -inf -> factor 0
+      st.run_max = mx;
+    }
+    if (st.run_max > -kInf) {
+      const float off = -st.run_max * kL2e;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        s0 += fast_exp2(fmaf(__uint_as_float(r[j + 0]), kL2e, off));
+        s1 += fast_exp2(fmaf(__uint_as_float(r[j + 1]), kL2e, off));
+        s2 += fast_exp2(fmaf(__uint_as_float(r[j + 2]), kL2e, off));
+        s3 += fast_exp2(fmaf(__uint_as_float(r[j + 3]), kL2e, off));
+      }
+      st.run_sum += (s0 + s1) + (s2 + s3);
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PairArgs args) {
@@ -161,7 +284,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiThreads / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -233,161 +356,102 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     __syncwarp();
   } else {
-    // ================= epilogue (one query row per thread) =================
+    // ================= epilogue =================
+    // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.
+    // One thread = one query row x one 128-column half of every tile; the two halves of a row
+    // never talk to each other except through row_min_bits (like CTAs on different spans do).
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_local = quad * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int etid = threadIdx.x - 64;   // 0..127 among the epilogue threads
-    float* cand_val = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
-    int* cand_col = reinterpret_cast<int*>(cand_val + kCandSlots * 128);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (BN / 2));
+    const int etid = threadIdx.x - 64;   // 0..255 among the epilogue threads
+    EpiShared sh;
+    sh.cand_val = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
+    sh.cand_col = reinterpret_cast<int*>(sh.cand_val + kCandSlots * kEpiThreads);
+    sh.etid = etid;
     int acc = 0;
     uint32_t acc_phase = 0;
     const float kInf = __int_as_float(0x7f800000);
     for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
       const tip_work_item it = args.items[w];
       const int ntiles = (it.col1 - it.col0 + BN - 1) / BN;
-      const bool valid_row = row_local < it.q_rows;
-      const int64_t row = (int64_t)it.q_row0 + row_local;
-
-      // ---- per-item state ----
-      float nx = 0.f, e2 = 0.f, g = 0.f, best = kInf, thr = kInf;  // MODE_NN
-      float run_max = -kInf, run_sum = 0.f;                          // MODE_LSE
-      float s_ref = kInf;   // smallest approximate squared distance known for this query (any CTA)
-      int n_staged = 0;
-      if (MODE == MODE_NN && valid_row) {
-        nx = args.q_sqnorm[row];
-        const float r = sqrtf(nx) + args.rmax;
-        e2 = args.eps2 * r;
-        g = args.gamma * r * r;
-        s_ref = __uint_as_float(*(volatile uint32_t*)(args.row_min_bits + row));
-        thr = nn_threshold(s_ref, nx, e2, g);
+      EpiState st;
+      st.valid_row = row_local < it.q_rows;
+      st.row = (int64_t)it.q_row0 + row_local;
+      st.nx = 0.f; st.e2 = 0.f; st.g = 0.f; st.best = kInf; st.thr = kInf; st.s_ref = kInf; st.n_staged = 0;
+      st.run_max = -kInf; st.run_sum = 0.f;
+      st.col1 = it.col1;
+      if (MODE == MODE_NN && st.valid_row) {
+        st.nx = args.q_sqnorm[st.row];
+        const float r = sqrtf(st.nx) + args.rmax;
+        st.e2 = args.eps2 * r;
+        st.g = args.gamma * r * r;
+        st.s_ref = __uint_as_float(ld_volatile_u32(args.row_min_bits + st.row));
+        st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
       }
 
       for (int t = 0; t < ntiles; t++) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        const int tile_col0 = it.col0 + t * BN;
-        const bool partial = tile_col0 + BN > it.col1;
-#pragma unroll 1
-        for (int qd = 0; qd < BN / 32; qd++) {
-          uint32_t r[32];
-          tmem_ld32(lane_addr + (uint32_t)(acc * BN + qd * 32), r);
-          tmem_wait_ld();
-          const int cbase = tile_col0 + qd * 32;
-          if (MODE == MODE_DUMP) {
-            if (w == 0 && t == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j++) args.dump[(int64_t)row_local * BN + qd * 32 + j] = __uint_as_float(r[j]);
-            }
-          } else if (MODE == MODE_NN) {
-            float mn = kInf;
-            if (partial) {
-#pragma unroll
-              for (int j = 0; j < 32; j++) {
-                const float v = (cbase + j < it.col1) ? __uint_as_float(r[j]) : kInf;
-                r[j] = __float_as_uint(v);
-                mn = fminf(mn, v);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) mn = fminf(mn, fminf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
-            }
-            if (valid_row && mn <= thr) {
-#pragma unroll
-              for (int j = 0; j < 32; j++) {
-                const float v = __uint_as_float(r[j]);
-                if (v <= thr && v < kInf) {
-                  if (v < best) {
-                    best = v;
-                    s_ref = fminf(s_ref, fmaxf(best + nx, 0.f));
-                    thr = nn_threshold(s_ref, nx, e2, g);
-                  }
-                  if (n_staged == kCandSlots) {   // compact against the (tighter) current threshold
-                    int keep = 0;
-                    for (int k = 0; k < kCandSlots; k++) {
-                      const float sv = cand_val[k * 128 + etid];
-                      if (sv <= thr) {
-                        cand_val[keep * 128 + etid] = sv;
-                        cand_col[keep * 128 + etid] = cand_col[k * 128 + etid];
-                        keep++;
-                      }
-                    }
-                    n_staged = keep;
-                  }
-                  if (n_staged < kCandSlots) {
-                    cand_val[n_staged * 128 + etid] = v;
-                    cand_col[n_staged * 128 + etid] = cbase + j;
-                    n_staged++;
-                  } else {                        // staging full of live candidates: emit directly
-                    const int pos = atomicAdd(args.cand_cnt + row, 1);
-                    if (pos < args.cap) args.cand_idx[row * args.cap + pos] = cbase + j;
-                  }
-                }
-              }
-            }
-          } else {  // MODE_LSE
-            constexpr float kL2e = 1.4426950408889634f;
-            float mx = -kInf;
-            if (partial) {
-#pragma unroll
-              for (int j = 0; j < 32; j++) {
-                const float v = (cbase + j < it.col1) ? __uint_as_float(r[j]) : -kInf;
-                r[j] = __float_as_uint(v);
-                mx = fmaxf(mx, v);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
-            }
-            if (mx > run_max) {
-              run_sum *= exp2f((run_max - mx) * kL2e);  // run_max = -inf -> factor 0
-              run_max = mx;
-            }
-            if (run_max > -kInf) {
-              const float off = -run_max * kL2e;
-              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                s0 += exp2f(fmaf(__uint_as_float(r[j + 0]), kL2e, off));
-                s1 += exp2f(fmaf(__uint_as_float(r[j + 1]), kL2e, off));
-                s2 += exp2f(fmaf(__uint_as_float(r[j + 2]), kL2e, off));
-                s3 += exp2f(fmaf(__uint_as_float(r[j + 3]), kL2e, off));
-              }
-              run_sum += (s0 + s1) + (s2 + s3);
-            }
-          }
-        }
-        if (MODE == MODE_NN && valid_row) {
-          // share the running minimum across CTAs scanning other spans for the same query
-          const float mine = fmaxf(best + nx, 0.f);
-          const float seen = __uint_as_float(*(volatile uint32_t*)(args.row_min_bits + row));
-          if (mine < seen) atomicMin(args.row_min_bits + row, __float_as_uint(mine));
-          if (seen < s_ref) {
-            s_ref = seen;
-            thr = nn_threshold(s_ref, nx, e2, g);
-          }
-        }
-        // accumulator drained: hand the TMEM stage back to the MMA warp
+        const int col_base = it.col0 + t * BN + half * (BN / 2);
+        const bool partial = col_base + BN / 2 > it.col1;
+        uint32_t seen_bits = 0x7f800000u;
+        if (MODE == MODE_NN && st.valid_row) seen_bits = ld_volatile_u32(args.row_min_bits + st.row);
+        const uint32_t taddr = lane_addr + (uint32_t)(acc * BN);
+        // software pipeline over the 4 x 32 columns of this half: the TMEM load of chunk q+1 is in
+        // flight while chunk q is reduced
+        uint32_t ra[32], rb[32];
+        tmem_ld32(taddr, ra);
+        tmem_wait_ld();
+        tmem_ld32(taddr + 32, rb);
+        epi_chunk<MODE>(args, st, sh, ra, col_base, partial, w == 0 && t == 0, row_local, half * (BN / 2));
+        tmem_wait_ld();
+        tmem_ld32(taddr + 64, ra);
+        epi_chunk<MODE>(args, st, sh, rb, col_base + 32, partial, w == 0 && t == 0, row_local, half * (BN / 2) + 32);
+        tmem_wait_ld();
+        tmem_ld32(taddr + 96, rb);
+        epi_chunk<MODE>(args, st, sh, ra, col_base + 64, partial, w == 0 && t == 0, row_local, half * (BN / 2) + 64);
+        tmem_wait_ld();
+        // accumulator drained into registers: hand the TMEM stage back to the MMA warp early
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
+        epi_chunk<MODE>(args, st, sh, rb, col_base + 96, partial, w == 0 && t == 0, row_local, half * (BN / 2) + 96);
+
+        if (MODE == MODE_NN && st.valid_row) {
+          // share the running minimum across everybody scanning other columns for the same query
+          const float mine = fmaxf(st.best + st.nx, 0.f);
+          const float seen = __uint_as_float(seen_bits);
+          if (mine < seen) atomicMin(args.row_min_bits + st.row, __float_as_uint(mine));
+          if (seen < st.s_ref) {
+            st.s_ref = seen;
+            st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
+          }
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
 
       if (MODE == MODE_NN) {
-        if (valid_row) {
-          for (int k = 0; k < n_staged; k++) {
-            if (cand_val[k * 128 + etid] <= thr) {
-              const int pos = atomicAdd(args.cand_cnt + row, 1);
-              if (pos < args.cap) args.cand_idx[row * args.cap + pos] = cand_col[k * 128 + etid];
+        if (st.valid_row) {
+          // other CTAs / halves have been scanning other columns of this query meanwhile: only
+          // flush the groups that survive the best bound known by now
+          const float seen = __uint_as_float(ld_volatile_u32(args.row_min_bits + st.row));
+          if (seen < st.s_ref) {
+            st.s_ref = seen;
+            st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
+          }
+          for (int k = 0; k < st.n_staged; k++) {
+            if (sh.cand_val[k * kEpiThreads + etid] <= st.thr) {
+              const int pos = atomicAdd(args.cand_cnt + st.row, 1);
+              if (pos < args.cap) args.cand_idx[st.row * args.cap + pos] = sh.cand_col[k * kEpiThreads + etid];
             }
           }
         }
       } else if (MODE == MODE_LSE) {
-        if (valid_row) {
-          args.part_max[(int64_t)it.slot * args.m + row] = run_max;
-          args.part_sum[(int64_t)it.slot * args.m + row] = run_sum;
+        if (st.valid_row) {
+          args.part_max[(int64_t)(it.slot * 2 + half) * args.m + st.row] = st.run_max;
+          args.part_sum[(int64_t)(it.slot * 2 + half) * args.m + st.row] = st.run_sum;
         }
       }
     }

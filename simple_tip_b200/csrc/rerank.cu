@@ -14,6 +14,7 @@
 namespace tip {
 
 constexpr int kRerankThreads = 128;
+constexpr int kCandGroup = 8;   // must match the group size of the filter epilogue (pair_tc.cu)
 
 template <typename T>
 struct Best {
@@ -38,12 +39,20 @@ rerank_kernel(const T* __restrict__ q, const T* __restrict__ t, int64_t m, int64
               const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_cnt, int cap,
               const int32_t* __restrict__ q_class, const int32_t* __restrict__ class_off, int n_classes,
               int mode, const int32_t* __restrict__ t_gid, T* __restrict__ out_dist,
-              int32_t* __restrict__ out_pos, unsigned long long* __restrict__ stats) {
+              int32_t* __restrict__ out_pos, unsigned long long* __restrict__ stats, bool xs_ok) {
   __shared__ T s_dist[kRerankThreads];
   __shared__ int s_gid[kRerankThreads];
   __shared__ int s_pos[kRerankThreads];
+  extern __shared__ __align__(16) unsigned char rerank_smem[];
+  T* xs = reinterpret_cast<T*>(rerank_smem);
   for (int64_t row = blockIdx.x; row < m; row += gridDim.x) {
-    const T* x = q + row * (int64_t)d;
+    const T* xg = q + row * (int64_t)d;
+    const T* x = xg;
+    if (xs_ok) {                       // query row reused by every candidate: keep it on chip
+      for (int i = threadIdx.x; i < d; i += kRerankThreads) xs[i] = xg[i];
+      __syncthreads();
+      x = xs;
+    }
     Best<T> best;
     best.dist = Rn<T>::inf();
     best.gid = 0x7fffffff;
@@ -51,28 +60,41 @@ rerank_kernel(const T* __restrict__ q, const T* __restrict__ t, int64_t m, int64
     const int cnt = cand_cnt ? cand_cnt[row] : 0;
     const int cls = q_class ? q_class[row] : 0;
     const bool listed = cand_cnt != nullptr && cnt >= 1 && cnt <= cap;
-    if (listed) {
-      for (int k = threadIdx.x; k < cnt; k += kRerankThreads) {
-        const int j = cand_idx[row * (int64_t)cap + k];
-        if (j < 0 || j >= n) continue;
-        const T s = np_sumsq<T>(x, t + (int64_t)j * d, d);
-        consider(best, Rn<T>::sqrt(s), t_gid ? t_gid[j] : j, j);
+    const int sub = threadIdx.x & 7;            // lane inside its 8-lane group
+    const int grp = threadIdx.x >> 3;           // 16 groups per block, one train row each
+    constexpr int kGroups = kRerankThreads / 8;
+    if (listed && cls >= 0 && cls < n_classes) {
+      // every candidate names a group of kCandGroup consecutive train rows (clipped to the
+      // class range it starts in)
+      const int c0 = class_off[cls], c1 = class_off[cls + 1], cn = class_off[n_classes];
+      const int total = cnt * kCandGroup;
+      for (int base = 0; base < total; base += kGroups) {
+        const int k = base + grp;
+        bool ok = k < total;
+        int j = 0;
+        if (ok) {
+          const int start = cand_idx[row * (int64_t)cap + k / kCandGroup];
+          j = start + (k % kCandGroup);
+          const int limit = mode == TIP_RANGE_SAME_CLASS ? c1 : (start < c0 ? c0 : cn);
+          ok = start >= 0 && j < limit && j < n;
+          if (!ok) j = 0;
+        }
+        const T s = np_sumsq_g8<T>(x, t + (int64_t)j * d, d, sub);
+        if (ok && sub == 0) consider(best, Rn<T>::sqrt(s), t_gid ? t_gid[j] : j, j);
       }
       if (threadIdx.x == 0 && stats) atomicAdd(stats + 1, (unsigned long long)cnt);
-    } else if (cls >= 0 && cls < n_classes) {
+    } else if (cls >= 0 && cls < n_classes && n > 0) {
       const int c0 = class_off[cls], c1 = class_off[cls + 1], cn = class_off[n_classes];
       // SAME_CLASS: [c0, c1);  OTHER_CLASSES: [0, c0) U [c1, cn)
-      const int lo0 = mode == TIP_RANGE_SAME_CLASS ? c0 : 0;
-      const int hi0 = mode == TIP_RANGE_SAME_CLASS ? c1 : c0;
-      const int lo1 = mode == TIP_RANGE_SAME_CLASS ? 0 : c1;
-      const int hi1 = mode == TIP_RANGE_SAME_CLASS ? 0 : cn;
-      for (int j = lo0 + threadIdx.x; j < hi0; j += kRerankThreads) {
-        const T s = np_sumsq<T>(x, t + (int64_t)j * d, d);
-        consider(best, Rn<T>::sqrt(s), t_gid ? t_gid[j] : j, j);
-      }
-      for (int j = lo1 + threadIdx.x; j < hi1; j += kRerankThreads) {
-        const T s = np_sumsq<T>(x, t + (int64_t)j * d, d);
-        consider(best, Rn<T>::sqrt(s), t_gid ? t_gid[j] : j, j);
+      const int lo[2] = {mode == TIP_RANGE_SAME_CLASS ? c0 : 0, mode == TIP_RANGE_SAME_CLASS ? 0 : c1};
+      const int hi[2] = {mode == TIP_RANGE_SAME_CLASS ? c1 : c0, mode == TIP_RANGE_SAME_CLASS ? 0 : cn};
+      for (int rg = 0; rg < 2; rg++) {
+        for (int base = lo[rg]; base < hi[rg]; base += kGroups) {
+          const int j = base + grp;
+          const bool ok = j < hi[rg];
+          const T s = np_sumsq_g8<T>(x, t + (int64_t)(ok ? j : lo[rg]) * d, d, sub);
+          if (ok && sub == 0) consider(best, Rn<T>::sqrt(s), t_gid ? t_gid[j] : j, j);
+        }
       }
       if (threadIdx.x == 0 && stats) atomicAdd(stats + 0, 1ULL);
     }
@@ -116,15 +138,18 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
   if (m == 0) return TIP_OK;
   const int grid = (int)std::min<int64_t>(m, (int64_t)sm_count() * 16);
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t elem = dtype == TIP_F64 ? 8 : 4;
+  const bool xs_ok = (size_t)d * elem <= 32 * 1024;
+  const size_t xs_bytes = xs_ok ? (size_t)d * elem : 0;
   if (dtype == TIP_F32)
-    rerank_kernel<float><<<grid, kRerankThreads, 0, st>>>((const float*)q, (const float*)t, m, n, (int)d, cand_idx,
+    rerank_kernel<float><<<grid, kRerankThreads, xs_bytes, st>>>((const float*)q, (const float*)t, m, n, (int)d, cand_idx,
                                                           cand_cnt, cap, q_class, class_off, n_classes, mode, t_gid,
-                                                          (float*)out_dist, out_pos, (unsigned long long*)stats);
+                                                          (float*)out_dist, out_pos, (unsigned long long*)stats, xs_ok);
   else if (dtype == TIP_F64)
-    rerank_kernel<double><<<grid, kRerankThreads, 0, st>>>((const double*)q, (const double*)t, m, n, (int)d,
+    rerank_kernel<double><<<grid, kRerankThreads, xs_bytes, st>>>((const double*)q, (const double*)t, m, n, (int)d,
                                                            cand_idx, cand_cnt, cap, q_class, class_off, n_classes,
                                                            mode, t_gid, (double*)out_dist, out_pos,
-                                                           (unsigned long long*)stats);
+                                                           (unsigned long long*)stats, xs_ok);
   else
     TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
   TIP_LAUNCH_CHECK();
