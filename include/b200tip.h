@@ -59,10 +59,11 @@ typedef enum tip_dtype {
 #define TIP_RANGE_SAME_CLASS 0   /* columns [off[c], off[c+1])                      */
 #define TIP_RANGE_OTHER_CLASSES 1 /* columns [0, off[c]) U [off[c+1], off[C])       */
 
-/* One unit of work of the tensor-core pass: 128 query rows x a span of train rows. */
+/* One unit of work of the tensor-core pass: a tile of query rows (128, or 256 for
+ * tip_nn_filter on short traces, see tip_nn_filter_tile) x a span of train rows. */
 typedef struct tip_work_item {
-  int32_t q_row0;  /* first query row of the 128-row tile                          */
-  int32_t q_rows;  /* valid rows in the tile (1..128); others are computed, not stored */
+  int32_t q_row0;  /* first query row of the tile                                   */
+  int32_t q_rows;  /* valid rows in the tile (1..tile); others are computed, not stored */
   int32_t col0;    /* first train row of the span                                   */
   int32_t col1;    /* one past the last train row of the span                       */
   int32_t slot;    /* tip_kde_lse: partial-result slot of this span; unused otherwise */
@@ -106,13 +107,20 @@ int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d, const flo
                   int role, int segments, float scale, float norm_coef, void* dst_bf16,
                   float* sqnorm, void* stream);
 
+/* Query side of tip_nn_filter in one launch: packs the queries (segments = 1, no scaling) and
+ * resets the per-query filter state (row_min_bits = +inf, cand_cnt = 0). */
+int tip_nn_query_prep(const void* q, int dtype, int64_t m, int64_t d, const float* center,
+                      void* q_pack, float* q_sqnorm, uint32_t* row_min_bits, int32_t* cand_cnt,
+                      void* stream);
+
 /* ---- nearest-neighbour candidate filter (tcgen05 + TMA) ------------------------------
  * q_pack: m x pitch, t_pack: n x pitch (tip_pair_prep, scale=-2, norm_coef=1).
  * For every query row and every work item covering it, scans the item's train span and
- * appends to cand_idx[row*cap + k] the first row of every group of 8 consecutive train rows
- * that contains a row whose approximate squared distance is within the proven error window of
- * the running minimum; cand_cnt[row] counts appends (may exceed cap:
- * overflow -> tip_nn_rerank falls back to an exact scan).
+ * appends one entry per 32-row chunk of train rows that contains a row whose approximate squared
+ * distance is within the proven error window of the running minimum:
+ * cand_idx[(row*cap + k)*2] = first train row of the chunk, cand_idx[(row*cap + k)*2 + 1] = 32-bit
+ * mask of the rows of the chunk that pass (cand_idx holds 2*cap int32 per query); cand_cnt[row]
+ * counts appends (may exceed cap: overflow -> tip_nn_rerank falls back to an exact scan).
  * row_min_bits[m] (uint32 float bits, initialised to +inf = 0x7f800000 by the caller) carries
  * the running minimum across items/CTAs.  t_rmax = max_j |h(y_j)| over the train rows. */
 int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const void* t_pack,
@@ -120,19 +128,28 @@ int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const vo
                   int32_t n_items, float t_rmax, uint32_t* row_min_bits, int32_t* cand_idx,
                   int32_t* cand_cnt, int32_t cap, void* stream);
 
+/* Tile geometry tip_nn_filter uses for traces of width d: work items must start on query rows
+ * that are multiples of nothing in particular but cover at most *q_rows rows (128, or 256 for
+ * the resident-query kernel used when the packed row has <= 9 K-steps, i.e. d <= 128); *t_rows
+ * is the train-tile height (256 or 128), useful for sizing spans. */
+int tip_nn_filter_tile(int64_t d, int32_t* q_rows, int32_t* t_rows);
+
 /* ---- exact re-rank (NumPy-order distances, first-occurrence argmin) -------------------
  * q, t: original-dtype (TIP_F32/TIP_F64) matrices m x d and n x d; train rows are grouped by
  * class (class_off[C+1]); q_class[m] gives each query's class, mode the column range.
- * Rows with 1..cap candidate groups (8 consecutive train rows each, clipped to the class range)
- * are re-ranked over those rows; rows with 0 or > cap
+ * Rows with 1..cap candidate entries (tip_nn_filter's chunk + mask pairs, rows clipped to the
+ * class range) are re-ranked over the flagged rows; rows with 0 or > cap
  * candidates (or cand_cnt == NULL) are scanned exhaustively over their range.
  * out_dist[m] (dtype) = sqrt(pairwise_sum((x-y)^2)) of the winner, out_pos[m] = its train row
- * (ties: lowest t_gid), stats[0] += exhaustive rows, stats[1] += candidates evaluated. */
+ * (ties: lowest t_gid); optional out_gid[m] = t_gid of the winner (-1 if none) and
+ * out_rows[m x d] = a copy of the winning train rows (DSA's stage-2 queries, surprise.py:648).
+ * work: int32 scratch of m + 1 entries (queue of queries that need the exhaustive scan).
+ * stats[0] += exhaustive rows, stats[1] += candidate entries walked. */
 int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n, int64_t d,
                   const int32_t* cand_idx, const int32_t* cand_cnt, int32_t cap,
                   const int32_t* q_class, const int32_t* class_off, int32_t n_classes, int mode,
-                  const int32_t* t_gid, void* out_dist, int32_t* out_pos, int64_t* stats,
-                  void* stream);
+                  const int32_t* t_gid, void* out_dist, int32_t* out_pos, int32_t* out_gid,
+                  void* out_rows, int32_t* work, int64_t* stats, void* stream);
 
 /* dst[i,:] = src[pos[i],:]  (rows of `row_bytes` bytes; pos < 0 -> zero row) */
 int tip_gather_rows(const void* src, int64_t row_bytes, const int32_t* pos, int64_t m, void* dst,
@@ -156,10 +173,18 @@ int tip_kde_lse(const void* q_pack, int64_t m, const void* t_pack, int64_t n, in
 int tip_kde_combine(const float* part_max, const float* part_sum, int64_t m, int32_t slots,
                     float* out_max, float* out_sum, void* stream);
 
-/* ---- bring-up / validation: plain accumulator dump of one 128 x 256 tile --------------
- * out[128*256] (fp32) = tail-augmented dot products of q rows [0,128) with t rows [0,256). */
+/* ---- bring-up / validation: plain accumulator dump ------------------------------------
+ * out[256*256] (fp32, row-major, leading dimension 256) = tail-augmented dot products of q rows
+ * [0,128) (streaming kernel) or [0,256) (resident-query kernel) with t rows [0,256).
+ * variant: 0 = the kernel tip_nn_filter would pick, 1 = streaming, 2 = resident-query. */
 int tip_pair_probe(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d,
-                   int segments, int64_t pitch, float* out, void* stream);
+                   int segments, int64_t pitch, int variant, float* out, void* stream);
+
+/* bring-up: while buf != NULL, block 0 of the resident-query filter kernel records clock64()
+ * stamps (16 int64 slots per train tile, up to `tiles` tiles): 0..3 MMA warp (before/after the
+ * TMEM-empty wait, after the operand wait, after issue), 4..7 one epilogue thread (before/after
+ * the accumulator wait, at TMEM release, at tile end), 8..10 TMA producer. */
+int tip_debug_timeline(long long* buf, int32_t tiles);
 
 #ifdef __cplusplus
 }

@@ -128,10 +128,11 @@ __device__ T np_sumsq(const T* __restrict__ x, const T* __restrict__ y, int n) {
 // ---- the same sums, computed cooperatively by a group of 8 consecutive lanes ----------------
 // Lane `sub` (0..7) owns NumPy's stride-8 accumulator r[sub]; the tree
 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is three xor-shuffles (IEEE addition is commutative, so
-// every lane of the group ends with the same bits).  All 32 lanes of the warp must call this
-// with the same n (four independent groups per warp).
+// every lane of the group ends with the same bits).  gmask names the 8 lanes of the calling
+// group, so the four groups of a warp may diverge (skip work independently).
 template <typename T>
-__device__ __forceinline__ T np_leaf_sumsq_g8(const T* __restrict__ x, const T* __restrict__ y, int n, int sub) {
+__device__ __forceinline__ T np_leaf_sumsq_g8(const T* __restrict__ x, const T* __restrict__ y, int n, int sub,
+                                              unsigned gmask) {
   using R = Rn<T>;
   auto term = [&](int i) -> T {
     T d = R::sub(x[i], y[i]);
@@ -151,16 +152,16 @@ __device__ __forceinline__ T np_leaf_sumsq_g8(const T* __restrict__ x, const T* 
     r = R::add(R::add(R::add(R::add(r, t0), t1), t2), t3);
   }
   for (; i < lim; i += 8) r = R::add(r, term(i + sub));
-  r = R::add(r, __shfl_xor_sync(0xffffffffu, r, 1));
-  r = R::add(r, __shfl_xor_sync(0xffffffffu, r, 2));
-  r = R::add(r, __shfl_xor_sync(0xffffffffu, r, 4));
+  r = R::add(r, __shfl_xor_sync(gmask, r, 1));
+  r = R::add(r, __shfl_xor_sync(gmask, r, 2));
+  r = R::add(r, __shfl_xor_sync(gmask, r, 4));
   for (; i < n; i++) r = R::add(r, term(i));
   return r;
 }
 
 template <typename T>
-__device__ T np_sumsq_g8(const T* __restrict__ x, const T* __restrict__ y, int n, int sub) {
-  if (n <= 128) return np_leaf_sumsq_g8<T>(x, y, n, sub);
+__device__ T np_sumsq_g8(const T* __restrict__ x, const T* __restrict__ y, int n, int sub, unsigned gmask) {
+  if (n <= 128) return np_leaf_sumsq_g8<T>(x, y, n, sub, gmask);
   int off[32], len[32];
   unsigned char phase[32];
   T vals[32];
@@ -170,7 +171,7 @@ __device__ T np_sumsq_g8(const T* __restrict__ x, const T* __restrict__ y, int n
     const int top = sp - 1;
     const int o = off[top], l = len[top];
     if (l <= 128) {
-      vals[vp++] = np_leaf_sumsq_g8<T>(x + o, y + o, l, sub);
+      vals[vp++] = np_leaf_sumsq_g8<T>(x + o, y + o, l, sub, gmask);
       sp--;
     } else {
       int n2 = l / 2;

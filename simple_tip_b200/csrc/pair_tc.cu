@@ -33,7 +33,7 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kEpiThreads = 256;             // 8 epilogue warps
 constexpr int kThreads = 64 + kEpiThreads;   // + TMA warp + MMA warp
 constexpr int kCandSlots = 8;   // per-query staging slots for candidates (MODE_NN)
-constexpr int kCandBytes = kCandSlots * 256 * 8;
+constexpr int kCandBytes = kCandSlots * 256 * 12;   // value, chunk start, 32-bit column mask
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kCandBytes;
 constexpr uint32_t kTmemCols = 512;
 
@@ -56,6 +56,9 @@ struct PairArgs {
   float* part_sum;
   // MODE_DUMP
   float* dump;
+  // bring-up: per-tile clock64 stamps of block 0 (16 slots per tile), or nullptr
+  long long* timeline;
+  int timeline_tiles;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------
@@ -106,6 +109,31 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16_acc(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_first(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -137,7 +165,9 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN 
 // distance so far is s: every train row whose exact NumPy distance could still be the minimum
 // has acc <= thr.  r = |x_b| + max|y_b|, e2 = 2*eps'*r, g = gamma*r^2.
 __device__ __forceinline__ float nn_threshold(float s, float nx, float e2, float g) {
-  float r = sqrtf(s + g) + e2;
+  float root;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(root) : "f"(s + g));   // <= 2 ulp; covered by the slack below
+  float r = root + e2;
   r *= 1.00004f;
   float thr = fmaf(r, r, g) - nx;
   return thr + fabsf(thr) * 1e-6f + 1e-30f;
@@ -154,6 +184,7 @@ struct EpiState {
 struct EpiShared {
   float* cand_val;
   int* cand_col;
+  uint32_t* cand_mask;
   int etid;
 };
 
@@ -172,12 +203,12 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
 // Reduce 32 accumulator columns [cbase, cbase+32) of one query row.
 template <int MODE>
 __device__ __forceinline__ void epi_chunk(const PairArgs& args, EpiState& st, const EpiShared& sh, uint32_t (&r)[32],
-                                          int cbase, bool partial, bool dump_tile, int row_local, int dump_col) {
+                                          int cbase, bool partial, bool dump_tile, int dump_row, int dump_col) {
   const float kInf = __int_as_float(0x7f800000);
   if (MODE == MODE_DUMP) {
     if (dump_tile) {
 #pragma unroll
-      for (int j = 0; j < 32; j++) args.dump[(int64_t)row_local * BN + dump_col + j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 32; j++) args.dump[(int64_t)dump_row * 256 + dump_col + j] = __uint_as_float(r[j]);
     }
   } else if (MODE == MODE_NN) {
     // Candidates are tracked per group of 8 consecutive train rows: one min per group, so the
@@ -199,35 +230,41 @@ __device__ __forceinline__ void epi_chunk(const PairArgs& args, EpiState& st, co
     }
     const float mn = fminf(fminf(gmin[0], gmin[1]), fminf(gmin[2], gmin[3]));
     if (st.valid_row && mn <= st.thr && mn < kInf) {
+      // event: this chunk holds a value inside the acceptance window of this query.  Kept short
+      // and branch-light — with 32 independent queries per warp, events are frequent until the
+      // running minima have warmed up.
       if (mn < st.best) {
         st.best = mn;
         st.s_ref = fminf(st.s_ref, fmaxf(st.best + st.nx, 0.f));
         st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
       }
-#pragma unroll 1
-      for (int gi = 0; gi < 4; gi++) {
-        const float v = gi == 0 ? gmin[0] : (gi == 1 ? gmin[1] : (gi == 2 ? gmin[2] : gmin[3]));
-        if (v <= st.thr) {
-          if (st.n_staged == kCandSlots) {   // compact against the (tighter) current threshold
-            int keep = 0;
-            for (int k = 0; k < kCandSlots; k++) {
-              const float sv = sh.cand_val[k * kEpiThreads + sh.etid];
-              if (sv <= st.thr) {
-                sh.cand_val[keep * kEpiThreads + sh.etid] = sv;
-                sh.cand_col[keep * kEpiThreads + sh.etid] = sh.cand_col[k * kEpiThreads + sh.etid];
-                keep++;
-              }
-            }
-            st.n_staged = keep;
+      // exact per-column mask of the chunk: the re-rank then touches only rows inside the window
+      uint32_t mask = 0;
+#pragma unroll
+      for (int j = 0; j < 32; j++) mask |= (__uint_as_float(r[j]) <= st.thr) ? (1u << j) : 0u;
+      if (st.n_staged == kCandSlots) {         // compact against the (tighter) current threshold
+        int keep = 0;
+        for (int k = 0; k < kCandSlots; k++) {
+          const float sv = sh.cand_val[k * kEpiThreads + sh.etid];
+          if (sv <= st.thr) {
+            sh.cand_val[keep * kEpiThreads + sh.etid] = sv;
+            sh.cand_col[keep * kEpiThreads + sh.etid] = sh.cand_col[k * kEpiThreads + sh.etid];
+            sh.cand_mask[keep * kEpiThreads + sh.etid] = sh.cand_mask[k * kEpiThreads + sh.etid];
+            keep++;
           }
-          if (st.n_staged < kCandSlots) {
-            sh.cand_val[st.n_staged * kEpiThreads + sh.etid] = v;
-            sh.cand_col[st.n_staged * kEpiThreads + sh.etid] = cbase + 8 * gi;
-            st.n_staged++;
-          } else {                           // staging full of live groups: emit directly
-            const int pos = atomicAdd(args.cand_cnt + st.row, 1);
-            if (pos < args.cap) args.cand_idx[st.row * args.cap + pos] = cbase + 8 * gi;
-          }
+        }
+        st.n_staged = keep;
+      }
+      if (st.n_staged < kCandSlots) {
+        sh.cand_val[st.n_staged * kEpiThreads + sh.etid] = mn;
+        sh.cand_col[st.n_staged * kEpiThreads + sh.etid] = cbase;
+        sh.cand_mask[st.n_staged * kEpiThreads + sh.etid] = mask;
+        st.n_staged++;
+      } else {                                 // staging full of live chunks: emit directly
+        const int pos = atomicAdd(args.cand_cnt + st.row, 1);
+        if (pos < args.cap) {
+          args.cand_idx[(st.row * args.cap + pos) * 2] = cbase;
+          args.cand_idx[(st.row * args.cap + pos) * 2 + 1] = (int)mask;
         }
       }
     }
@@ -368,6 +405,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     EpiShared sh;
     sh.cand_val = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
     sh.cand_col = reinterpret_cast<int*>(sh.cand_val + kCandSlots * kEpiThreads);
+    sh.cand_mask = reinterpret_cast<uint32_t*>(sh.cand_col + kCandSlots * kEpiThreads);
     sh.etid = etid;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -444,7 +482,10 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < st.n_staged; k++) {
             if (sh.cand_val[k * kEpiThreads + etid] <= st.thr) {
               const int pos = atomicAdd(args.cand_cnt + st.row, 1);
-              if (pos < args.cap) args.cand_idx[st.row * args.cap + pos] = sh.cand_col[k * kEpiThreads + etid];
+              if (pos < args.cap) {
+                args.cand_idx[(st.row * args.cap + pos) * 2] = sh.cand_col[k * kEpiThreads + etid];
+                args.cand_idx[(st.row * args.cap + pos) * 2 + 1] = (int)sh.cand_mask[k * kEpiThreads + etid];
+              }
             }
           }
         }
@@ -452,6 +493,282 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (st.valid_row) {
           args.part_max[(int64_t)(it.slot * 2 + half) * args.m + st.row] = st.run_max;
           args.part_sum[(int64_t)(it.slot * 2 + half) * args.m + st.row] = st.run_sum;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// =============================================================================================
+// Resident-query variant for short traces (packed width <= 9 K-steps, e.g. D = 128):
+// 256 query rows stay in shared memory for a whole work item and only 128-row train tiles are
+// streamed, so the L2 -> SM traffic per 256 x 128 output tile is the train tile alone
+// (36.9 KB at D = 128, against 147 KB per 128 x 256 tile in the streaming kernel above, which is
+// L2-bandwidth-bound at that size).  The packed row is consumed as full 64-element chunks
+// (128-byte swizzle) plus 16-element panels (32-byte swizzle) so no padding is fetched.
+// TMEM: 2 buffers x 2 query halves x 128 columns.  Epilogue as above (one query row per thread).
+// =============================================================================================
+constexpr int RS_BM = 256;
+constexpr int RS_BN = 128;
+constexpr int kRsMaxK16 = 9;
+constexpr uint32_t kIdescN128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(RS_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+struct RsGeom {
+  int nfull, rem, stages;
+  uint32_t a_bytes, b_bytes;
+};
+
+__host__ __device__ inline RsGeom rs_geom(int k16) {
+  RsGeom g;
+  g.nfull = k16 / 4;
+  g.rem = k16 % 4;
+  g.a_bytes = (uint32_t)(g.nfull * RS_BM * 128 + g.rem * RS_BM * 32);
+  g.b_bytes = (uint32_t)(g.nfull * RS_BN * 128 + g.rem * RS_BN * 32);
+  g.stages = 3;
+  return g;
+}
+constexpr int kRsBarBytes = 256;
+__host__ inline int rs_smem_bytes(int k16) {
+  const RsGeom g = rs_geom(k16);
+  return (int)(g.a_bytes + g.stages * g.b_bytes) + 1024 + kRsBarBytes + kCandBytes;
+}
+
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t addr) {
+  // K-major, 32-byte swizzle: rows of 32 B, 8-row groups 256 B apart
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
+}
+
+template <int MODE, int K16>
+__global__ void __launch_bounds__(kThreads, 1)
+pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAt,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt, const PairArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  constexpr int NFULL = K16 / 4, REM = K16 % 4;
+  const RsGeom geo = rs_geom(K16);
+  int tl_tile = 0;
+#define TL(slot)                                                                              \
+  do {                                                                                        \
+    if (args.timeline && blockIdx.x == 0 && tl_tile < args.timeline_tiles)                    \
+      args.timeline[(int64_t)tl_tile * 16 + (slot)] = clock64();                              \
+  } while (0)
+  const uint32_t a_base = base;
+  const uint32_t a_rem = a_base + (uint32_t)geo.nfull * RS_BM * 128;
+  const uint32_t b_base = a_base + geo.a_bytes;
+  const uint32_t tiles_bytes = geo.a_bytes + (uint32_t)geo.stages * geo.b_bytes;
+  const uint32_t bar0 = base + tiles_bytes;
+  // barriers: 0 a_full, 1 a_empty, 2..4 b_full, 5..7 b_empty, 8..9 tfull, 10..11 tempty
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tiles_bytes + 8 * 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmAt); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBt);
+    mbar_init(bar(0), 1); mbar_init(bar(1), 1);
+    for (int s = 0; s < 3; s++) { mbar_init(bar(2 + s), 1); mbar_init(bar(5 + s), 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(bar(8 + a), 1); mbar_init(bar(10 + a), kEpiThreads / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+        const tip_work_item it = args.items[w];
+        const int ntiles = (it.col1 - it.col0 + RS_BN - 1) / RS_BN;
+        // train tiles of the new item are prefetched while the previous item still owns the
+        // query buffer; the queries follow as soon as the MMA warp releases it
+        const int a_at = min(geo.stages - 1, ntiles);
+        for (int t = 0; t <= ntiles; t++) {
+          if (t == a_at) {
+            mbar_wait(bar(1), a_phase ^ 1u);
+            mbar_expect_tx(bar(0), geo.a_bytes);
+            for (int c = 0; c < geo.nfull; c++) tma_load_2d(a_base + (uint32_t)c * RS_BM * 128, &tmA, bar(0), c * 64, it.q_row0);
+            for (int p = 0; p < geo.rem; p++)
+              tma_load_2d(a_rem + (uint32_t)p * RS_BM * 32, &tmAt, bar(0), geo.nfull * 64 + p * 16, it.q_row0);
+            a_phase ^= 1u;
+          }
+          if (t == ntiles) break;
+          TL(8);
+          mbar_wait(bar(5 + stage), phase ^ 1u);
+          TL(9);
+          mbar_expect_tx(bar(2 + stage), geo.b_bytes);
+          const uint32_t b_dst = b_base + (uint32_t)stage * geo.b_bytes;
+          const int row = it.col0 + t * RS_BN;
+          for (int c = 0; c < geo.nfull; c++) tma_load_2d(b_dst + (uint32_t)c * RS_BN * 128, &tmB, bar(2 + stage), c * 64, row);
+          for (int p = 0; p < geo.rem; p++)
+            tma_load_2d(b_dst + (uint32_t)(geo.nfull * RS_BN * 128 + p * RS_BN * 32), &tmBt, bar(2 + stage),
+                        geo.nfull * 64 + p * 16, row);
+          TL(10);
+          tl_tile++;
+          if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    // The whole warp runs this loop (warp-uniform control flow keeps descriptors and barrier
+    // addresses in uniform registers); one elected lane issues tcgen05.mma / commit.  The 2*K16
+    // MMAs of a tile are straight-line code: a single thread's dependent instruction stream is
+    // the critical path of this kernel (measured: ~45 cycles per issue at best).
+    const bool leader = elect_one();
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+    for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+      const tip_work_item it = args.items[w];
+      const int ntiles = (it.col1 - it.col0 + RS_BN - 1) / RS_BN;
+      mbar_wait(bar(0), a_phase);
+      a_phase ^= 1u;
+      for (int t = 0; t < ntiles; t++) {
+        if (leader) TL(0);
+        mbar_wait(bar(10 + acc), acc_phase ^ 1u);
+        if (leader) TL(1);
+        mbar_wait(bar(2 + stage), phase);
+        if (leader) TL(2);
+        tc_fence_after();
+        const uint32_t b_src = b_base + (uint32_t)stage * geo.b_bytes;
+        if (leader) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256 + h * RS_BN);
+#pragma unroll
+            for (int c = 0; c < NFULL; c++) {
+              const uint64_t adesc = smem_desc(a_base + (uint32_t)c * RS_BM * 128 + (uint32_t)h * 128 * 128);
+              const uint64_t bdesc = smem_desc(b_src + (uint32_t)c * RS_BN * 128);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                if (c == 0 && k == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdescN128);
+                else umma_bf16_acc(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdescN128);
+              }
+            }
+#pragma unroll
+            for (int p = 0; p < REM; p++) {
+              const uint64_t adesc = smem_desc_sw32(a_rem + (uint32_t)p * RS_BM * 32 + (uint32_t)h * 128 * 32);
+              const uint64_t bdesc = smem_desc_sw32(b_src + (uint32_t)(NFULL * RS_BN * 128 + p * RS_BN * 32));
+              if (NFULL == 0 && p == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdescN128);
+              else umma_bf16_acc(d_tmem, adesc, bdesc, kIdescN128);
+            }
+          }
+          umma_commit(bar(5 + stage));
+          umma_commit(bar(8 + acc));
+          TL(3);
+          if (t == ntiles - 1) umma_commit(bar(1));   // query buffer free once this item's MMAs retire
+        }
+        __syncwarp();
+        tl_tile++;
+        if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ================= epilogue: warps 2..9, query half = (warp-2)/4, lane quadrant = warp%4 ====
+    const int quad = warp & 3;
+    const int mhalf = (warp - 2) >> 2;
+    const int row_local = mhalf * 128 + quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mhalf * RS_BN);
+    EpiShared sh;
+    sh.cand_val = reinterpret_cast<float*>(smem + tiles_bytes + kRsBarBytes);
+    sh.cand_col = reinterpret_cast<int*>(sh.cand_val + kCandSlots * kEpiThreads);
+    sh.cand_mask = reinterpret_cast<uint32_t*>(sh.cand_col + kCandSlots * kEpiThreads);
+    sh.etid = threadIdx.x - 64;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const float kInf = __int_as_float(0x7f800000);
+    for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+      const tip_work_item it = args.items[w];
+      const int ntiles = (it.col1 - it.col0 + RS_BN - 1) / RS_BN;
+      EpiState st;
+      st.valid_row = row_local < it.q_rows;
+      st.row = (int64_t)it.q_row0 + row_local;
+      st.nx = 0.f; st.e2 = 0.f; st.g = 0.f; st.best = kInf; st.thr = kInf; st.s_ref = kInf; st.n_staged = 0;
+      st.run_max = -kInf; st.run_sum = 0.f;
+      st.col1 = it.col1;
+      if (MODE == MODE_NN && st.valid_row) {
+        st.nx = args.q_sqnorm[st.row];
+        const float r = sqrtf(st.nx) + args.rmax;
+        st.e2 = args.eps2 * r;
+        st.g = args.gamma * r * r;
+        st.s_ref = __uint_as_float(ld_volatile_u32(args.row_min_bits + st.row));
+        st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
+      }
+      for (int t = 0; t < ntiles; t++) {
+        if (threadIdx.x == 64) TL(4);
+        mbar_wait(bar(8 + acc), acc_phase);
+        if (threadIdx.x == 64) TL(5);
+        tc_fence_after();
+        const int col_base = it.col0 + t * RS_BN;
+        const bool partial = col_base + RS_BN > it.col1;
+        const bool dump = (w == 0 && t < 2);
+        uint32_t seen_bits = 0x7f800000u;
+        if (MODE == MODE_NN && st.valid_row) seen_bits = ld_volatile_u32(args.row_min_bits + st.row);
+        const uint32_t taddr = lane_addr + (uint32_t)(acc * 256);
+        uint32_t ra[32], rb[32];
+        tmem_ld32(taddr, ra);
+        tmem_wait_ld();
+        tmem_ld32(taddr + 32, rb);
+        epi_chunk<MODE>(args, st, sh, ra, col_base, partial, dump, row_local, t * RS_BN);
+        tmem_wait_ld();
+        tmem_ld32(taddr + 64, ra);
+        epi_chunk<MODE>(args, st, sh, rb, col_base + 32, partial, dump, row_local, t * RS_BN + 32);
+        tmem_wait_ld();
+        tmem_ld32(taddr + 96, rb);
+        epi_chunk<MODE>(args, st, sh, ra, col_base + 64, partial, dump, row_local, t * RS_BN + 64);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(10 + acc));
+        if (threadIdx.x == 64) TL(6);
+        epi_chunk<MODE>(args, st, sh, rb, col_base + 96, partial, dump, row_local, t * RS_BN + 96);
+        if (MODE == MODE_NN && st.valid_row) {
+          const float mine = fmaxf(st.best + st.nx, 0.f);
+          const float seen = __uint_as_float(seen_bits);
+          if (mine < seen) atomicMin(args.row_min_bits + st.row, __float_as_uint(mine));
+          if (seen < st.s_ref) {
+            st.s_ref = seen;
+            st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
+          }
+        }
+        if (threadIdx.x == 64) { TL(7); tl_tile++; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (MODE == MODE_NN && st.valid_row) {
+        const float seen = __uint_as_float(ld_volatile_u32(args.row_min_bits + st.row));
+        if (seen < st.s_ref) {
+          st.s_ref = seen;
+          st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
+        }
+        for (int k = 0; k < st.n_staged; k++) {
+          if (sh.cand_val[k * kEpiThreads + sh.etid] <= st.thr) {
+            const int pos = atomicAdd(args.cand_cnt + st.row, 1);
+            if (pos < args.cap) {
+              args.cand_idx[(st.row * args.cap + pos) * 2] = sh.cand_col[k * kEpiThreads + sh.etid];
+              args.cand_idx[(st.row * args.cap + pos) * 2 + 1] = (int)sh.cand_mask[k * kEpiThreads + sh.etid];
+            }
+          }
         }
       }
     }
@@ -478,15 +795,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const void* basep, int64_t rows, int64_t pitch, int box_rows) {
+static int make_map(CUtensorMap* map, const void* basep, int64_t rows, int64_t pitch, int box_rows, int box_cols = BK) {
   auto fn = get_encode();
   if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return TIP_ERR_CUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)pitch * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(basep), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return TIP_ERR_CUDA; }
   return TIP_OK;
@@ -531,6 +849,50 @@ static int launch_pair(const void* q_pack, int64_t m, const void* t_pack, int64_
   return TIP_OK;
 }
 
+template <int MODE>
+static int launch_pair_rs(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t pitch, PairArgs args,
+                          cudaStream_t st) {
+  int rc = check_device();
+  if (rc != TIP_OK) return rc;
+  TIP_REQUIRE(((uintptr_t)q_pack & 127) == 0 && ((uintptr_t)t_pack & 127) == 0, "packed operands must be 128-byte aligned");
+  TIP_REQUIRE(args.k16 >= 1 && args.k16 <= kRsMaxK16 && args.k16 * 16 <= pitch, "packed width too large for the resident kernel");
+  TIP_REQUIRE(m >= 1 && n >= 1 && m < (1LL << 31) && n < (1LL << 31), "shape");
+  CUtensorMap ma, mat, mb, mbt;
+  if ((rc = make_map(&ma, q_pack, m, pitch, RS_BM, 64)) != TIP_OK) return rc;
+  if ((rc = make_map(&mat, q_pack, m, pitch, RS_BM, 16)) != TIP_OK) return rc;
+  if ((rc = make_map(&mb, t_pack, n, pitch, RS_BN, 64)) != TIP_OK) return rc;
+  if ((rc = make_map(&mbt, t_pack, n, pitch, RS_BN, 16)) != TIP_OK) return rc;
+  const int smem = rs_smem_bytes(kRsMaxK16);
+  static bool attr_set[3][kRsMaxK16 + 1] = {};
+  if (!attr_set[MODE][args.k16]) {
+#define TIP_RS_ATTR(K)                                                                                   \
+  case K:                                                                                                \
+    TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_rs_kernel<MODE, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    break;
+    switch (args.k16) {
+      TIP_RS_ATTR(1) TIP_RS_ATTR(2) TIP_RS_ATTR(3) TIP_RS_ATTR(4) TIP_RS_ATTR(5)
+      TIP_RS_ATTR(6) TIP_RS_ATTR(7) TIP_RS_ATTR(8) TIP_RS_ATTR(9)
+      default: TIP_REQUIRE(false, "k16");
+    }
+#undef TIP_RS_ATTR
+    attr_set[MODE][args.k16] = true;
+  }
+  const int grid = std::min(args.n_items, sm_count());
+  const int smem_k = rs_smem_bytes(args.k16);
+#define TIP_RS_CASE(K)                                                                                   \
+  case K:                                                                                                \
+    pair_rs_kernel<MODE, K><<<grid, kThreads, smem_k, st>>>(ma, mat, mb, mbt, args);                     \
+    break;
+  switch (args.k16) {
+    TIP_RS_CASE(1) TIP_RS_CASE(2) TIP_RS_CASE(3) TIP_RS_CASE(4) TIP_RS_CASE(5)
+    TIP_RS_CASE(6) TIP_RS_CASE(7) TIP_RS_CASE(8) TIP_RS_CASE(9)
+    default: TIP_REQUIRE(false, "k16");
+  }
+#undef TIP_RS_CASE
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
+}
+
 static int k16_of(int64_t d, int segments) {
   const int64_t d16 = (d + 15) & ~(int64_t)15;
   return (int)((segments * d16 + 16) / 16);
@@ -539,6 +901,14 @@ static int k16_of(int64_t d, int segments) {
 }  // namespace tip
 
 using namespace tip;
+
+static long long* g_timeline = nullptr;
+static int g_timeline_tiles = 0;
+extern "C" int tip_debug_timeline(long long* buf, int32_t tiles) {
+  g_timeline = buf;
+  g_timeline_tiles = tiles;
+  return TIP_OK;
+}
 
 extern "C" int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const void* t_pack, int64_t n,
                              int64_t d, int64_t pitch, const tip_work_item* items, int32_t n_items, float t_rmax,
@@ -557,7 +927,17 @@ extern "C" int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t 
   a.eps2 = 2.0f * 1.96e-3f;
   a.gamma = (float)(a.k16 * 16 + 16) * 1.1920929e-7f;
   a.row_min_bits = row_min_bits; a.cand_idx = cand_idx; a.cand_cnt = cand_cnt; a.cap = cap;
+  a.timeline = g_timeline; a.timeline_tiles = g_timeline_tiles;
+  if (a.k16 <= kRsMaxK16) return launch_pair_rs<MODE_NN>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
   return launch_pair<MODE_NN>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
+}
+
+extern "C" int tip_nn_filter_tile(int64_t d, int32_t* q_rows, int32_t* t_rows) {
+  TIP_REQUIRE(d >= 1 && q_rows && t_rows, "arguments");
+  const bool rs = k16_of(d, 1) <= kRsMaxK16;
+  *q_rows = rs ? RS_BM : BM;
+  *t_rows = rs ? RS_BN : BN;
+  return TIP_OK;
 }
 
 extern "C" int tip_kde_lse(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d, int64_t pitch,
@@ -573,14 +953,18 @@ extern "C" int tip_kde_lse(const void* q_pack, int64_t m, const void* t_pack, in
 }
 
 extern "C" int tip_pair_probe(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d, int segments,
-                              int64_t pitch, float* out, void* stream) {
+                              int64_t pitch, int variant, float* out, void* stream) {
   TIP_REQUIRE(q_pack && t_pack && out, "null pointer");
   TIP_REQUIRE(pitch == tip_pair_pitch(d, segments), "pitch does not match tip_pair_pitch");
+  TIP_REQUIRE(variant >= 0 && variant <= 2, "variant: 0 auto, 1 streaming, 2 resident");
   static tip_work_item* d_item = nullptr;
   if (!d_item) TIP_CHECK_CUDA(cudaMalloc(&d_item, sizeof(tip_work_item)));
-  tip_work_item h{0, (int32_t)std::min<int64_t>(m, BM), 0, (int32_t)std::min<int64_t>(n, BN), 0, 0};
+  const int k16 = k16_of(d, segments);
+  const bool rs = variant == 2 || (variant == 0 && k16 <= kRsMaxK16);
+  tip_work_item h{0, (int32_t)std::min<int64_t>(m, rs ? RS_BM : BM), 0, (int32_t)std::min<int64_t>(n, 256), 0, 0};
   TIP_CHECK_CUDA(cudaMemcpyAsync(d_item, &h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   PairArgs a{};
-  a.items = d_item; a.n_items = 1; a.k16 = k16_of(d, segments); a.m = m; a.dump = out;
+  a.items = d_item; a.n_items = 1; a.k16 = k16; a.m = m; a.dump = out;
+  if (rs) return launch_pair_rs<MODE_DUMP>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
   return launch_pair<MODE_DUMP>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
 }

@@ -6,15 +6,20 @@
 // does it: difference, square, NumPy's pairwise summation order, correctly rounded sqrt — all in
 // the input dtype with no FMA contraction — and the winner is the lexicographic minimum of
 // (distance, original train index), i.e. np.argmin's first occurrence (surprise.py:645-647).
-// Rows without a usable candidate list (0 or > cap candidates, or no filter at all) are scanned
-// exhaustively over their class range, which is also the reference-grade fallback path.
+//
+// Two kernels: (1) one WARP per query walks its short candidate list (the work per query is a
+// handful of rows, so the kernel is a chain of dependent memory latencies: many queries in
+// flight matter, not threads per query); queries without a usable list (0 or > cap entries, or
+// no filter at all) are appended to a work list; (2) one BLOCK per listed query scans its class
+// range exhaustively — the reference-grade fallback, normally empty.
+// Both also emit the winner's original index and (optionally) copy the winning train row, which
+// is the query of DSA's second stage (surprise.py:627-629, 648).
 #include <algorithm>
 #include "common.cuh"
 
 namespace tip {
 
-constexpr int kRerankThreads = 128;
-constexpr int kCandGroup = 8;   // must match the group size of the filter epilogue (pair_tc.cu)
+constexpr int kScanThreads = 128;
 
 template <typename T>
 struct Best {
@@ -34,92 +39,152 @@ __device__ __forceinline__ void consider(Best<T>& b, T dist, int gid, int pos) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kRerankThreads)
-rerank_kernel(const T* __restrict__ q, const T* __restrict__ t, int64_t m, int64_t n, int d,
-              const int32_t* __restrict__ cand_idx, const int32_t* __restrict__ cand_cnt, int cap,
-              const int32_t* __restrict__ q_class, const int32_t* __restrict__ class_off, int n_classes,
-              int mode, const int32_t* __restrict__ t_gid, T* __restrict__ out_dist,
-              int32_t* __restrict__ out_pos, unsigned long long* __restrict__ stats, bool xs_ok) {
-  __shared__ T s_dist[kRerankThreads];
-  __shared__ int s_gid[kRerankThreads];
-  __shared__ int s_pos[kRerankThreads];
-  extern __shared__ __align__(16) unsigned char rerank_smem[];
-  T* xs = reinterpret_cast<T*>(rerank_smem);
-  for (int64_t row = blockIdx.x; row < m; row += gridDim.x) {
-    const T* xg = q + row * (int64_t)d;
-    const T* x = xg;
-    if (xs_ok) {                       // query row reused by every candidate: keep it on chip
-      for (int i = threadIdx.x; i < d; i += kRerankThreads) xs[i] = xg[i];
-      __syncthreads();
-      x = xs;
-    }
-    Best<T> best;
-    best.dist = Rn<T>::inf();
-    best.gid = 0x7fffffff;
-    best.pos = -1;
-    const int cnt = cand_cnt ? cand_cnt[row] : 0;
-    const int cls = q_class ? q_class[row] : 0;
-    const bool listed = cand_cnt != nullptr && cnt >= 1 && cnt <= cap;
-    const int sub = threadIdx.x & 7;            // lane inside its 8-lane group
-    const int grp = threadIdx.x >> 3;           // 16 groups per block, one train row each
-    constexpr int kGroups = kRerankThreads / 8;
-    if (listed && cls >= 0 && cls < n_classes) {
-      // every candidate names a group of kCandGroup consecutive train rows (clipped to the
-      // class range it starts in)
-      const int c0 = class_off[cls], c1 = class_off[cls + 1], cn = class_off[n_classes];
-      const int total = cnt * kCandGroup;
-      for (int base = 0; base < total; base += kGroups) {
-        const int k = base + grp;
-        bool ok = k < total;
-        int j = 0;
-        if (ok) {
-          const int start = cand_idx[row * (int64_t)cap + k / kCandGroup];
-          j = start + (k % kCandGroup);
-          const int limit = mode == TIP_RANGE_SAME_CLASS ? c1 : (start < c0 ? c0 : cn);
-          ok = start >= 0 && j < limit && j < n;
-          if (!ok) j = 0;
-        }
-        const T s = np_sumsq_g8<T>(x, t + (int64_t)j * d, d, sub);
-        if (ok && sub == 0) consider(best, Rn<T>::sqrt(s), t_gid ? t_gid[j] : j, j);
+__device__ __forceinline__ Best<T> merge(Best<T> a, T dist, int gid, int pos) {
+  if (pos >= 0) {
+    if (a.pos < 0) { a.dist = dist; a.gid = gid; a.pos = pos; }
+    else consider(a, dist, gid, pos);
+  }
+  return a;
+}
+
+template <typename T>
+struct RerankArgs {
+  const T* q;
+  const T* t;
+  int64_t m, n;
+  int d;
+  const int32_t* cand_idx;
+  const int32_t* cand_cnt;
+  int cap;
+  const int32_t* q_class;
+  const int32_t* class_off;
+  int n_classes;
+  int mode;
+  const int32_t* t_gid;
+  T* out_dist;
+  int32_t* out_pos;
+  int32_t* out_gid;   // nullable
+  T* out_rows;        // nullable: m x d copy of the winning train rows
+  int32_t* work;      // work[0] = number of queued queries, work[1..] = their rows
+  unsigned long long* stats;
+};
+
+template <typename T>
+__device__ __forceinline__ void write_result(const RerankArgs<T>& a, int64_t row, const Best<T>& b, int lane, int nlanes) {
+  // all `nlanes` threads of the caller hold the same `b`
+  if (lane == 0) {
+    a.out_dist[row] = b.pos >= 0 ? b.dist : (T)NAN;   // empty range -> NaN / -1
+    a.out_pos[row] = b.pos;
+    if (a.out_gid) a.out_gid[row] = b.pos >= 0 ? (a.t_gid ? a.t_gid[b.pos] : b.pos) : -1;
+  }
+  if (a.out_rows) {
+    T* dst = a.out_rows + row * (int64_t)a.d;
+    const T* src = a.t + (int64_t)(b.pos < 0 ? 0 : b.pos) * a.d;
+    for (int i = lane; i < a.d; i += nlanes) dst[i] = b.pos >= 0 ? src[i] : (T)0;
+  }
+}
+
+// ---- kernel 1: one warp per query, candidate lists ----------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) rerank_list_kernel(const RerankArgs<T> a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= a.m) return;
+  const int cnt = a.cand_cnt ? a.cand_cnt[row] : 0;
+  const int cls = a.q_class ? a.q_class[row] : 0;
+  if (cls < 0 || cls >= a.n_classes) {   // never scored by the reference either
+    Best<T> none{Rn<T>::inf(), 0x7fffffff, -1};
+    write_result(a, row, none, lane, 32);
+    return;
+  }
+  if (a.cand_cnt == nullptr || cnt < 1 || cnt > a.cap) {
+    if (lane == 0) a.work[1 + atomicAdd(a.work, 1)] = (int32_t)row;
+    return;
+  }
+  const int c0 = a.class_off[cls], c1 = a.class_off[cls + 1], cn = a.class_off[a.n_classes];
+  const int sub = lane & 7, grp = lane >> 3;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  const T* x = a.q + row * (int64_t)a.d;
+  Best<T> best{Rn<T>::inf(), 0x7fffffff, -1};
+  // entries are (first train row of a 32-row chunk, 32-bit mask of the rows inside the window);
+  // the four 8-lane groups of the warp take entries round-robin and walk their mask bits
+  for (int e0 = 0; e0 < cnt; e0 += 4) {
+    const int e = e0 + grp;
+    if (e < cnt) {
+      const int start = a.cand_idx[(row * (int64_t)a.cap + e) * 2];
+      unsigned cmask = (unsigned)a.cand_idx[(row * (int64_t)a.cap + e) * 2 + 1];
+      const int limit = a.mode == TIP_RANGE_SAME_CLASS ? c1 : (start < c0 ? c0 : cn);
+      while (cmask) {
+        const int bit = __ffs(cmask) - 1;
+        cmask &= cmask - 1;
+        const int j = start + bit;
+        if (start < 0 || j >= limit || j >= a.n) continue;
+        const T s = np_sumsq_g8<T>(x, a.t + (int64_t)j * a.d, a.d, sub, gmask);
+        consider(best, Rn<T>::sqrt(s), a.t_gid ? a.t_gid[j] : j, j);   // all 8 lanes agree
       }
-      if (threadIdx.x == 0 && stats) atomicAdd(stats + 1, (unsigned long long)cnt);
-    } else if (cls >= 0 && cls < n_classes && n > 0) {
-      const int c0 = class_off[cls], c1 = class_off[cls + 1], cn = class_off[n_classes];
-      // SAME_CLASS: [c0, c1);  OTHER_CLASSES: [0, c0) U [c1, cn)
-      const int lo[2] = {mode == TIP_RANGE_SAME_CLASS ? c0 : 0, mode == TIP_RANGE_SAME_CLASS ? 0 : c1};
-      const int hi[2] = {mode == TIP_RANGE_SAME_CLASS ? c1 : c0, mode == TIP_RANGE_SAME_CLASS ? 0 : cn};
-      for (int rg = 0; rg < 2; rg++) {
-        for (int base = lo[rg]; base < hi[rg]; base += kGroups) {
-          const int j = base + grp;
-          const bool ok = j < hi[rg];
-          const T s = np_sumsq_g8<T>(x, t + (int64_t)(ok ? j : lo[rg]) * d, d, sub);
-          if (ok && sub == 0) consider(best, Rn<T>::sqrt(s), t_gid ? t_gid[j] : j, j);
-        }
-      }
-      if (threadIdx.x == 0 && stats) atomicAdd(stats + 0, 1ULL);
     }
-    s_dist[threadIdx.x] = best.dist;
-    s_gid[threadIdx.x] = best.gid;
-    s_pos[threadIdx.x] = best.pos;
+  }
+  __syncwarp();
+  for (int o = 8; o < 32; o <<= 1) {
+    const T od = __shfl_xor_sync(0xffffffffu, best.dist, o);
+    const int og = __shfl_xor_sync(0xffffffffu, best.gid, o);
+    const int op = __shfl_xor_sync(0xffffffffu, best.pos, o);
+    best = merge(best, od, og, op);
+  }
+  if (lane == 0 && a.stats) atomicAdd(a.stats + 1, (unsigned long long)cnt);
+  write_result(a, row, best, lane, 32);
+}
+
+// ---- kernel 2: one block per queued query, exhaustive scan of its class range --------------------
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) rerank_scan_kernel(const RerankArgs<T> a) {
+  __shared__ T s_dist[kScanThreads / 8];
+  __shared__ int s_gid[kScanThreads / 8];
+  __shared__ int s_pos[kScanThreads / 8];
+  __shared__ Best<T> s_best;
+  const int queued = a.work[0];
+  const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  constexpr int kGroups = kScanThreads / 8;
+  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+  for (int w = blockIdx.x; w < queued; w += gridDim.x) {
+    const int64_t row = a.work[1 + w];
+    const int cls = a.q_class ? a.q_class[row] : 0;
+    const T* x = a.q + row * (int64_t)a.d;
+    Best<T> best{Rn<T>::inf(), 0x7fffffff, -1};
+    const int c0 = a.class_off[cls], c1 = a.class_off[cls + 1], cn = a.class_off[a.n_classes];
+    // SAME_CLASS: [c0, c1);  OTHER_CLASSES: [0, c0) U [c1, cn)
+    const int lo[2] = {a.mode == TIP_RANGE_SAME_CLASS ? c0 : 0, a.mode == TIP_RANGE_SAME_CLASS ? 0 : c1};
+    const int hi[2] = {a.mode == TIP_RANGE_SAME_CLASS ? c1 : c0, a.mode == TIP_RANGE_SAME_CLASS ? 0 : cn};
+    for (int rg = 0; rg < 2; rg++) {
+      for (int j = lo[rg] + grp; j < hi[rg]; j += kGroups) {
+        const T s = np_sumsq_g8<T>(x, a.t + (int64_t)j * a.d, a.d, sub, gmask);
+        consider(best, Rn<T>::sqrt(s), a.t_gid ? a.t_gid[j] : j, j);
+      }
+    }
+    if (sub == 0) { s_dist[grp] = best.dist; s_gid[grp] = best.gid; s_pos[grp] = best.pos; }
     __syncthreads();
-    for (int o = kRerankThreads / 2; o > 0; o >>= 1) {
-      if (threadIdx.x < o) {
-        Best<T> a{s_dist[threadIdx.x], s_gid[threadIdx.x], s_pos[threadIdx.x]};
-        const int p2 = s_pos[threadIdx.x + o];
-        if (p2 >= 0) {
-          if (a.pos < 0) { a.dist = s_dist[threadIdx.x + o]; a.gid = s_gid[threadIdx.x + o]; a.pos = p2; }
-          else consider(a, s_dist[threadIdx.x + o], s_gid[threadIdx.x + o], p2);
-        }
-        s_dist[threadIdx.x] = a.dist; s_gid[threadIdx.x] = a.gid; s_pos[threadIdx.x] = a.pos;
-      }
-      __syncthreads();
-    }
     if (threadIdx.x == 0) {
-      out_dist[row] = s_pos[0] >= 0 ? s_dist[0] : (T)NAN;   // empty range -> NaN / -1
-      out_pos[row] = s_pos[0];
+      Best<T> b{Rn<T>::inf(), 0x7fffffff, -1};
+      for (int g = 0; g < kGroups; g++) b = merge(b, s_dist[g], s_gid[g], s_pos[g]);
+      s_best = b;
+      if (a.stats) atomicAdd(a.stats + 0, 1ULL);
     }
+    __syncthreads();
+    write_result(a, row, s_best, threadIdx.x, kScanThreads);
     __syncthreads();
   }
+}
+
+template <typename T>
+static int launch_rerank(const RerankArgs<T>& a, cudaStream_t st) {
+  TIP_CHECK_CUDA(cudaMemsetAsync(a.work, 0, sizeof(int32_t), st));
+  const int64_t blocks = (a.m + 7) / 8;
+  rerank_list_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a);
+  TIP_LAUNCH_CHECK();
+  const int grid = (int)std::min<int64_t>(a.m, (int64_t)sm_count() * 8);
+  rerank_scan_kernel<T><<<grid, kScanThreads, 0, st>>>(a);
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
 }
 
 }  // namespace tip
@@ -129,29 +194,26 @@ using namespace tip;
 extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n, int64_t d,
                              const int32_t* cand_idx, const int32_t* cand_cnt, int32_t cap, const int32_t* q_class,
                              const int32_t* class_off, int32_t n_classes, int mode, const int32_t* t_gid,
-                             void* out_dist, int32_t* out_pos, int64_t* stats, void* stream) {
-  TIP_REQUIRE(q && t && out_dist && out_pos, "null pointer");
+                             void* out_dist, int32_t* out_pos, int32_t* out_gid, void* out_rows, int32_t* work,
+                             int64_t* stats, void* stream) {
+  TIP_REQUIRE(q && t && out_dist && out_pos && work, "null pointer");
   TIP_REQUIRE(class_off && n_classes >= 1, "class offsets");
-  TIP_REQUIRE(m >= 0 && n >= 0 && n < (1LL << 31) && d >= 1 && d < (1LL << 31), "shape");
+  TIP_REQUIRE(m >= 0 && m < (1LL << 31) - 8 && n >= 0 && n < (1LL << 31) && d >= 1 && d < (1LL << 31), "shape");
   TIP_REQUIRE(mode == TIP_RANGE_SAME_CLASS || mode == TIP_RANGE_OTHER_CLASSES, "mode");
   TIP_REQUIRE(cand_cnt == nullptr || (cand_idx != nullptr && cap >= 1), "candidate buffers");
   if (m == 0) return TIP_OK;
-  const int grid = (int)std::min<int64_t>(m, (int64_t)sm_count() * 16);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t elem = dtype == TIP_F64 ? 8 : 4;
-  const bool xs_ok = (size_t)d * elem <= 32 * 1024;
-  const size_t xs_bytes = xs_ok ? (size_t)d * elem : 0;
-  if (dtype == TIP_F32)
-    rerank_kernel<float><<<grid, kRerankThreads, xs_bytes, st>>>((const float*)q, (const float*)t, m, n, (int)d, cand_idx,
-                                                          cand_cnt, cap, q_class, class_off, n_classes, mode, t_gid,
-                                                          (float*)out_dist, out_pos, (unsigned long long*)stats, xs_ok);
-  else if (dtype == TIP_F64)
-    rerank_kernel<double><<<grid, kRerankThreads, xs_bytes, st>>>((const double*)q, (const double*)t, m, n, (int)d,
-                                                           cand_idx, cand_cnt, cap, q_class, class_off, n_classes,
-                                                           mode, t_gid, (double*)out_dist, out_pos,
-                                                           (unsigned long long*)stats, xs_ok);
-  else
-    TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
-  TIP_LAUNCH_CHECK();
-  return TIP_OK;
+  if (dtype == TIP_F32) {
+    RerankArgs<float> a{(const float*)q, (const float*)t, m, n, (int)d, cand_idx, cand_cnt, cap, q_class, class_off,
+                        n_classes, mode, t_gid, (float*)out_dist, out_pos, out_gid, (float*)out_rows, work,
+                        (unsigned long long*)stats};
+    return launch_rerank<float>(a, st);
+  }
+  if (dtype == TIP_F64) {
+    RerankArgs<double> a{(const double*)q, (const double*)t, m, n, (int)d, cand_idx, cand_cnt, cap, q_class,
+                         class_off, n_classes, mode, t_gid, (double*)out_dist, out_pos, out_gid, (double*)out_rows,
+                         work, (unsigned long long*)stats};
+    return launch_rerank<double>(a, st);
+  }
+  TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
 }

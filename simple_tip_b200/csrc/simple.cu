@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(256) pair_prep_kernel(const T* __restrict__ sr
                                                         const float* __restrict__ center, int role,
                                                         int segments, float scale, float norm_coef,
                                                         __nv_bfloat16* __restrict__ dst, int64_t pitch,
-                                                        float* __restrict__ sqnorm) {
+                                                        float* __restrict__ sqnorm, uint32_t* __restrict__ row_min,
+                                                        int32_t* __restrict__ cand_cnt) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -335,7 +336,11 @@ __global__ void __launch_bounds__(256) pair_prep_kernel(const T* __restrict__ sr
     }
     out[c] = __float2bfloat16_rn(v);
   }
-  if (lane == 0 && sqnorm) sqnorm[row] = nrm;
+  if (lane == 0) {
+    if (sqnorm) sqnorm[row] = nrm;
+    if (row_min) row_min[row] = 0x7f800000u;   // +inf: no distance seen yet (tip_nn_filter)
+    if (cand_cnt) cand_cnt[row] = 0;
+  }
 }
 
 // =============================================================================================
@@ -503,8 +508,9 @@ extern "C" int64_t tip_pair_pitch(int64_t d, int segments) {
   return (segments * d16 + 16 + 63) & ~(int64_t)63;
 }
 
-extern "C" int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d, const float* center, int role,
-                             int segments, float scale, float norm_coef, void* dst, float* sqnorm, void* stream) {
+static int pair_prep_impl(const void* src, int dtype, int64_t rows, int64_t d, const float* center, int role,
+                          int segments, float scale, float norm_coef, void* dst, float* sqnorm, uint32_t* row_min,
+                          int32_t* cand_cnt, void* stream) {
   TIP_REQUIRE(src && dst, "null pointer");
   TIP_REQUIRE(segments == 1 || segments == 3, "segments must be 1 or 3");
   TIP_REQUIRE(role == TIP_ROLE_QUERY || role == TIP_ROLE_TRAIN, "role");
@@ -517,15 +523,29 @@ extern "C" int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == TIP_F32)
     pair_prep_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)src, rows, (int)d, center, role, segments,
-                                                             scale, norm_coef, (__nv_bfloat16*)dst, pitch, sqnorm);
+                                                             scale, norm_coef, (__nv_bfloat16*)dst, pitch, sqnorm,
+                                                             row_min, cand_cnt);
   else if (dtype == TIP_F64)
     pair_prep_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double*)src, rows, (int)d, center, role,
                                                               segments, scale, norm_coef, (__nv_bfloat16*)dst, pitch,
-                                                              sqnorm);
+                                                              sqnorm, row_min, cand_cnt);
   else
     TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
   TIP_LAUNCH_CHECK();
   return TIP_OK;
+}
+
+extern "C" int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d, const float* center, int role,
+                             int segments, float scale, float norm_coef, void* dst, float* sqnorm, void* stream) {
+  return pair_prep_impl(src, dtype, rows, d, center, role, segments, scale, norm_coef, dst, sqnorm, nullptr, nullptr,
+                        stream);
+}
+
+extern "C" int tip_nn_query_prep(const void* q, int dtype, int64_t m, int64_t d, const float* center, void* q_pack,
+                                 float* q_sqnorm, uint32_t* row_min_bits, int32_t* cand_cnt, void* stream) {
+  TIP_REQUIRE(q_sqnorm && row_min_bits && cand_cnt, "null pointer");
+  return pair_prep_impl(q, dtype, m, d, center, TIP_ROLE_QUERY, 1, 1.0f, 0.0f, q_pack, q_sqnorm, row_min_bits,
+                        cand_cnt, stream);
 }
 
 extern "C" int tip_gather_rows(const void* src, int64_t row_bytes, const int32_t* pos, int64_t m, void* dst,

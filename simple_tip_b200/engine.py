@@ -90,18 +90,18 @@ def shard_rows(labels: np.ndarray, num_classes: int, rank: int, world: int) -> n
     return np.sort(np.concatenate(keep)) if keep else np.zeros(0, dtype=np.int64)
 
 
-def span_tiles_for(total_tile_pairs: int, sms: int) -> int:
-    """Column tiles per work item: aim for ~6 items per SM so the static round-robin balances."""
-    return int(min(32, max(2, round(total_tile_pairs / max(1, sms * 6)))))
+def span_tiles_for(total_tile_pairs: int, sms: int, per_sm: int = 6, lo: int = 2, hi: int = 32) -> int:
+    """Column tiles per work item: aim for ~per_sm items per SM so the static round-robin balances."""
+    return int(min(hi, max(lo, round(total_tile_pairs / max(1, sms * per_sm)))))
 
 
-def build_items(q_off: np.ndarray, ranges_per_class: Sequence[Sequence[Tuple[int, int]]], span_tiles: int
-                ) -> Tuple[np.ndarray, int]:
+def build_items(q_off: np.ndarray, ranges_per_class: Sequence[Sequence[Tuple[int, int]]], span_tiles: int,
+                row_tile: int = _lib.ROW_TILE, col_tile: int = _lib.COL_TILE) -> Tuple[np.ndarray, int]:
     """Work list of the tensor-core pass.  q_off[c]..q_off[c+1] are the (class-sorted) query rows
     of class c; ranges_per_class[c] the train-row ranges they must be compared with.  Every item is
-    one 128-row query tile x one span of at most span_tiles*256 train rows.  Returns
+    one row_tile-row query tile x one span of at most span_tiles*col_tile train rows.  Returns
     (int32 array [n, 6] laid out as tip_work_item, max number of spans per class)."""
-    width = span_tiles * _lib.COL_TILE
+    width = span_tiles * col_tile
     out = []
     max_slots = 1
     for c, ranges in enumerate(ranges_per_class):
@@ -115,8 +115,8 @@ def build_items(q_off: np.ndarray, ranges_per_class: Sequence[Sequence[Tuple[int
         if not spans:
             continue
         max_slots = max(max_slots, len(spans))
-        r0 = np.arange(int(q_off[c]), int(q_off[c + 1]), _lib.ROW_TILE, dtype=np.int64)
-        rows = np.minimum(_lib.ROW_TILE, int(q_off[c + 1]) - r0)
+        r0 = np.arange(int(q_off[c]), int(q_off[c + 1]), row_tile, dtype=np.int64)
+        rows = np.minimum(row_tile, int(q_off[c + 1]) - r0)
         sp = np.asarray(spans, dtype=np.int64)
         nt, ns = r0.shape[0], sp.shape[0]
         item = np.zeros((nt * ns, 6), dtype=np.int32)
@@ -131,14 +131,15 @@ def build_items(q_off: np.ndarray, ranges_per_class: Sequence[Sequence[Tuple[int
     return np.concatenate(out), max_slots
 
 
-def count_tile_pairs(q_off: np.ndarray, ranges_per_class) -> int:
+def count_tile_pairs(q_off: np.ndarray, ranges_per_class, row_tile: int = _lib.ROW_TILE,
+                     col_tile: int = _lib.COL_TILE) -> int:
     total = 0
     for c, ranges in enumerate(ranges_per_class):
         cnt = int(q_off[c + 1] - q_off[c])
         if cnt <= 0:
             continue
         cols = sum(max(0, int(hi) - int(lo)) for lo, hi in ranges)
-        total += math.ceil(cnt / _lib.ROW_TILE) * math.ceil(cols / _lib.COL_TILE)
+        total += math.ceil(cnt / row_tile) * math.ceil(cols / col_tile)
     return total
 
 
@@ -224,9 +225,13 @@ class NnEngine:
         sms = C.c_int(0)
         _lib.check(self.lib.tip_device_info(C.byref(sms), None, None), "tip_device_info")
         self.sms = sms.value
+        qt, tt = C.c_int32(0), C.c_int32(0)
+        _lib.check(self.lib.tip_nn_filter_tile(self.d, C.byref(qt), C.byref(tt)), "tip_nn_filter_tile")
+        self.row_tile, self.col_tile = qt.value, tt.value
         self.stats = torch.zeros(2, dtype=torch.int64, device=self.dev)
         self._item_cache = {}
         self._plans = {}
+        self.last_cand_cnt_by_mode = {}
         if self.n > 0:
             self.center = self.t.mean(dim=0, dtype=torch.float64).to(torch.float32).contiguous()
             self.t_pack = torch.empty((self.n, self.pitch), dtype=torch.bfloat16, device=self.dev)
@@ -254,16 +259,19 @@ class NnEngine:
             return [[(off[c], off[c + 1])] for c in range(self.num_classes)]
         return [[(0, off[c]), (off[c + 1], off[-1])] for c in range(self.num_classes)]
 
-    def search(self, q: torch.Tensor, q_class: torch.Tensor, q_off: np.ndarray, mode: int, use_filter: bool = True
-               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    def search(self, q: torch.Tensor, q_class: torch.Tensor, q_off: np.ndarray, mode: int, use_filter: bool = True,
+               want_rows: bool = False):
         """q: [m, d] queries grouped by class (q_off), q_class[m] int32.  Returns, per query, the
         exact NumPy-order distance to its nearest train row in the range selected by `mode`
-        (NaN when the range is empty on this shard) and that row's position (-1 when empty)."""
+        (NaN when the range is empty on this shard), that row's position (-1 when empty), its
+        original index, and (want_rows) a copy of the winning train rows."""
         m = q.shape[0]
         out_dist = torch.empty(m, dtype=q.dtype, device=self.dev)
         out_pos = torch.empty(m, dtype=torch.int32, device=self.dev)
+        out_gid = torch.empty(m, dtype=torch.int32, device=self.dev)
+        out_rows = torch.empty((m, self.d), dtype=q.dtype, device=self.dev) if want_rows else None
         if m == 0:
-            return out_dist, out_pos
+            return out_dist, out_pos, out_gid, out_rows
         lib = self.lib
         cand_idx = cand_cnt = None
         if use_filter and self.n > 0:
@@ -271,21 +279,27 @@ class NnEngine:
             key = (mode, np.asarray(q_off, dtype=np.int64).tobytes())
             plan = self._item_cache.get(key)
             if plan is None:       # host planning + upload once per (mode, class histogram)
-                pairs = count_tile_pairs(q_off, ranges)
-                items, _ = build_items(q_off, ranges, span_tiles_for(pairs, self.sms))
-                plan = (torch.from_numpy(items).to(self.dev) if items.shape[0] else None, items.shape[0])
+                pairs = count_tile_pairs(q_off, ranges, self.row_tile, self.col_tile)
+                if self.row_tile == 256:    # resident-query kernel: long items amortise the query load
+                    span = span_tiles_for(pairs, self.sms, per_sm=3, lo=24, hi=64)   # and the cold start
+                else:
+                    span = span_tiles_for(pairs, self.sms)
+                items, _ = build_items(q_off, ranges, span, self.row_tile, self.col_tile)
+                flops = 2.0 * self.d * sum(int(q_off[c + 1] - q_off[c]) * sum(int(hi) - int(lo) for lo, hi in ranges[c])
+                                           for c in range(self.num_classes))
+                plan = (torch.from_numpy(items).to(self.dev) if items.shape[0] else None, items.shape[0], flops)
                 if len(self._item_cache) > 64:
                     self._item_cache.clear()
                 self._item_cache[key] = plan
-            items_dev, n_items = plan
+            items_dev, n_items, flops = plan
             if n_items > 0:
                 q_pack = torch.empty((m, self.pitch), dtype=torch.bfloat16, device=self.dev)
                 q_sq = torch.empty(m, dtype=torch.float32, device=self.dev)
-                _lib.check(lib.tip_pair_prep(_p(q), tip_dtype(q.dtype), m, self.d, _p(self.center), _lib.ROLE_QUERY, 1,
-                                             1.0, 0.0, _p(q_pack), _p(q_sq), _stream()), "tip_pair_prep")
-                row_min = torch.full((m,), 0x7F800000, dtype=torch.int32, device=self.dev)
-                cand_cnt = torch.zeros(m, dtype=torch.int32, device=self.dev)
-                cand_idx = torch.empty((m, self.cap), dtype=torch.int32, device=self.dev)
+                row_min = torch.empty(m, dtype=torch.int32, device=self.dev)
+                cand_cnt = torch.empty(m, dtype=torch.int32, device=self.dev)
+                cand_idx = torch.empty((m, self.cap, 2), dtype=torch.int32, device=self.dev)
+                _lib.check(lib.tip_nn_query_prep(_p(q), tip_dtype(q.dtype), m, self.d, _p(self.center), _p(q_pack),
+                                                 _p(q_sq), _p(row_min), _p(cand_cnt), _stream()), "tip_nn_query_prep")
                 ev = None
                 if PROFILE is not None:
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -295,16 +309,17 @@ class NnEngine:
                                              _p(cand_cnt), self.cap, _stream()), "tip_nn_filter")
                 if ev is not None:
                     ev[1].record()
-                    pairs = sum(int(q_off[c + 1] - q_off[c]) * sum(int(hi) - int(lo) for lo, hi in ranges[c])
-                                for c in range(self.num_classes))
                     name = "nn_filter_same_class" if mode == _lib.RANGE_SAME_CLASS else "nn_filter_other_classes"
-                    PROFILE.append((name, 2.0 * self.d * pairs, ev[0], ev[1]))
+                    PROFILE.append((name, flops, ev[0], ev[1]))
+        work = torch.empty(m + 1, dtype=torch.int32, device=self.dev)
         _lib.check(lib.tip_nn_rerank(_p(q), _p(self.t), tip_dtype(q.dtype), m, self.n, self.d, _p(cand_idx),
                                      _p(cand_cnt), self.cap, _p(q_class), _p(self.class_off_dev), self.num_classes,
-                                     mode, _p(self.t_gid), _p(out_dist), _p(out_pos), _p(self.stats), _stream()),
-                   "tip_nn_rerank")
+                                     mode, _p(self.t_gid), _p(out_dist), _p(out_pos), _p(out_gid), _p(out_rows),
+                                     _p(work), _p(self.stats), _stream()), "tip_nn_rerank")
         self.last_cand_cnt = cand_cnt
-        return out_dist, out_pos
+        if cand_cnt is not None:
+            self.last_cand_cnt_by_mode[mode] = (cand_cnt, cand_idx)
+        return out_dist, out_pos, out_gid, out_rows
 
     def gather(self, pos: torch.Tensor) -> torch.Tensor:
         out = torch.empty((pos.shape[0], self.d), dtype=self.t.dtype, device=self.dev)
@@ -318,16 +333,10 @@ def dsa_distances(engine: NnEngine, x: torch.Tensor, q_class: torch.Tensor, q_of
                   comm: Optional[TrainShardComm] = None, use_filter: bool = True
                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """surprise.py:615-631 for class-sorted queries x: (dist_a, dist_b, winner original index)."""
-    dist_a, pos_a = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter)
-    winners = engine.gather(pos_a)
-    if engine.n > 0:
-        gid = torch.where(pos_a >= 0, engine.t_gid[pos_a.clamp(min=0).long()], torch.full_like(pos_a, -1))
-    else:
-        gid = torch.full_like(pos_a, -1)
+    dist_a, _, gid, winners = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter, want_rows=True)
     if comm is not None and comm.world > 1:
-        dist_a, gid64, winners = comm.reduce_winners(dist_a, gid, winners)
-        gid = gid64
-    dist_b, _ = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter)
+        dist_a, gid, winners = comm.reduce_winners(dist_a, gid, winners)
+    dist_b = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter)[0]
     if comm is not None and comm.world > 1:
         dist_b = comm.reduce_min_nan(dist_b)
     return dist_a, dist_b, gid

@@ -29,8 +29,12 @@ def _torch():
 # ------------------------------------------------------------------------------------------
 # tensor-core pass: raw accumulator tile vs an fp32 matmul of the packed operands
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("d,segments", [(16, 1), (128, 1), (100, 1), (300, 1), (2048, 1), (10, 3), (256, 3), (40, 3)])
-def test_pair_probe_matches_packed_matmul(d, segments):
+@pytest.mark.parametrize("d,segments,variant", [(16, 1, 1), (16, 1, 2), (128, 1, 1), (128, 1, 2), (100, 1, 0),
+                                                (64, 1, 2), (120, 1, 2), (5, 1, 2), (300, 1, 0), (2048, 1, 0),
+                                                (10, 3, 0), (256, 3, 0), (40, 3, 1), (40, 3, 2)])
+def test_pair_probe_matches_packed_matmul(d, segments, variant):
+    """variant 1 = streaming kernel (128 x 256 tiles), 2 = resident-query kernel (256 x 128 tiles,
+    128-byte-swizzled chunks + 32-byte-swizzled tail panels), 0 = whatever tip_nn_filter picks."""
     torch = _torch()
     from simple_tip_b200 import _lib
     from simple_tip_b200 import engine as E
@@ -38,22 +42,30 @@ def test_pair_probe_matches_packed_matmul(d, segments):
     lib = _lib.load()
     dev = E.require_cuda()
     rng = np.random.default_rng(d * 7 + segments)
-    q = torch.from_numpy(rng.normal(size=(128, d)).astype(np.float32)).to(dev)
+    q = torch.from_numpy(rng.normal(size=(256, d)).astype(np.float32)).to(dev)
     t = torch.from_numpy(rng.normal(size=(256, d)).astype(np.float32) * 1.5).to(dev)
     center = torch.from_numpy(rng.normal(size=d).astype(np.float32) * 0.1).to(dev)
     pitch = int(lib.tip_pair_pitch(d, segments))
-    qp = torch.empty((128, pitch), dtype=torch.bfloat16, device=dev)
+    k16 = (segments * ((d + 15) // 16 * 16) + 16) // 16
+    if variant == 2 and k16 > 9:
+        pytest.skip("packed row too wide for the resident-query kernel")
+    resident = variant == 2 or (variant == 0 and k16 <= 9)
+    rows = 256 if resident else 128
+    qp = torch.empty((256, pitch), dtype=torch.bfloat16, device=dev)
     tp = torch.empty((256, pitch), dtype=torch.bfloat16, device=dev)
-    qs = torch.empty(128, dtype=torch.float32, device=dev)
+    qs = torch.empty(256, dtype=torch.float32, device=dev)
     ts = torch.empty(256, dtype=torch.float32, device=dev)
     scale, coef = (-2.0, 1.0) if segments == 1 else (1.0, -0.5)
-    _lib.check(lib.tip_pair_prep(E._p(q), _lib.TIP_F32, 128, d, E._p(center), _lib.ROLE_QUERY, segments, 1.0, 0.0,
+    _lib.check(lib.tip_pair_prep(E._p(q), _lib.TIP_F32, 256, d, E._p(center), _lib.ROLE_QUERY, segments, 1.0, 0.0,
                                  E._p(qp), E._p(qs), E._stream()), "prep q")
     _lib.check(lib.tip_pair_prep(E._p(t), _lib.TIP_F32, 256, d, E._p(center), _lib.ROLE_TRAIN, segments, scale, coef,
                                  E._p(tp), E._p(ts), E._stream()), "prep t")
-    out = torch.empty((128, 256), dtype=torch.float32, device=dev)
-    _lib.check(lib.tip_pair_probe(E._p(qp), 128, E._p(tp), 256, d, segments, pitch, E._p(out), E._stream()), "probe")
+    out_full = torch.zeros((256, 256), dtype=torch.float32, device=dev)
+    _lib.check(lib.tip_pair_probe(E._p(qp), 256, E._p(tp), 256, d, segments, pitch, variant, E._p(out_full),
+                                  E._stream()), "probe")
     torch.cuda.synchronize()
+    out = out_full[:rows]
+    qp, qs, q = qp[:rows], qs[:rows], q[:rows]
     want = qp.to(torch.float64) @ tp.to(torch.float64).T
     scale_ref = float((qp.to(torch.float64).abs() @ tp.to(torch.float64).abs().T).max())
     err = float((out.to(torch.float64) - want).abs().max())

@@ -49,6 +49,13 @@ def main():
     mn, med = timed(lambda: eng.search(w, qc, q_off, _lib.RANGE_OTHER_CLASSES))
     print(f"  stage-2 search: {mn:.3f} ms")
     print("  stats (exhaustive rows, candidates):", eng.stats.cpu().numpy())
+    E.dsa_distances(eng, x, qc, q_off, None, True)
+    for mode, (cnt, idx) in eng.last_cand_cnt_by_mode.items():
+        c = cnt.cpu().numpy()
+        masks = idx.cpu().numpy()[:, :, 1].view(np.uint32)
+        bits = np.array([sum(bin(int(v)).count("1") for v in masks[i, :min(c[i], masks.shape[1])]) for i in range(0, len(c), 7)])
+        print(f"  mode {mode}: candidate chunks per query mean {c.mean():.2f} p50 {np.median(c):.0f} p99 {np.percentile(c, 99):.0f} "
+              f"max {c.max()};  rows to re-rank per query mean {bits.mean():.1f} p50 {np.median(bits):.0f} p99 {np.percentile(bits, 99):.0f} max {bits.max()}")
     mn, med = timed(lambda: sa(xte, pte), n=5)
     print(f"DSA C2 end-to-end (host numpy in/out): min {mn:.3f} ms median {med:.3f} ms")
     t0 = time.time(); sa(xte, pte); print(f"  wall {1e3 * (time.time() - t0):.3f} ms")
