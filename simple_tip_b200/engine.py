@@ -71,9 +71,18 @@ def class_layout(labels: np.ndarray, num_classes: int) -> Tuple[np.ndarray, np.n
     positions of rows with 0 <= label < num_classes, grouped by class, ascending position inside
     a class (the order `np.argwhere(pred == label)` gives, surprise.py:554,581)."""
     labels = np.asarray(labels)
-    valid = np.flatnonzero((labels >= 0) & (labels < num_classes))
-    order = valid[np.argsort(labels[valid], kind="stable")]
-    counts = np.bincount(labels[valid].astype(np.int64), minlength=num_classes)[:num_classes]
+    ok = (labels >= 0) & (labels < num_classes)
+    # NumPy's stable sort is a radix sort for <= 16-bit integers: ~10x faster than on int64
+    small = np.uint16 if num_classes <= 65535 else np.int64
+    if ok.all():
+        keys = labels.astype(small)
+        order = np.argsort(keys, kind="stable")
+        counts = np.bincount(keys, minlength=num_classes)[:num_classes]
+    else:
+        valid = np.flatnonzero(ok)
+        keys = labels[valid].astype(small)
+        order = valid[np.argsort(keys, kind="stable")]
+        counts = np.bincount(keys, minlength=num_classes)[:num_classes]
     offsets = np.zeros(num_classes + 1, dtype=np.int64)
     np.cumsum(counts, out=offsets[1:])
     return order, offsets

@@ -1,0 +1,51 @@
+"""Host-side breakdown of DSA.__call__ (bring-up tool)."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from oracle import np_oracle  # noqa: E402
+from simple_tip_b200 import engine as E  # noqa: E402
+from simple_tip_b200.core import surprise as S  # noqa: E402
+
+xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(60000, 10000, 128, 10, seed=2)
+sa = S.DSA(xtr, ytr)
+pin = torch.from_numpy(xte).pin_memory().numpy()
+for _ in range(5):
+    sa(pin, pte)
+
+
+def T():
+    torch.cuda.synchronize()
+    return time.perf_counter()
+
+
+reps = 20
+acc = {}
+for _ in range(reps):
+    t = [T()]
+    target_pred = S._class_predictions(pte); t.append(T())
+    order, q_off = E.class_layout(target_pred, 10); t.append(T())
+    x_all = E.to_device(pin, sa._engine.dev); t.append(T())
+    idx = torch.from_numpy(order).to(sa._engine.dev, non_blocking=True); t.append(T())
+    plan = E.dsa_plan(sa._engine, int(order.size), q_off, x_all.dtype, True); t.append(T())
+    torch.index_select(x_all, 0, idx, out=plan.x); t.append(T())
+    out = plan.run(); t.append(T())
+    res = out.cpu().numpy(); t.append(T())
+    a = res[0].astype(np.float32); b = res[1].astype(np.float32); g = res[2].astype(np.int64)
+    dsa = np.full(10000, np.nan); w = np.full(10000, -1, dtype=np.int64); w[order] = g
+    la = np.full(10000, np.nan, dtype=np.float32); lb = np.full(10000, np.nan, dtype=np.float32)
+    la[order], lb[order] = a, b
+    dsa[order] = a / b; t.append(T())
+    names = ["class_predictions", "class_layout", "H2D traces (pinned)", "H2D order", "plan lookup", "gather", "graph replay", "D2H", "numpy scatter"]
+    for n, d in zip(names, np.diff(t)):
+        acc[n] = acc.get(n, 0) + d
+for n, v in acc.items():
+    print(f"{n:24s} {1e6 * v / reps:8.1f} us")
+t0 = T()
+for _ in range(reps):
+    sa(pin, pte)
+print("full __call__", 1e6 * (T() - t0) / reps, "us")
