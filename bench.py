@@ -181,6 +181,7 @@ def run_ours(args):
     plan = None
     if comm is None and sa.use_graphs:
         # steady-state path of DSA.__call__: the whole two-stage search replayed as one CUDA graph
+        # (sharded runs launch eagerly: NCCL all-reduces sit between the kernels)
         plan = E.dsa_plan(eng, n_test, q_off, x_sorted.dtype, sa.use_filter)
         plan.x.copy_(x_sorted)
 

@@ -67,7 +67,8 @@ typedef struct tip_work_item {
   int32_t col0;    /* first train row of the span                                   */
   int32_t col1;    /* one past the last train row of the span                       */
   int32_t slot;    /* tip_kde_lse: partial-result slot of this span; unused otherwise */
-  int32_t reserved;
+  int32_t reserved; /* flags: bit 0 = every query ignores the train rows of its own class
+                     * (tip_nn_filter with q_class / class_off) */
 } tip_work_item;
 
 int tip_version(void);
@@ -122,11 +123,15 @@ int tip_nn_query_prep(const void* q, int dtype, int64_t m, int64_t d, const floa
  * mask of the rows of the chunk that pass (cand_idx holds 2*cap int32 per query); cand_cnt[row]
  * counts appends (may exceed cap: overflow -> tip_nn_rerank falls back to an exact scan).
  * row_min_bits[m] (uint32 float bits, initialised to +inf = 0x7f800000 by the caller) carries
- * the running minimum across items/CTAs.  t_rmax = max_j |h(y_j)| over the train rows. */
+ * the running minimum across items/CTAs.  t_rmax = max_j |h(y_j)| over the train rows.
+ * q_class[m] / class_off[C+1] (may be NULL if no item sets flag bit 0): for flagged items a query of
+ * class c ignores train rows [class_off[c], class_off[c+1]) — DSA's other-class search over
+ * query tiles that mix classes (surprise.py:622-629). */
 int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const void* t_pack,
                   int64_t n, int64_t d, int64_t pitch, const tip_work_item* items,
-                  int32_t n_items, float t_rmax, uint32_t* row_min_bits, int32_t* cand_idx,
-                  int32_t* cand_cnt, int32_t cap, void* stream);
+                  int32_t n_items, const int32_t* q_class, const int32_t* class_off, float t_rmax,
+                  uint32_t* row_min_bits, int32_t* cand_idx, int32_t* cand_cnt, int32_t cap,
+                  void* stream);
 
 /* Tile geometry tip_nn_filter uses for traces of width d: work items must start on query rows
  * that are multiples of nothing in particular but cover at most *q_rows rows (128, or 256 for
@@ -143,8 +148,10 @@ int tip_nn_filter_tile(int64_t d, int32_t* q_rows, int32_t* t_rows);
  * out_dist[m] (dtype) = sqrt(pairwise_sum((x-y)^2)) of the winner, out_pos[m] = its train row
  * (ties: lowest t_gid); optional out_gid[m] = t_gid of the winner (-1 if none) and
  * out_rows[m x d] = a copy of the winning train rows (DSA's stage-2 queries, surprise.py:648).
- * work: int32 scratch of m + 1 entries (queue of queries that need the exhaustive scan).
+ * work: scratch of tip_nn_rerank_work_bytes(m, dtype) bytes (queue of queries that need the
+ * exhaustive scan + the per-slice partial winners of that scan).
  * stats[0] += exhaustive rows, stats[1] += candidate entries walked. */
+int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype);
 int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n, int64_t d,
                   const int32_t* cand_idx, const int32_t* cand_cnt, int32_t cap,
                   const int32_t* q_class, const int32_t* class_off, int32_t n_classes, int mode,

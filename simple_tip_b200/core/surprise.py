@@ -371,7 +371,9 @@ class DSA(SA):
         idx = torch.from_numpy(order).to(dev, non_blocking=True)
         sharded = self._comm is not None and self._comm.world > 1
         if self.use_graphs and not sharded:
-            # steady state: gather straight into the captured graph's input, one replay
+            # steady state: gather straight into the captured graph's input, one replay.  (Capturing
+            # the NCCL all-reduces of the sharded path works in the 2-GPU parity test but hung in a
+            # mixed eager/replay sequence, so sharded calls launch eagerly for now.)
             plan = E.dsa_plan(eng, int(order.size), q_off, x_all.dtype, self.use_filter)
             torch.index_select(x_all, 0, idx, out=plan.x)
             packed = plan.run()

@@ -45,6 +45,8 @@ struct PairArgs {
   int k16;  // number of K=16 MMA steps per tile (packed width / 16)
   int64_t m;
   // MODE_NN
+  const int32_t* q_class;     // with class_off: per-query excluded train range (items flagged 1)
+  const int32_t* class_off;
   const float* q_sqnorm;
   float rmax, eps2, gamma;  // error-window constants
   uint32_t* row_min_bits;
@@ -177,6 +179,7 @@ struct EpiState {
   bool valid_row;
   int64_t row;
   int col1;
+  int ex_lo, ex_hi;                    // train rows this query must ignore (its own class), or empty
   float nx, e2, g, best, thr, s_ref;   // MODE_NN
   int n_staged;
   float run_max, run_sum;              // MODE_LSE
@@ -201,7 +204,10 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
 }
 
 // Reduce 32 accumulator columns [cbase, cbase+32) of one query row.
-template <int MODE>
+// (Keeping the rare paths out of line was tried and is far slower: taking the address of the
+// register tile demotes it to local memory.  Code size is what matters here: the four unrolled
+// chunk bodies of a tile have to stay inside the instruction cache.)
+template <int MODE, bool EXCL>
 __device__ __forceinline__ void epi_chunk(const PairArgs& args, EpiState& st, const EpiShared& sh, uint32_t (&r)[32],
                                           int cbase, bool partial, bool dump_tile, int dump_row, int dump_col) {
   const float kInf = __int_as_float(0x7f800000);
@@ -211,13 +217,13 @@ __device__ __forceinline__ void epi_chunk(const PairArgs& args, EpiState& st, co
       for (int j = 0; j < 32; j++) args.dump[(int64_t)dump_row * 256 + dump_col + j] = __uint_as_float(r[j]);
     }
   } else if (MODE == MODE_NN) {
-    // Candidates are tracked per group of 8 consecutive train rows: one min per group, so the
-    // (frequent: 32 independent queries per warp) event path is a few dozen instructions.  The
-    // re-rank evaluates all rows of a surviving group exactly.
-    if (partial) {
+    if (partial || (EXCL && cbase < st.ex_hi && cbase + 32 > st.ex_lo)) {
+      // rare: the chunk runs past the span, or overlaps the train rows this query must ignore
 #pragma unroll
-      for (int j = 0; j < 32; j++)
-        if (cbase + j >= st.col1) r[j] = 0x7f800000u;
+      for (int j = 0; j < 32; j++) {
+        const int c = cbase + j;
+        if (c >= st.col1 || (EXCL && c >= st.ex_lo && c < st.ex_hi)) r[j] = 0x7f800000u;
+      }
     }
     float gmin[4];
 #pragma unroll
@@ -301,7 +307,7 @@ __device__ __forceinline__ void epi_chunk(const PairArgs& args, EpiState& st, co
   }
 }
 
-template <int MODE>
+template <int MODE, bool EXCL>
 __global__ void __launch_bounds__(kThreads, 1)
 pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PairArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -361,37 +367,46 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
-        const tip_work_item it = args.items[w];
-        const int ntiles = (it.col1 - it.col0 + BN - 1) / BN;
-        for (int t = 0; t < ntiles; t++) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+    // Whole warp runs the loop (uniform control flow -> descriptors live in uniform registers),
+    // one elected lane issues; full chunks are four straight-line MMAs.
+    const bool leader = elect_one();
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+      const tip_work_item it = args.items[w];
+      const int ntiles = (it.col1 - it.col0 + BN - 1) / BN;
+      for (int t = 0; t < ntiles; t++) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        for (int c = 0; c < nchunks; c++) {
+          mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-          for (int c = 0; c < nchunks; c++) {
-            mbar_wait(full_bar(stage), phase);
-            tc_fence_after();
-            const uint32_t a_addr = base + stage * kStageBytes;
-            const uint64_t adesc = smem_desc(a_addr);
-            const uint64_t bdesc = smem_desc(a_addr + kABytes);
-            const int nm = min(4, k16 - 4 * c);
-            for (int k = 0; k < nm; k++) {
-              // +32 bytes (one K=16 slice) inside the 128-byte swizzle row = +2 in the >>4 field
-              umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc, (uint32_t)((c | k) != 0));
+          const uint32_t a_addr = base + stage * kStageBytes;
+          const uint64_t adesc = smem_desc(a_addr);
+          const uint64_t bdesc = smem_desc(a_addr + kABytes);
+          const int nm = min(4, k16 - 4 * c);
+          if (leader) {
+            // +32 bytes (one K=16 slice) inside the 128-byte swizzle row = +2 in the >>4 field
+            if (c == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdesc);
+            else umma_bf16_acc(d_tmem, adesc, bdesc, kIdesc);
+            if (nm == 4) {
+              umma_bf16_acc(d_tmem, adesc + 2u, bdesc + 2u, kIdesc);
+              umma_bf16_acc(d_tmem, adesc + 4u, bdesc + 4u, kIdesc);
+              umma_bf16_acc(d_tmem, adesc + 6u, bdesc + 6u, kIdesc);
+            } else {
+              for (int k = 1; k < nm; k++) umma_bf16_acc(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc);
             }
             umma_commit(empty_bar(stage));
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            if (c == nchunks - 1) umma_commit(tfull_bar(acc));
           }
-          umma_commit(tfull_bar(acc));
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1u;
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
       }
     }
-    __syncwarp();
   } else {
     // ================= epilogue =================
     // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.
@@ -419,7 +434,13 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       st.nx = 0.f; st.e2 = 0.f; st.g = 0.f; st.best = kInf; st.thr = kInf; st.s_ref = kInf; st.n_staged = 0;
       st.run_max = -kInf; st.run_sum = 0.f;
       st.col1 = it.col1;
+      st.ex_lo = 0; st.ex_hi = 0;
       if (MODE == MODE_NN && st.valid_row) {
+        if (EXCL && (it.reserved & 1) && args.q_class) {
+          const int cls = args.q_class[st.row];
+          st.ex_lo = args.class_off[cls];
+          st.ex_hi = args.class_off[cls + 1];
+        }
         st.nx = args.q_sqnorm[st.row];
         const float r = sqrtf(st.nx) + args.rmax;
         st.e2 = args.eps2 * r;
@@ -440,21 +461,24 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // flight while chunk q is reduced
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr, ra);
-        tmem_wait_ld();
-        tmem_ld32(taddr + 32, rb);
-        epi_chunk<MODE>(args, st, sh, ra, col_base, partial, w == 0 && t == 0, row_local, half * (BN / 2));
-        tmem_wait_ld();
-        tmem_ld32(taddr + 64, ra);
-        epi_chunk<MODE>(args, st, sh, rb, col_base + 32, partial, w == 0 && t == 0, row_local, half * (BN / 2) + 32);
-        tmem_wait_ld();
-        tmem_ld32(taddr + 96, rb);
-        epi_chunk<MODE>(args, st, sh, ra, col_base + 64, partial, w == 0 && t == 0, row_local, half * (BN / 2) + 64);
-        tmem_wait_ld();
-        // accumulator drained into registers: hand the TMEM stage back to the MMA warp early
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        epi_chunk<MODE>(args, st, sh, rb, col_base + 96, partial, w == 0 && t == 0, row_local, half * (BN / 2) + 96);
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {   // rolled on purpose: the epilogue has to stay inside the I-cache
+          tmem_wait_ld();
+          tmem_ld32(taddr + 64 * h + 32, rb);
+          epi_chunk<MODE, EXCL>(args, st, sh, ra, col_base + 64 * h, partial, w == 0 && t == 0, row_local,
+                          half * (BN / 2) + 64 * h);
+          tmem_wait_ld();
+          if (h == 0) {
+            tmem_ld32(taddr + 64, ra);
+          } else {
+            // accumulator drained into registers: hand the TMEM stage back to the MMA warp early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          epi_chunk<MODE, EXCL>(args, st, sh, rb, col_base + 64 * h + 32, partial, w == 0 && t == 0, row_local,
+                          half * (BN / 2) + 64 * h + 32);
+        }
 
         if (MODE == MODE_NN && st.valid_row) {
           // share the running minimum across everybody scanning other columns for the same query
@@ -545,7 +569,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
 }
 
-template <int MODE, int K16>
+template <int MODE, int K16, bool EXCL>
 __global__ void __launch_bounds__(kThreads, 1)
 pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAt,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt, const PairArgs args) {
@@ -706,7 +730,13 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       st.nx = 0.f; st.e2 = 0.f; st.g = 0.f; st.best = kInf; st.thr = kInf; st.s_ref = kInf; st.n_staged = 0;
       st.run_max = -kInf; st.run_sum = 0.f;
       st.col1 = it.col1;
+      st.ex_lo = 0; st.ex_hi = 0;
       if (MODE == MODE_NN && st.valid_row) {
+        if (EXCL && (it.reserved & 1) && args.q_class) {
+          const int cls = args.q_class[st.row];
+          st.ex_lo = args.class_off[cls];
+          st.ex_hi = args.class_off[cls + 1];
+        }
         st.nx = args.q_sqnorm[st.row];
         const float r = sqrtf(st.nx) + args.rmax;
         st.e2 = args.eps2 * r;
@@ -727,21 +757,22 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t taddr = lane_addr + (uint32_t)(acc * 256);
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr, ra);
-        tmem_wait_ld();
-        tmem_ld32(taddr + 32, rb);
-        epi_chunk<MODE>(args, st, sh, ra, col_base, partial, dump, row_local, t * RS_BN);
-        tmem_wait_ld();
-        tmem_ld32(taddr + 64, ra);
-        epi_chunk<MODE>(args, st, sh, rb, col_base + 32, partial, dump, row_local, t * RS_BN + 32);
-        tmem_wait_ld();
-        tmem_ld32(taddr + 96, rb);
-        epi_chunk<MODE>(args, st, sh, ra, col_base + 64, partial, dump, row_local, t * RS_BN + 64);
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(10 + acc));
-        if (threadIdx.x == 64) TL(6);
-        epi_chunk<MODE>(args, st, sh, rb, col_base + 96, partial, dump, row_local, t * RS_BN + 96);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {   // unrolled: measured faster than rolled for this kernel
+          tmem_wait_ld();
+          tmem_ld32(taddr + 64 * h + 32, rb);
+          epi_chunk<MODE, EXCL>(args, st, sh, ra, col_base + 64 * h, partial, dump, row_local, t * RS_BN + 64 * h);
+          tmem_wait_ld();
+          if (h == 0) {
+            tmem_ld32(taddr + 64, ra);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(10 + acc));
+            if (threadIdx.x == 64) TL(6);
+          }
+          epi_chunk<MODE, EXCL>(args, st, sh, rb, col_base + 64 * h + 32, partial, dump, row_local, t * RS_BN + 64 * h + 32);
+        }
         if (MODE == MODE_NN && st.valid_row) {
           const float mine = fmaxf(st.best + st.nx, 0.f);
           const float seen = __uint_as_float(seen_bits);
@@ -825,7 +856,7 @@ static int check_device() {
   return TIP_OK;
 }
 
-template <int MODE>
+template <int MODE, bool EXCL = false>
 static int launch_pair(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t pitch, PairArgs args,
                        cudaStream_t st) {
   int rc = check_device();
@@ -838,18 +869,18 @@ static int launch_pair(const void* q_pack, int64_t m, const void* t_pack, int64_
   if (rc != TIP_OK) return rc;
   rc = make_map(&mb, t_pack, n, pitch, BN);
   if (rc != TIP_OK) return rc;
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[MODE]) {
-    TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set[MODE] = true;
+  static bool attr_set = false;   // one flag per template instantiation
+  if (!attr_set) {
+    TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_kernel<MODE, EXCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
   }
   const int grid = min(args.n_items, sm_count());
-  pair_kernel<MODE><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, args);
+  pair_kernel<MODE, EXCL><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, args);
   TIP_LAUNCH_CHECK();
   return TIP_OK;
 }
 
-template <int MODE>
+template <int MODE, bool EXCL = false>
 static int launch_pair_rs(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t pitch, PairArgs args,
                           cudaStream_t st) {
   int rc = check_device();
@@ -863,11 +894,11 @@ static int launch_pair_rs(const void* q_pack, int64_t m, const void* t_pack, int
   if ((rc = make_map(&mb, t_pack, n, pitch, RS_BN, 64)) != TIP_OK) return rc;
   if ((rc = make_map(&mbt, t_pack, n, pitch, RS_BN, 16)) != TIP_OK) return rc;
   const int smem = rs_smem_bytes(kRsMaxK16);
-  static bool attr_set[3][kRsMaxK16 + 1] = {};
-  if (!attr_set[MODE][args.k16]) {
+  static bool attr_set[kRsMaxK16 + 1] = {};   // per template instantiation
+  if (!attr_set[args.k16]) {
 #define TIP_RS_ATTR(K)                                                                                   \
   case K:                                                                                                \
-    TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_rs_kernel<MODE, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_rs_kernel<MODE, K, EXCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
     break;
     switch (args.k16) {
       TIP_RS_ATTR(1) TIP_RS_ATTR(2) TIP_RS_ATTR(3) TIP_RS_ATTR(4) TIP_RS_ATTR(5)
@@ -875,13 +906,13 @@ static int launch_pair_rs(const void* q_pack, int64_t m, const void* t_pack, int
       default: TIP_REQUIRE(false, "k16");
     }
 #undef TIP_RS_ATTR
-    attr_set[MODE][args.k16] = true;
+    attr_set[args.k16] = true;
   }
   const int grid = std::min(args.n_items, sm_count());
   const int smem_k = rs_smem_bytes(args.k16);
 #define TIP_RS_CASE(K)                                                                                   \
   case K:                                                                                                \
-    pair_rs_kernel<MODE, K><<<grid, kThreads, smem_k, st>>>(ma, mat, mb, mbt, args);                     \
+    pair_rs_kernel<MODE, K, EXCL><<<grid, kThreads, smem_k, st>>>(ma, mat, mb, mbt, args);               \
     break;
   switch (args.k16) {
     TIP_RS_CASE(1) TIP_RS_CASE(2) TIP_RS_CASE(3) TIP_RS_CASE(4) TIP_RS_CASE(5)
@@ -911,7 +942,8 @@ extern "C" int tip_debug_timeline(long long* buf, int32_t tiles) {
 }
 
 extern "C" int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const void* t_pack, int64_t n,
-                             int64_t d, int64_t pitch, const tip_work_item* items, int32_t n_items, float t_rmax,
+                             int64_t d, int64_t pitch, const tip_work_item* items, int32_t n_items,
+                             const int32_t* q_class, const int32_t* class_off, float t_rmax,
                              uint32_t* row_min_bits, int32_t* cand_idx, int32_t* cand_cnt, int32_t cap,
                              void* stream) {
   TIP_REQUIRE(q_pack && q_sqnorm && t_pack && items && row_min_bits && cand_idx && cand_cnt, "null pointer");
@@ -921,6 +953,7 @@ extern "C" int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t 
   PairArgs a{};
   a.items = items; a.n_items = n_items; a.k16 = k16_of(d, 1); a.m = m;
   a.q_sqnorm = q_sqnorm; a.rmax = t_rmax;
+  a.q_class = q_class; a.class_off = class_off;
   // eps' = (2^-9 + 2^-23)/(1 - that): bf16 rounding of the centred traces (triangle inequality);
   // gamma: fp32 accumulation over K products + norm rounding, assuming nothing better than
   // truncating adds inside the tensor core.
@@ -928,8 +961,12 @@ extern "C" int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t 
   a.gamma = (float)(a.k16 * 16 + 16) * 1.1920929e-7f;
   a.row_min_bits = row_min_bits; a.cand_idx = cand_idx; a.cand_cnt = cand_cnt; a.cap = cap;
   a.timeline = g_timeline; a.timeline_tiles = g_timeline_tiles;
-  if (a.k16 <= kRsMaxK16) return launch_pair_rs<MODE_NN>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
-  return launch_pair<MODE_NN>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
+  const bool excl = q_class != nullptr && class_off != nullptr;   // per-query own-class masking compiled in only then
+  if (a.k16 <= kRsMaxK16)
+    return excl ? launch_pair_rs<MODE_NN, true>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream)
+                : launch_pair_rs<MODE_NN, false>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
+  return excl ? launch_pair<MODE_NN, true>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream)
+              : launch_pair<MODE_NN, false>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
 }
 
 extern "C" int tip_nn_filter_tile(int64_t d, int32_t* q_rows, int32_t* t_rows) {

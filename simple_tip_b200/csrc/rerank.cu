@@ -113,12 +113,12 @@ __global__ void __launch_bounds__(256) rerank_list_kernel(const RerankArgs<T> a)
     if (e < cnt) {
       const int start = a.cand_idx[(row * (int64_t)a.cap + e) * 2];
       unsigned cmask = (unsigned)a.cand_idx[(row * (int64_t)a.cap + e) * 2 + 1];
-      const int limit = a.mode == TIP_RANGE_SAME_CLASS ? c1 : (start < c0 ? c0 : cn);
       while (cmask) {
         const int bit = __ffs(cmask) - 1;
         cmask &= cmask - 1;
         const int j = start + bit;
-        if (start < 0 || j >= limit || j >= a.n) continue;
+        const bool in_range = a.mode == TIP_RANGE_SAME_CLASS ? (j >= c0 && j < c1) : (j >= 0 && j < cn && (j < c0 || j >= c1));
+        if (!in_range || j >= a.n) continue;
         const T s = np_sumsq_g8<T>(x, a.t + (int64_t)j * a.d, a.d, sub, gmask);
         consider(best, Rn<T>::sqrt(s), a.t_gid ? a.t_gid[j] : j, j);   // all 8 lanes agree
       }
@@ -135,43 +135,99 @@ __global__ void __launch_bounds__(256) rerank_list_kernel(const RerankArgs<T> a)
   write_result(a, row, best, lane, 32);
 }
 
-// ---- kernel 2: one block per queued query, exhaustive scan of its class range --------------------
+// ---- kernels 2+3: exhaustive scan of the class range for queued queries ---------------------------
+// The queue is normally empty or a handful of queries, each needing up to N x D work, so every
+// queued query is split into S column slices ("units") spread over the whole grid; a unit writes
+// its local winner to scratch and a merge kernel picks the lexicographic minimum per query.
+constexpr int kScanUnitTarget = 4096;
+
+__device__ __forceinline__ int scan_slices(int queued) {
+  const int s = kScanUnitTarget / max(queued, 1);
+  return s < 1 ? 1 : (s > 64 ? 64 : s);
+}
+
+template <typename T>
+struct ScanScratch {
+  T* dist;
+  int32_t* gid;
+  int32_t* pos;
+};
+
+template <typename T>
+__device__ __forceinline__ ScanScratch<T> scan_scratch(const RerankArgs<T>& a) {
+  // layout after the queue (1 + m ints): [cap] T dist (8-byte aligned), [cap] gid, [cap] pos
+  const int64_t cap = a.m + kScanUnitTarget;
+  uintptr_t base = reinterpret_cast<uintptr_t>(a.work + 1 + a.m);
+  base = (base + 7) & ~(uintptr_t)7;
+  ScanScratch<T> sc;
+  sc.dist = reinterpret_cast<T*>(base);
+  sc.gid = reinterpret_cast<int32_t*>(sc.dist + cap);
+  sc.pos = sc.gid + cap;
+  return sc;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kScanThreads) rerank_scan_kernel(const RerankArgs<T> a) {
   __shared__ T s_dist[kScanThreads / 8];
   __shared__ int s_gid[kScanThreads / 8];
   __shared__ int s_pos[kScanThreads / 8];
-  __shared__ Best<T> s_best;
   const int queued = a.work[0];
+  if (queued == 0) return;
+  const int S = scan_slices(queued);
+  const ScanScratch<T> sc = scan_scratch(a);
   const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
   constexpr int kGroups = kScanThreads / 8;
   const unsigned gmask = 0xFFu << (threadIdx.x & 24);
-  for (int w = blockIdx.x; w < queued; w += gridDim.x) {
+  const int64_t units = (int64_t)queued * S;
+  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+    const int w = (int)(u / S), sl = (int)(u % S);
     const int64_t row = a.work[1 + w];
     const int cls = a.q_class ? a.q_class[row] : 0;
     const T* x = a.q + row * (int64_t)a.d;
     Best<T> best{Rn<T>::inf(), 0x7fffffff, -1};
     const int c0 = a.class_off[cls], c1 = a.class_off[cls + 1], cn = a.class_off[a.n_classes];
-    // SAME_CLASS: [c0, c1);  OTHER_CLASSES: [0, c0) U [c1, cn)
-    const int lo[2] = {a.mode == TIP_RANGE_SAME_CLASS ? c0 : 0, a.mode == TIP_RANGE_SAME_CLASS ? 0 : c1};
-    const int hi[2] = {a.mode == TIP_RANGE_SAME_CLASS ? c1 : c0, a.mode == TIP_RANGE_SAME_CLASS ? 0 : cn};
-    for (int rg = 0; rg < 2; rg++) {
-      for (int j = lo[rg] + grp; j < hi[rg]; j += kGroups) {
-        const T s = np_sumsq_g8<T>(x, a.t + (int64_t)j * a.d, a.d, sub, gmask);
-        consider(best, Rn<T>::sqrt(s), a.t_gid ? a.t_gid[j] : j, j);
-      }
+    // SAME_CLASS: [c0, c1);  OTHER_CLASSES: [0, c0) U [c1, cn) — as one linear index space
+    const int len0 = a.mode == TIP_RANGE_SAME_CLASS ? c1 - c0 : c0;
+    const int len1 = a.mode == TIP_RANGE_SAME_CLASS ? 0 : cn - c1;
+    const int base0 = a.mode == TIP_RANGE_SAME_CLASS ? c0 : 0;
+    const int64_t total = (int64_t)len0 + len1;
+    const int64_t lo = total * sl / S, hi = total * (sl + 1) / S;
+    for (int64_t li = lo + grp; li < hi; li += kGroups) {
+      const int j = li < len0 ? base0 + (int)li : c1 + (int)(li - len0);
+      const T s = np_sumsq_g8<T>(x, a.t + (int64_t)j * a.d, a.d, sub, gmask);
+      consider(best, Rn<T>::sqrt(s), a.t_gid ? a.t_gid[j] : j, j);
     }
     if (sub == 0) { s_dist[grp] = best.dist; s_gid[grp] = best.gid; s_pos[grp] = best.pos; }
     __syncthreads();
     if (threadIdx.x == 0) {
       Best<T> b{Rn<T>::inf(), 0x7fffffff, -1};
       for (int g = 0; g < kGroups; g++) b = merge(b, s_dist[g], s_gid[g], s_pos[g]);
-      s_best = b;
-      if (a.stats) atomicAdd(a.stats + 0, 1ULL);
+      sc.dist[u] = b.dist; sc.gid[u] = b.gid; sc.pos[u] = b.pos;
     }
     __syncthreads();
-    write_result(a, row, s_best, threadIdx.x, kScanThreads);
-    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) rerank_merge_kernel(const RerankArgs<T> a) {
+  const int queued = a.work[0];
+  const int S = scan_slices(queued);
+  const ScanScratch<T> sc = scan_scratch(a);
+  const int lane = threadIdx.x & 31;
+  for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < queued; w += gridDim.x * 8) {
+    Best<T> best{Rn<T>::inf(), 0x7fffffff, -1};
+    for (int sl = lane; sl < S; sl += 32) {
+      const int64_t u = (int64_t)w * S + sl;
+      best = merge(best, sc.dist[u], sc.gid[u], sc.pos[u]);
+    }
+    for (int o = 1; o < 32; o <<= 1) {
+      const T od = __shfl_xor_sync(0xffffffffu, best.dist, o);
+      const int og = __shfl_xor_sync(0xffffffffu, best.gid, o);
+      const int op = __shfl_xor_sync(0xffffffffu, best.pos, o);
+      best = merge(best, od, og, op);
+    }
+    if (lane == 0 && a.stats) atomicAdd(a.stats + 0, 1ULL);
+    write_result(a, a.work[1 + w], best, lane, 32);
   }
 }
 
@@ -181,8 +237,9 @@ static int launch_rerank(const RerankArgs<T>& a, cudaStream_t st) {
   const int64_t blocks = (a.m + 7) / 8;
   rerank_list_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a);
   TIP_LAUNCH_CHECK();
-  const int grid = (int)std::min<int64_t>(a.m, (int64_t)sm_count() * 8);
-  rerank_scan_kernel<T><<<grid, kScanThreads, 0, st>>>(a);
+  rerank_scan_kernel<T><<<sm_count() * 8, kScanThreads, 0, st>>>(a);
+  TIP_LAUNCH_CHECK();
+  rerank_merge_kernel<T><<<std::max(1, std::min(sm_count(), (int)((a.m + 7) / 8))), 256, 0, st>>>(a);
   TIP_LAUNCH_CHECK();
   return TIP_OK;
 }
@@ -190,6 +247,12 @@ static int launch_rerank(const RerankArgs<T>& a, cudaStream_t st) {
 }  // namespace tip
 
 using namespace tip;
+
+extern "C" int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype) {
+  if (m < 0) return -1;
+  const int64_t cap = m + kScanUnitTarget;
+  return (1 + m) * 4 + 8 + cap * ((dtype == TIP_F64 ? 8 : 4) + 8);
+}
 
 extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n, int64_t d,
                              const int32_t* cand_idx, const int32_t* cand_cnt, int32_t cap, const int32_t* q_class,

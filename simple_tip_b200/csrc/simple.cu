@@ -183,6 +183,8 @@ __device__ __forceinline__ int kmnc_bucket(TA a_in, TS lo, TS jump, int k) {
     const double est = ((double)a_in - (double)lo) / (double)jump;
     i = est >= (double)(k - 1) ? k - 1 : (est > 0.0 ? (int)est : 0);
   }
+  // common case: the estimate is already the section (one exact check); otherwise walk
+  if (a >= t(i) && a < t(i + 1)) return i;
   while (i > 0 && a < t(i)) i--;
   while (i < k - 1 && a >= t(i + 1)) i++;
   // i is now the only possible section; NaN / out-of-range values fail this test
@@ -228,33 +230,48 @@ __global__ void __launch_bounds__(256) kmnc_vec4_kernel(const float* __restrict_
   const int64_t cpr = (d4 + 31) >> 5;  // chunks per row
   const int64_t total = n * cpr;
   const int64_t nwarps = (int64_t)gridDim.x * 8;
-  for (int64_t chunk = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); chunk < total; chunk += nwarps) {
-    const int64_t row = chunk / cpr;
-    const int64_t j = (chunk - row * cpr) * 32 + lane;
-    int cnt = 0;
-    if (j < d4) {
-      float4 v;
-      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                   : "l"(reinterpret_cast<const float4*>(act + row * d) + j));
-      const float4 lo = __ldg(reinterpret_cast<const float4*>(mins) + j);
-      const float4 jp = __ldg(reinterpret_cast<const float4*>(jumps) + j);
-      const int i0 = kmnc_bucket<float, float>(v.x, lo.x, jp.x, k);
-      const int i1 = kmnc_bucket<float, float>(v.y, lo.y, jp.y, k);
-      const int i2 = kmnc_bucket<float, float>(v.z, lo.z, jp.z, k);
-      const int i3 = kmnc_bucket<float, float>(v.w, lo.w, jp.w, k);
-      cnt = (i0 >= 0) + (i1 >= 0) + (i2 >= 0) + (i3 >= 0);
-      if (bucket) {
-        TB* b = bucket + row * d + (j << 2);
-        if (sizeof(TB) == 2) {
-          *reinterpret_cast<short4*>(b) = make_short4((short)i0, (short)i1, (short)i2, (short)i3);
-        } else {
-          *reinterpret_cast<int4*>(b) = make_int4(i0, i1, i2, i3);
-        }
+  constexpr int kUnroll = 4;   // four independent 16-byte loads in flight per thread
+  for (int64_t chunk0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); chunk0 < total; chunk0 += nwarps * kUnroll) {
+    float4 v[kUnroll];
+    int64_t row[kUnroll], j[kUnroll];
+    bool ok[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      const int64_t chunk = chunk0 + (int64_t)u * nwarps;
+      row[u] = chunk / cpr;
+      j[u] = (chunk - row[u] * cpr) * 32 + lane;
+      ok[u] = chunk < total && j[u] < d4;
+      if (ok[u]) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                     : "l"(reinterpret_cast<const float4*>(act + row[u] * d) + j[u]));
       }
     }
-    cnt = warp_sum(cnt);
-    if (lane == 0 && cnt) atomicAdd(score + row, cnt);
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      int cnt = 0;
+      if (ok[u]) {
+        const float4 lo = __ldg(reinterpret_cast<const float4*>(mins) + j[u]);
+        const float4 jp = __ldg(reinterpret_cast<const float4*>(jumps) + j[u]);
+        const int i0 = kmnc_bucket<float, float>(v[u].x, lo.x, jp.x, k);
+        const int i1 = kmnc_bucket<float, float>(v[u].y, lo.y, jp.y, k);
+        const int i2 = kmnc_bucket<float, float>(v[u].z, lo.z, jp.z, k);
+        const int i3 = kmnc_bucket<float, float>(v[u].w, lo.w, jp.w, k);
+        cnt = (i0 >= 0) + (i1 >= 0) + (i2 >= 0) + (i3 >= 0);
+        if (bucket) {
+          TB* bp = bucket + row[u] * d + (j[u] << 2);
+          if (sizeof(TB) == 2) {
+            *reinterpret_cast<short4*>(bp) = make_short4((short)i0, (short)i1, (short)i2, (short)i3);
+          } else {
+            *reinterpret_cast<int4*>(bp) = make_int4(i0, i1, i2, i3);
+          }
+        }
+      }
+      if (chunk0 + (int64_t)u * nwarps < total) {   // warp-uniform
+        cnt = warp_sum(cnt);
+        if (lane == 0 && cnt) atomicAdd(score + row[u], cnt);
+      }
+    }
   }
 }
 

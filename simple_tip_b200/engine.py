@@ -26,7 +26,8 @@ import torch
 
 from . import _lib
 
-DEFAULT_CAP = 64
+DEFAULT_CAP = 64          # candidate chunks per query (short traces)
+DEFAULT_CAP_LONG = 256    # long traces: distances concentrate, more rows fall inside the window
 
 # bench.py sets this to a list to collect (kernel name, algorithmic flops, start event, end event)
 # around the tensor-core launches; None (default) records nothing.
@@ -140,6 +141,40 @@ def build_items(q_off: np.ndarray, ranges_per_class: Sequence[Sequence[Tuple[int
     return np.concatenate(out), max_slots
 
 
+def build_other_class_items(q_off: np.ndarray, t_off: np.ndarray, row_tile: int, col_tile: int, span_of) -> np.ndarray:
+    """Work list of DSA's second stage (every query against the train rows of all OTHER classes,
+    surprise.py:622-629).  Queries are tiled in class-sorted order regardless of class boundaries, so
+    tiles are full however many classes there are.  A tile whose queries share one class scans the
+    two train ranges around that class; a tile that mixes classes scans every train row and each
+    query masks out its own class in the epilogue (item flag bit 0)."""
+    q_off = np.asarray(q_off, dtype=np.int64)
+    t_off = np.asarray(t_off, dtype=np.int64)
+    m, n = int(q_off[-1]), int(t_off[-1])
+    if m == 0 or n == 0:
+        return np.zeros((0, 6), dtype=np.int32)
+    starts = np.arange(0, m, row_tile, dtype=np.int64)
+    rows = np.minimum(row_tile, m - starts)
+    first_cls = np.searchsorted(q_off, starts, side="right") - 1
+    last_cls = np.searchsorted(q_off, starts + rows - 1, side="right") - 1
+    single = first_cls == last_cls
+    cols = np.where(single, n - (t_off[np.minimum(first_cls + 1, len(t_off) - 1)] - t_off[first_cls]), n)
+    pairs = int(np.sum(np.ceil(cols / col_tile)))
+    width = span_of(pairs) * col_tile
+    out = []
+    for r0, nr, c, one in zip(starts, rows, first_cls, single):
+        ranges = [(0, int(t_off[c])), (int(t_off[c + 1]), n)] if one else [(0, n)]
+        spans = [(s0, min(s0 + width, hi)) for lo, hi in ranges for s0 in range(lo, hi, width)]
+        if not spans:
+            continue
+        item = np.zeros((len(spans), 6), dtype=np.int32)
+        item[:, 0], item[:, 1] = r0, nr
+        item[:, 2:4] = np.asarray(spans, dtype=np.int64)
+        item[:, 4] = np.arange(len(spans))
+        item[:, 5] = 0 if one else 1
+        out.append(item)
+    return np.concatenate(out) if out else np.zeros((0, 6), dtype=np.int32)
+
+
 def count_tile_pairs(q_off: np.ndarray, ranges_per_class, row_tile: int = _lib.ROW_TILE,
                      col_tile: int = _lib.COL_TILE) -> int:
     total = 0
@@ -217,7 +252,7 @@ class TrainShardComm:
 # nearest-neighbour engine (DSA)
 # ------------------------------------------------------------------------------------------
 class NnEngine:
-    def __init__(self, t_sorted: torch.Tensor, class_off: np.ndarray, t_gid: torch.Tensor, cap: int = DEFAULT_CAP):
+    def __init__(self, t_sorted: torch.Tensor, class_off: np.ndarray, t_gid: torch.Tensor, cap: Optional[int] = None):
         """t_sorted: [n, d] float32/float64 on the GPU, rows grouped by class (offsets class_off,
         ascending original index inside a class); t_gid[n] int32 original indices."""
         self.dev = require_cuda()
@@ -229,7 +264,7 @@ class NnEngine:
         self.num_classes = self.class_off.shape[0] - 1
         self.class_off_dev = torch.from_numpy(self.class_off.astype(np.int32)).to(self.dev)
         self.t_gid = t_gid.to(torch.int32).contiguous()
-        self.cap = int(cap)
+        self.cap = int(cap) if cap else (DEFAULT_CAP if self.d <= 256 else DEFAULT_CAP_LONG)
         self.pitch = int(self.lib.tip_pair_pitch(self.d, 1))
         sms = C.c_int(0)
         _lib.check(self.lib.tip_device_info(C.byref(sms), None, None), "tip_device_info")
@@ -254,7 +289,7 @@ class NnEngine:
 
     @classmethod
     def from_host(cls, train: np.ndarray, labels: np.ndarray, num_classes: int, gids: Optional[np.ndarray] = None,
-                  cap: int = DEFAULT_CAP) -> "NnEngine":
+                  cap: Optional[int] = None) -> "NnEngine":
         dev = require_cuda()
         order, off = class_layout(labels, num_classes)
         t = to_device(train, dev)
@@ -288,19 +323,26 @@ class NnEngine:
             key = (mode, np.asarray(q_off, dtype=np.int64).tobytes())
             plan = self._item_cache.get(key)
             if plan is None:       # host planning + upload once per (mode, class histogram)
-                pairs = count_tile_pairs(q_off, ranges, self.row_tile, self.col_tile)
                 if self.row_tile == 256:    # resident-query kernel: long items amortise the query load
-                    span = span_tiles_for(pairs, self.sms, per_sm=3, lo=24, hi=64)   # and the cold start
+                    span_of = lambda pairs: span_tiles_for(pairs, self.sms, per_sm=3, lo=24, hi=64)
                 else:
-                    span = span_tiles_for(pairs, self.sms)
-                items, _ = build_items(q_off, ranges, span, self.row_tile, self.col_tile)
+                    span_of = lambda pairs: span_tiles_for(pairs, self.sms)
+                populated = int(np.count_nonzero(np.diff(np.asarray(q_off))))
+                if mode == _lib.RANGE_OTHER_CLASSES and m < 2 * self.row_tile * max(1, populated):
+                    # few queries per class: tile across class boundaries (full tiles), per-query masking
+                    items = build_other_class_items(q_off, self.class_off, self.row_tile, self.col_tile, span_of)
+                else:
+                    # many queries per class: class-aligned tiles never touch their own class's rows
+                    pairs = count_tile_pairs(q_off, ranges, self.row_tile, self.col_tile)
+                    items, _ = build_items(q_off, ranges, span_of(pairs), self.row_tile, self.col_tile)
                 flops = 2.0 * self.d * sum(int(q_off[c + 1] - q_off[c]) * sum(int(hi) - int(lo) for lo, hi in ranges[c])
                                            for c in range(self.num_classes))
-                plan = (torch.from_numpy(items).to(self.dev) if items.shape[0] else None, items.shape[0], flops)
+                flagged = bool(items.shape[0] and (items[:, 5] & 1).any())
+                plan = (torch.from_numpy(items).to(self.dev) if items.shape[0] else None, items.shape[0], flops, flagged)
                 if len(self._item_cache) > 64:
                     self._item_cache.clear()
                 self._item_cache[key] = plan
-            items_dev, n_items, flops = plan
+            items_dev, n_items, flops, flagged = plan
             if n_items > 0:
                 q_pack = torch.empty((m, self.pitch), dtype=torch.bfloat16, device=self.dev)
                 q_sq = torch.empty(m, dtype=torch.float32, device=self.dev)
@@ -314,13 +356,15 @@ class NnEngine:
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                     ev[0].record()
                 _lib.check(lib.tip_nn_filter(_p(q_pack), _p(q_sq), m, _p(self.t_pack), self.n, self.d, self.pitch,
-                                             _p(items_dev), n_items, self.rmax, _p(row_min), _p(cand_idx),
+                                             _p(items_dev), n_items, _p(q_class if flagged else None),
+                                             _p(self.class_off_dev if flagged else None), self.rmax,
+                                             _p(row_min), _p(cand_idx),
                                              _p(cand_cnt), self.cap, _stream()), "tip_nn_filter")
                 if ev is not None:
                     ev[1].record()
                     name = "nn_filter_same_class" if mode == _lib.RANGE_SAME_CLASS else "nn_filter_other_classes"
                     PROFILE.append((name, flops, ev[0], ev[1]))
-        work = torch.empty(m + 1, dtype=torch.int32, device=self.dev)
+        work = torch.empty(int(lib.tip_nn_rerank_work_bytes(m, tip_dtype(q.dtype))), dtype=torch.uint8, device=self.dev)
         _lib.check(lib.tip_nn_rerank(_p(q), _p(self.t), tip_dtype(q.dtype), m, self.n, self.d, _p(cand_idx),
                                      _p(cand_cnt), self.cap, _p(q_class), _p(self.class_off_dev), self.num_classes,
                                      mode, _p(self.t_gid), _p(out_dist), _p(out_pos), _p(out_gid), _p(out_rows),
@@ -356,7 +400,8 @@ class DsaPlan:
     ~14 kernels (pack, filter, re-rank, gather, x2) replayed with one launch.  Inputs are copied
     into `x` (class-sorted queries); outputs live in `out` = [dist_a, dist_b, winner index]."""
 
-    def __init__(self, engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool):
+    def __init__(self, engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool,
+                 comm: Optional[TrainShardComm] = None):
         self.engine = engine
         self.q_off = np.asarray(q_off, dtype=np.int64).copy()
         dev = engine.dev
@@ -366,28 +411,41 @@ class DsaPlan:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):          # eager warm-up: fills caches, sets kernel attributes
-            dsa_distances(engine, self.x, self.q_class, self.q_off, None, use_filter)
+            dsa_distances(engine, self.x, self.q_class, self.q_off, comm, use_filter)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            a, b, gid = dsa_distances(engine, self.x, self.q_class, self.q_off, None, use_filter)
-            self.dist_a, self.dist_b, self.gid = a, b, gid
-            # one D2H transfer later: float32/float64 -> float64 and int -> float64 are exact
-            self.out = torch.stack([a.to(torch.float64), b.to(torch.float64), gid.to(torch.float64)])
+        # Garbage from earlier engines (old graphs, their private pools) must not be released in the
+        # middle of the capture: a cudaFree / graph destroy there invalidates it.
+        import gc
+
+        gc.collect()
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                # with a communicator the NCCL all-reduces are captured too (every rank replays in step)
+                a, b, gid = dsa_distances(engine, self.x, self.q_class, self.q_off, comm, use_filter)
+                self.dist_a, self.dist_b, self.gid = a, b, gid
+                # one D2H transfer later: float32/float64 -> float64 and int -> float64 are exact
+                self.out = torch.stack([a.to(torch.float64), b.to(torch.float64), gid.to(torch.float64)])
+        finally:
+            if was_enabled:
+                gc.enable()
 
     def run(self):
         self.graph.replay()
         return self.out
 
 
-def dsa_plan(engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool) -> DsaPlan:
-    key = (m, np.asarray(q_off, dtype=np.int64).tobytes(), dtype, use_filter, engine.cap)
+def dsa_plan(engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool,
+             comm: Optional[TrainShardComm] = None) -> DsaPlan:
+    key = (m, np.asarray(q_off, dtype=np.int64).tobytes(), dtype, use_filter, engine.cap, comm is not None)
     plan = engine._plans.get(key)
     if plan is None:
         if len(engine._plans) >= 8:
             engine._plans.pop(next(iter(engine._plans)))
-        plan = DsaPlan(engine, m, q_off, dtype, use_filter)
+        plan = DsaPlan(engine, m, q_off, dtype, use_filter, comm)
         engine._plans[key] = plan
     return plan
 

@@ -357,3 +357,38 @@ def test_lsa_api_edges():
     assert sa(x[:0]).shape == (0,)
     assert sa(x[:1]).shape == (1,)
     _close(sa(x[:50].reshape(50, 3, 4)), np_oracle.lsa_oracle(x, x[:50]))
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE config 5 shape (D = 2048, many classes, ragged class sizes) at reduced N
+# ------------------------------------------------------------------------------------------
+def test_dsa_config5_shape_streaming_kernel():
+    """Exercises the streaming tcgen05 kernel (33 K-chunks), 100 classes with ragged sizes and
+    query tiles that are mostly partial; checked against the C oracle on a row subset and against
+    the exhaustive GPU scan on every row."""
+    from src.core.surprise import DSA
+
+    rng = np.random.default_rng(5)
+    classes, d = 100, 2048
+    sizes = rng.integers(40, 400, size=classes)
+    ytr = np.repeat(np.arange(classes), sizes)
+    rng.shuffle(ytr)
+    centres = rng.normal(0.0, 0.5, size=(classes, d)).astype(np.float32)
+    xtr = (centres[ytr] + rng.normal(size=(ytr.size, d)).astype(np.float32)).astype(np.float32)
+    yte = rng.integers(0, classes, size=3000)
+    xte = (centres[yte] + rng.normal(size=(3000, d)).astype(np.float32)).astype(np.float32)
+    pte = yte.copy()
+    flip = rng.random(3000) < 0.1
+    pte[flip] = rng.integers(0, classes, size=int(flip.sum()))
+    sa = DSA(xtr, ytr)
+    got = sa(xte, pte)
+    win, da, db = sa.last_winner_index.copy(), sa.last_dist_a.copy(), sa.last_dist_b.copy()
+    assert sa._engine.stats.cpu().numpy()[0] == 0
+    rows = rng.choice(3000, size=48, replace=False)
+    want = c_oracle.dsa(xtr, ytr, xte[rows], pte[rows])
+    assert np.array_equal(win[rows], want["idx_a"])
+    assert np.array_equal(da[rows], want["dist_a"]) and np.array_equal(db[rows], want["dist_b"])
+    assert np.array_equal(got[rows], want["dsa"])
+    sa.use_filter = False
+    assert np.array_equal(sa(xte, pte), got)
+    assert np.array_equal(sa.last_winner_index, win)

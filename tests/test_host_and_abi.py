@@ -92,6 +92,36 @@ def test_work_items_cover_every_pair_exactly_once():
     assert 2 <= E.span_tiles_for(10, 148) <= 32 and E.span_tiles_for(10 ** 7, 148) == 32
 
 
+def test_other_class_items_cover_every_pair_exactly_once():
+    """Stage-2 work list: tiles ignore class boundaries; single-class tiles skip their own class's
+    train rows, mixed tiles scan everything and rely on the per-query mask (flag bit 0)."""
+    for q_off, t_off in [(np.array([0, 300, 300, 1000]), np.array([0, 5000, 5600, 9000])),
+                         (np.arange(0, 1001, 10), np.arange(0, 16001, 160)),          # 100 classes of 10 queries
+                         (np.array([0, 7]), np.array([0, 50]))]:
+        m, n = int(q_off[-1]), int(t_off[-1])
+        classes = len(q_off) - 1
+        q_class = np.repeat(np.arange(classes), np.diff(q_off))
+        for row_tile, col_tile in ((128, 256), (256, 128)):
+            items = E.build_other_class_items(q_off, t_off, row_tile, col_tile, lambda pairs: 3)
+            cover = np.zeros((m, n), dtype=np.int32)
+            for q0, rows, c0, c1, slot, flag in items:
+                assert 1 <= rows <= row_tile and 0 < c1 - c0 <= 3 * col_tile
+                block = np.ones((rows, c1 - c0), dtype=np.int32)
+                if flag & 1:      # the kernel masks each query's own class
+                    for r in range(rows):
+                        c = q_class[q0 + r]
+                        lo, hi = max(t_off[c], c0), min(t_off[c + 1], c1)
+                        if hi > lo:
+                            block[r, lo - c0:hi - c0] = 0
+                else:
+                    assert len(set(q_class[q0:q0 + rows])) == 1
+                cover[q0:q0 + rows, c0:c1] += block
+            want = np.ones((m, n), dtype=np.int32)
+            for c in range(classes):
+                want[q_off[c]:q_off[c + 1], t_off[c]:t_off[c + 1]] = 0
+            assert np.array_equal(cover, want)
+
+
 def test_shard_rows_partition_preserves_class_order():
     labels = np.random.default_rng(1).integers(0, 5, size=1003)
     parts = [E.shard_rows(labels, 5, r, 4) for r in range(4)]

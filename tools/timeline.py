@@ -51,3 +51,5 @@ for mode in (_lib.RANGE_OTHER_CLASSES, _lib.RANGE_SAME_CLASS):
     print("  first 6 tiles (relative cycles):")
     for i in range(min(6, n)):
         print("   ", " ".join(f"{int(v - t0):7d}" for v in t[i, :11]))
+    rel = (t[:, 6] - t[:, 5])
+    print("  EPI ready->release per tile:", " ".join(f"{int(v)}" for v in rel[:170]))
