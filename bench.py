@@ -159,6 +159,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL would print its banner on stdout; the contract is ONE JSON line
+
         dist.init_process_group("nccl", device_id=dev)
         comm = E.TrainShardComm()
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
@@ -179,10 +182,10 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     plan = None
-    if comm is None and sa.use_graphs:
-        # steady-state path of DSA.__call__: the whole two-stage search replayed as one CUDA graph
-        # (sharded runs launch eagerly: NCCL all-reduces sit between the kernels)
-        plan = E.dsa_plan(eng, n_test, q_off, x_sorted.dtype, sa.use_filter)
+    if sa.use_graphs:
+        # steady-state path of DSA.__call__: the search replayed as CUDA graph(s); sharded runs replay
+        # one graph per stage with eager NCCL all-reduces in between
+        plan = E.dsa_plan(eng, n_test, q_off, x_sorted.dtype, sa.use_filter, comm)
         plan.x.copy_(x_sorted)
 
     def step_eager():
@@ -271,7 +274,8 @@ def run_ours(args):
                            "parallelism": f"N_train sharded over {world} GPU(s), test batch 10000 x {world}",
                            "filter": "bf16 tcgen05 candidate filter + exact fp32 re-rank (bit-identical to NumPy)",
                            "l2": "flushed between steps (256 MiB write)", "timing": "per-step CUDA events, summed",
-                           "launch": "CUDA-graph replay of the search" if plan is not None else "eager launches"},
+                           "launch": ("CUDA-graph replay of the search" if comm is None else
+                                      "per-stage CUDA graphs + eager NCCL all-reduces") if plan is not None else "eager launches"},
                 "e2e": {"value": e2e, "unit": "inputs/s", "ms_per_step": tot_e2e_ms / args.steps,
                         "h2d_bytes_per_step": int(xte.nbytes + pte.shape[0] * 4),
                         "d2h_bytes_per_step": int(3 * n_test * 4)},

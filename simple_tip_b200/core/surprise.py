@@ -370,11 +370,10 @@ class DSA(SA):
             return np.full(shape=n_total, fill_value=np.nan)
         idx = torch.from_numpy(order).to(dev, non_blocking=True)
         sharded = self._comm is not None and self._comm.world > 1
-        if self.use_graphs and not sharded:
-            # steady state: gather straight into the captured graph's input, one replay.  (Capturing
-            # the NCCL all-reduces of the sharded path works in the 2-GPU parity test but hung in a
-            # mixed eager/replay sequence, so sharded calls launch eagerly for now.)
-            plan = E.dsa_plan(eng, int(order.size), q_off, x_all.dtype, self.use_filter)
+        if self.use_graphs:
+            # steady state: gather straight into the captured graph's input and replay.  Sharded
+            # training sets replay one graph per stage with eager NCCL all-reduces in between.
+            plan = E.dsa_plan(eng, int(order.size), q_off, x_all.dtype, self.use_filter, self._comm if sharded else None)
             torch.index_select(x_all, 0, idx, out=plan.x)
             packed = plan.run()
         else:

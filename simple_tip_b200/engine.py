@@ -438,6 +438,57 @@ class DsaPlan:
         return self.out
 
 
+class StagePlan:
+    """One stage of the search (pack -> filter -> re-rank) for a fixed batch shape as a CUDA graph;
+    inputs are copied into `q`, outputs are `dist`, `gid`, `rows`."""
+
+    def __init__(self, engine: "NnEngine", m: int, q_off: np.ndarray, q_class: torch.Tensor, dtype: torch.dtype,
+                 mode: int, use_filter: bool, want_rows: bool):
+        import gc
+
+        self.q = torch.zeros((m, engine.d), dtype=dtype, device=engine.dev)
+        side = torch.cuda.Stream(device=engine.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            engine.search(self.q, q_class, q_off, mode, use_filter, want_rows)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        gc.collect()
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.dist, _, self.gid, self.rows = engine.search(self.q, q_class, q_off, mode, use_filter, want_rows)
+        finally:
+            if was_enabled:
+                gc.enable()
+
+
+class ShardedDsaPlan:
+    """N_train-sharded search: the two local stages are CUDA graphs, the all-reduces between them
+    are ordinary (eager) NCCL calls — no collective is captured."""
+
+    def __init__(self, engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool,
+                 comm: TrainShardComm):
+        self.comm = comm
+        self.q_off = np.asarray(q_off, dtype=np.int64).copy()
+        q_class = np.repeat(np.arange(engine.num_classes, dtype=np.int32), np.diff(self.q_off))
+        self.q_class = torch.from_numpy(q_class).to(engine.dev)
+        self.stage1 = StagePlan(engine, m, self.q_off, self.q_class, dtype, _lib.RANGE_SAME_CLASS, use_filter, True)
+        self.stage2 = StagePlan(engine, m, self.q_off, self.q_class, dtype, _lib.RANGE_OTHER_CLASSES, use_filter, False)
+        self.x = self.stage1.q
+
+    def run(self) -> torch.Tensor:
+        self.stage1.graph.replay()
+        dist_a, gid, winners = self.comm.reduce_winners(self.stage1.dist, self.stage1.gid, self.stage1.rows)
+        self.stage2.q.copy_(winners)
+        self.stage2.graph.replay()
+        dist_b = self.comm.reduce_min_nan(self.stage2.dist)
+        self.dist_a, self.dist_b, self.gid = dist_a, dist_b, gid
+        return torch.stack([dist_a.to(torch.float64), dist_b.to(torch.float64), gid.to(torch.float64)])
+
+
 def dsa_plan(engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool,
              comm: Optional[TrainShardComm] = None) -> DsaPlan:
     key = (m, np.asarray(q_off, dtype=np.int64).tobytes(), dtype, use_filter, engine.cap, comm is not None)
@@ -445,7 +496,10 @@ def dsa_plan(engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, 
     if plan is None:
         if len(engine._plans) >= 8:
             engine._plans.pop(next(iter(engine._plans)))
-        plan = DsaPlan(engine, m, q_off, dtype, use_filter, comm)
+        if comm is not None and comm.world > 1:
+            plan = ShardedDsaPlan(engine, m, q_off, dtype, use_filter, comm)
+        else:
+            plan = DsaPlan(engine, m, q_off, dtype, use_filter)
         engine._plans[key] = plan
     return plan
 
