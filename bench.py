@@ -153,6 +153,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the contract is ONE JSON line on stdout: anything libraries print there (NCCL's version banner)
+    # goes to stderr until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     comm = None
@@ -282,7 +287,10 @@ def run_ours(args):
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(xtr, ytr, xte, pte)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if comm is not None:
         comm.dist.destroy_process_group()
 
