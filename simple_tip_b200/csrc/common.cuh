@@ -135,7 +135,7 @@ __device__ __forceinline__ T np_leaf_sumsq_g8(const T* __restrict__ x, const T* 
                                               unsigned gmask) {
   using R = Rn<T>;
   auto term = [&](int i) -> T {
-    T d = R::sub(x[i], y[i]);
+    T d = y ? R::sub(x[i], y[i]) : x[i];
     return R::mul(d, d);
   };
   if (n < 8) {
@@ -171,7 +171,7 @@ __device__ T np_sumsq_g8(const T* __restrict__ x, const T* __restrict__ y, int n
     const int top = sp - 1;
     const int o = off[top], l = len[top];
     if (l <= 128) {
-      vals[vp++] = np_leaf_sumsq_g8<T>(x + o, y + o, l, sub, gmask);
+      vals[vp++] = np_leaf_sumsq_g8<T>(x + o, y ? y + o : nullptr, l, sub, gmask);
       sp--;
     } else {
       int n2 = l / 2;

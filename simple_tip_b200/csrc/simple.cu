@@ -5,6 +5,9 @@
 #include <algorithm>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -73,54 +76,78 @@ __global__ void __launch_bounds__(kGiniRows) gini_small_kernel(const T* __restri
   }
 }
 
-// Wide rows: one warp per row.  Lanes evaluate the <=128-element leaves of NumPy's pairwise
-// tree round-robin (each leaf is contiguous, so all fetched sectors are used), lane 0 then
-// combines the leaf sums in tree order.
+// Wide rows: one warp per row.  NumPy's pairwise tree for a row of c elements is fixed, so the
+// host builds it once per width: the list of <=128-element leaves and a post-order combine
+// program.  The row is staged in shared memory with coalesced loads; the four 8-lane groups of
+// the warp evaluate leaves cooperatively (lane j owns NumPy's stride-8 accumulator j), lane 0 then
+// runs the combine program over the leaf sums.
 constexpr int kGiniMaxLeaves = 1024;
+constexpr int kGiniStageElems = 4096;   // rows up to this width are staged in shared memory
 
-template <typename T>
-__device__ int walk_leaves(int n, int lane, const T* row, T* leaf_sums, bool combine, T* result) {
-  int off[32], len[32];
-  unsigned char phase[32];
-  T vals[32];
-  int sp = 1, vp = 0, leaf = 0;
-  off[0] = 0; len[0] = n; phase[0] = 0;
-  while (sp > 0) {
-    const int top = sp - 1;
-    const int o = off[top], l = len[top];
-    if (l <= 128) {
-      if (combine) vals[vp++] = leaf_sums[leaf];
-      else if ((leaf & 31) == lane) leaf_sums[leaf] = np_leaf_sumsq<T>(row + o, nullptr, l);
-      leaf++;
-      sp--;
-    } else {
-      int n2 = l / 2;
-      n2 -= n2 % 8;
-      if (phase[top] == 0) { phase[top] = 1; off[sp] = o; len[sp] = n2; phase[sp] = 0; sp++; }
-      else if (phase[top] == 1) { phase[top] = 2; off[sp] = o + n2; len[sp] = l - n2; phase[sp] = 0; sp++; }
-      else {
-        if (combine) { const T r = vals[--vp]; const T a = vals[--vp]; vals[vp++] = Rn<T>::add(a, r); }
-        sp--;
-      }
-    }
+struct GiniTree {
+  int n_leaves = 0, n_prog = 0;
+  int* leaf_off = nullptr;   // device: [n_leaves]
+  int* leaf_len = nullptr;   // device: [n_leaves]
+  short* prog = nullptr;     // device: [n_prog], >= 0: push leaf, -1: pop two, push their sum
+};
+
+static void gini_build(int off, int n, std::vector<int>& lo, std::vector<int>& ll, std::vector<short>& prog) {
+  if (n <= 128) {
+    prog.push_back((short)lo.size());
+    lo.push_back(off);
+    ll.push_back(n);
+    return;
   }
-  if (combine) *result = vals[0];
-  return leaf;
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  gini_build(off, n2, lo, ll, prog);
+  gini_build(off + n2, n - n2, lo, ll, prog);
+  prog.push_back(-1);
+}
+
+static int gini_tree_for(int c, GiniTree* out) {
+  static std::mutex mu;
+  static std::map<int, GiniTree> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(c);
+  if (it == cache.end()) {
+    std::vector<int> lo, ll;
+    std::vector<short> prog;
+    gini_build(0, c, lo, ll, prog);
+    GiniTree t;
+    t.n_leaves = (int)lo.size();
+    t.n_prog = (int)prog.size();
+    TIP_CHECK_CUDA(cudaMalloc(&t.leaf_off, lo.size() * sizeof(int)));
+    TIP_CHECK_CUDA(cudaMalloc(&t.leaf_len, ll.size() * sizeof(int)));
+    TIP_CHECK_CUDA(cudaMalloc(&t.prog, prog.size() * sizeof(short)));
+    TIP_CHECK_CUDA(cudaMemcpy(t.leaf_off, lo.data(), lo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TIP_CHECK_CUDA(cudaMemcpy(t.leaf_len, ll.data(), ll.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TIP_CHECK_CUDA(cudaMemcpy(t.prog, prog.data(), prog.size() * sizeof(short), cudaMemcpyHostToDevice));
+    it = cache.emplace(c, t).first;
+  }
+  *out = it->second;
+  return TIP_OK;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(128) gini_wide_kernel(const T* __restrict__ p, int64_t n, int c,
-                                                        int32_t* __restrict__ pred, T* __restrict__ gini) {
+__global__ void __launch_bounds__(128) gini_wide_kernel(const T* __restrict__ p, int64_t n, int c, GiniTree tree,
+                                                        bool staged, int32_t* __restrict__ pred,
+                                                        T* __restrict__ gini) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  T* leaf_sums = reinterpret_cast<T*>(smem_raw) + warp * kGiniMaxLeaves;
+  const int sub = lane & 7, grp = lane >> 3;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  // per-warp scratch sized by the actual tree / row width (occupancy: smem is what limits it)
+  T* leaf_sums = reinterpret_cast<T*>(smem_raw) + warp * tree.n_leaves;
+  T* stage = reinterpret_cast<T*>(smem_raw) + 4 * tree.n_leaves + warp * c;
   for (int64_t row = (int64_t)blockIdx.x * 4 + warp; row < n; row += (int64_t)gridDim.x * 4) {
     const T* src = p + row * c;
-    // argmax, first occurrence
+    // coalesced pass: argmax (first occurrence) and, if the row fits, a copy into shared memory
     T bv = src[0];
     int bi = 0;
     for (int k = lane; k < c; k += 32) {
       const T v = src[k];
+      if (staged) stage[k] = v;
       if (v > bv || (v == bv && k < bi)) { bv = v; bi = k; }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -128,14 +155,26 @@ __global__ void __launch_bounds__(128) gini_wide_kernel(const T* __restrict__ p,
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
-    T dummy;
-    walk_leaves<T>(c, lane, src, leaf_sums, false, &dummy);
+    __syncwarp();
+    const T* x = staged ? stage : src;
+    for (int l0 = 0; l0 < tree.n_leaves; l0 += 4) {
+      const int l = l0 + grp;
+      if (l < tree.n_leaves) {
+        const T s = np_leaf_sumsq_g8<T>(x + tree.leaf_off[l], nullptr, tree.leaf_len[l], sub, gmask);
+        if (sub == 0) leaf_sums[l] = s;
+      }
+    }
     __syncwarp();
     if (lane == 0) {
-      T ss;
-      walk_leaves<T>(c, 0, src, leaf_sums, true, &ss);
+      T stack[32];
+      int sp = 0;
+      for (int i = 0; i < tree.n_prog; i++) {
+        const int op = tree.prog[i];
+        if (op >= 0) stack[sp++] = leaf_sums[op];
+        else { const T r = stack[--sp]; const T a = stack[--sp]; stack[sp++] = Rn<T>::add(a, r); }
+      }
       pred[row] = bi;
-      gini[row] = Rn<T>::sub((T)1, ss);
+      gini[row] = Rn<T>::sub((T)1, stack[0]);
     }
     __syncwarp();
   }
@@ -153,9 +192,16 @@ static int launch_gini(const T* p, int64_t n, int64_t c, int32_t* pred, T* gini,
     gini_small_kernel<T><<<grid, kGiniRows, small_bytes, st>>>(p, n, (int)c, pred, gini);
   } else {
     TIP_REQUIRE(c <= (int64_t)kGiniMaxLeaves * 64, "row too wide");
-    const size_t bytes = 4 * kGiniMaxLeaves * sizeof(T);
+    GiniTree tree;
+    int rc = gini_tree_for((int)c, &tree);
+    if (rc != TIP_OK) return rc;
+    TIP_REQUIRE(tree.n_leaves <= kGiniMaxLeaves, "row too wide");
+    const bool staged = c <= kGiniStageElems;
+    const size_t bytes = 4 * (size_t)tree.n_leaves * sizeof(T) + (staged ? 4 * (size_t)c * sizeof(T) : 0);
+    TIP_CHECK_CUDA(cudaFuncSetAttribute(gini_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(4 * (kGiniMaxLeaves + kGiniStageElems) * sizeof(T))));
     const int grid = (int)std::min<int64_t>((n + 3) / 4, (int64_t)sms * 16);
-    gini_wide_kernel<T><<<grid, 128, bytes, st>>>(p, n, (int)c, pred, gini);
+    gini_wide_kernel<T><<<grid, 128, bytes, st>>>(p, n, (int)c, tree, staged, pred, gini);
   }
   TIP_LAUNCH_CHECK();
   return TIP_OK;
@@ -189,6 +235,24 @@ __device__ __forceinline__ int kmnc_bucket(TA a_in, TS lo, TS jump, int k) {
   while (i < k - 1 && a >= t(i + 1)) i++;
   // i is now the only possible section; NaN / out-of-range values fail this test
   return (a >= t(i) && a < t(i + 1)) ? i : -1;
+}
+
+// float traces + float statistics: the hot configuration.  ~16 instructions on the common path
+// (estimate, clamp, the two NumPy-rounded thresholds around it, one exact check); anything unusual
+// (section edge, constant neuron, out of range, NaN) takes the generic routine.
+__device__ __noinline__ int kmnc_bucket_slow(float a, float lo, float jump, int k) {
+  return kmnc_bucket<float, float>(a, lo, jump, k);
+}
+
+__device__ __forceinline__ int kmnc_bucket_ff(float a, float lo, float jump, int k) {
+  const float est = __fdividef(__fsub_rn(a, lo), jump);
+  int i = __float2int_rd(est);
+  i = min(max(i, 0), k - 1);
+  const float fi = (float)i;
+  const float t0 = __fadd_rn(lo, __fmul_rn(jump, fi));
+  const float t1 = __fadd_rn(lo, __fmul_rn(jump, fi + 1.0f));   // (float)(i+1) == fi + 1 exactly for i < 2^24
+  if (a >= t0 && a < t1 && jump > 0.f) return i;
+  return kmnc_bucket_slow(a, lo, jump, k);
 }
 
 template <typename TA, typename TS, typename TB>
@@ -229,6 +293,7 @@ __global__ void __launch_bounds__(256) kmnc_vec4_kernel(const float* __restrict_
   const int64_t d4 = d >> 2;
   const int64_t cpr = (d4 + 31) >> 5;  // chunks per row
   const int64_t total = n * cpr;
+  const bool small = total < (1LL << 31);
   const int64_t nwarps = (int64_t)gridDim.x * 8;
   constexpr int kUnroll = 4;   // four independent 16-byte loads in flight per thread
   for (int64_t chunk0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); chunk0 < total; chunk0 += nwarps * kUnroll) {
@@ -238,7 +303,8 @@ __global__ void __launch_bounds__(256) kmnc_vec4_kernel(const float* __restrict_
 #pragma unroll
     for (int u = 0; u < kUnroll; u++) {
       const int64_t chunk = chunk0 + (int64_t)u * nwarps;
-      row[u] = chunk / cpr;
+      // 64-bit division is emulated (~70 instructions); chunk indices fit 32 bits in practice
+      row[u] = small ? (int64_t)((uint32_t)chunk / (uint32_t)cpr) : chunk / cpr;
       j[u] = (chunk - row[u] * cpr) * 32 + lane;
       ok[u] = chunk < total && j[u] < d4;
       if (ok[u]) {
@@ -253,10 +319,10 @@ __global__ void __launch_bounds__(256) kmnc_vec4_kernel(const float* __restrict_
       if (ok[u]) {
         const float4 lo = __ldg(reinterpret_cast<const float4*>(mins) + j[u]);
         const float4 jp = __ldg(reinterpret_cast<const float4*>(jumps) + j[u]);
-        const int i0 = kmnc_bucket<float, float>(v[u].x, lo.x, jp.x, k);
-        const int i1 = kmnc_bucket<float, float>(v[u].y, lo.y, jp.y, k);
-        const int i2 = kmnc_bucket<float, float>(v[u].z, lo.z, jp.z, k);
-        const int i3 = kmnc_bucket<float, float>(v[u].w, lo.w, jp.w, k);
+        const int i0 = kmnc_bucket_ff(v[u].x, lo.x, jp.x, k);
+        const int i1 = kmnc_bucket_ff(v[u].y, lo.y, jp.y, k);
+        const int i2 = kmnc_bucket_ff(v[u].z, lo.z, jp.z, k);
+        const int i3 = kmnc_bucket_ff(v[u].w, lo.w, jp.w, k);
         cnt = (i0 >= 0) + (i1 >= 0) + (i2 >= 0) + (i3 >= 0);
         if (bucket) {
           TB* bp = bucket + row[u] * d + (j[u] << 2);

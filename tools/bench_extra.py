@@ -139,3 +139,27 @@ out["c5_slice_dsa"] = {"n_train_shard": n_train, "n_test": n_test, "d": d, "clas
 print(json.dumps({"c5_slice_dsa": out["c5_slice_dsa"]}))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/bench_extra.json", "w"), indent=1)
+
+# ---- DeepGini bandwidth variants --------------------------------------------
+from simple_tip_b200.core.deepgini import DeepGini  # noqa: E402
+
+res = {}
+for n, c in ((10_000_000, 10), (1_000_000, 1000)):
+    p = torch.rand((n, c), device=dev, dtype=torch.float32)
+    p /= p.sum(dim=1, keepdim=True)
+    pred = torch.empty(n, dtype=torch.int32, device=dev)
+    gini = torch.empty(n, dtype=torch.float32, device=dev)
+    f = lambda: lib.tip_deepgini(E._p(p), 0, n, c, E._p(pred), E._p(gini), E._stream())
+    ms = timed(f, n=5, warm=2)
+    nbytes = n * c * 4 + n * 8
+    sub = p[:2000].cpu().numpy()
+    wp, wg = np_oracle.deepgini_oracle(sub)
+    f()
+    torch.cuda.synchronize()
+    ok = bool(np.array_equal(pred[:2000].cpu().numpy(), wp) and np.array_equal(gini[:2000].cpu().numpy(), wg))
+    res[f"{n}x{c}"] = {"ms": ms, "GBps": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / PEAK_GBS,
+                       "bit_exact_vs_oracle_2000_rows": ok}
+    del p, pred, gini
+out["deepgini"] = res
+print(json.dumps({"deepgini": res}))
+json.dump(out, open("gpurun_out/bench_extra.json", "w"), indent=1)
