@@ -146,7 +146,16 @@ __device__ __forceinline__ T np_leaf_sumsq_g8(const T* __restrict__ x, const T* 
   T r = term(sub);
   int i = 8;
   const int lim = n - (n % 8);
-  // loads/squares of four steps are independent of the (ordered) accumulation: batch them
+  // loads/squares are independent of the (ordered) accumulation: issue them in batches so a leaf
+  // costs one or two memory round trips instead of one per step (this code runs at the end of a
+  // chain of dependent loads, latency is all that matters)
+  for (; i + 56 < lim; i += 64) {
+    T t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) t[u] = term(i + 8 * u + sub);
+#pragma unroll
+    for (int u = 0; u < 8; u++) r = R::add(r, t[u]);
+  }
   for (; i + 24 < lim; i += 32) {
     const T t0 = term(i + sub), t1 = term(i + 8 + sub), t2 = term(i + 16 + sub), t3 = term(i + 24 + sub);
     r = R::add(R::add(R::add(R::add(r, t0), t1), t2), t3);

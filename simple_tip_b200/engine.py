@@ -324,7 +324,7 @@ class NnEngine:
             plan = self._item_cache.get(key)
             if plan is None:       # host planning + upload once per (mode, class histogram)
                 if self.row_tile == 256:    # resident-query kernel: long items amortise the query load
-                    span_of = lambda pairs: span_tiles_for(pairs, self.sms, per_sm=3, lo=24, hi=64)
+                    span_of = lambda pairs: span_tiles_for(pairs, self.sms, per_sm=3, lo=12, hi=64)
                 else:
                     span_of = lambda pairs: span_tiles_for(pairs, self.sms)
                 populated = int(np.count_nonzero(np.diff(np.asarray(q_off))))
