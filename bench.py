@@ -1,6 +1,6 @@
 """bench.py — DSA inputs prioritized / second on B200 (BASELINE.json metric), driver contract.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch of synthetic test traces:
@@ -9,7 +9,8 @@ A "step" is one pass of the hot path over one batch of synthetic test traces:
       With N GPUs the training set is sharded over the ranks (N_train axis, north_star) and the
       test batch grows to 10 000 x N so that per-GPU work is fixed ("scaling": "weak"); the
       per-shard minima are merged with NCCL all-reduces (engine.TrainShardComm).
-  c3 / c4: LSA 10k x 60k x 256 and KMNC 10k x 4096 x 1000 sections, single GPU, same JSON shape.
+  c1 / c3 / c4: DeepGini 10k x 10 (+APFD), LSA 10k x 60k x 256 and KMNC 10k x 4096 x 1000 sections,
+      single GPU, same JSON shape (each with its own cpu_baseline from the oracle port).
 
 `value` times the device-resident path (test traces already in HBM, result left in HBM);
 `e2e` times the reference-facing call `DSA.__call__(numpy, numpy) -> numpy` from pinned host
@@ -295,6 +296,170 @@ def run_ours(args):
         comm.dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------
+# secondary workloads (single GPU): same JSON shape, selected with --workload
+# ----------------------------------------------------------------------------------------------
+def run_secondary(args):
+    """c1 DeepGini 10k x 10 (+ APFD parity), c3 LSA 10k x 60k x 256 (bf16-stored traces),
+    c4 KMNC 10k x 4096 x 1000 sections — BASELINE.json configs 1, 3, 4 on one B200."""
+    import torch
+
+    from oracle import c_oracle, np_oracle   # synthetic generators + cpu_baseline only
+    from simple_tip_b200 import _lib
+    from simple_tip_b200 import engine as E
+
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    tflops_peak, hbm_peak, peak_src = _peaks()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def timed(fn, steps):
+        out = []
+        for _ in range(steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            out.append(a.elapsed_time(b))
+        return float(np.sum(out))
+
+    wl = args.workload
+    extra = {}
+    if wl == "c3":
+        from simple_tip_b200.core.surprise import LSA
+
+        xtr, _, xte, _, _ = np_oracle.synth_clusters(60000, 10000, 256, 10, seed=3, spread=1.0)
+        rb = lambda a: torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()   # bf16-stored traces
+        xtr, xte = rb(xtr), rb(xte)
+        sa = LSA(xtr)
+        kde = sa.kde
+        xd = E.to_device(xte, dev)
+        pinned = torch.from_numpy(xte).pin_memory().numpy()
+        n_units, metric, dtype = 10000, "lsa_inputs_prioritized_per_sec", "bf16x3 (split-bf16 tensor-core dot, fp32 log-sum-exp, f64 finish)"
+        workload = "C3: LSA Gaussian-KDE 10000 test x 60000 train x 256-d, traces stored in bf16 (seed 3)"
+        step_device = lambda: kde._engine.log_kernel_sum(E.whiten(xd, None, kde._mu_dev, kde._w_dev))
+        step_e2e = lambda: sa(pinned)
+        h2d, d2h = int(xte.nbytes), 2 * 10000 * 8
+        flops = 2.0 * 256 * 10000 * 60000
+
+        def roofline(ms):
+            return {"kernel": "pair_kernel<MODE_LSE> + whiten/pack/merge (whole device step)", "bound": "tensor",
+                    "achieved": flops / (ms * 1e-3) / 1e12, "peak": tflops_peak, "unit": "TFLOP/s",
+                    "frac": flops / (ms * 1e-3) / 1e12 / tflops_peak, "traffic": None, "peak_source": peak_src,
+                    "note": "algorithmic 2*D flop per pair; 3 bf16 MMAs are executed per algorithmic one"}
+
+        def cpu():
+            n_s = 600          # ~10 s of single-threaded CPU work
+            kf = np_oracle.KdeFit(xtr.T.astype(np.float64))
+            w = np.linalg.cholesky(kf.inv_cov)
+            p, q = kf.dataset.T @ w, xte[:n_s].astype(np.float64) @ w
+            t0 = time.perf_counter()
+            c_oracle.kde_eval(p, q, 1.0 / kf.n, 1.0, threads=1)
+            dt = time.perf_counter() - t0
+            return {"value": n_s / dt, "unit": "inputs/s", "cores": 1, "kind": "port",
+                    "sample": f"{n_s} test inputs vs all 60000 train rows, {dt:.1f} s; literal loop nest of scipy 1.4.1 "
+                              "gaussian_kernel_estimate (single-threaded, as in the reference)"}
+    elif wl == "c4":
+        from simple_tip_b200.core.neuron_coverage import KMNC
+
+        act, mins, maxs = np_oracle.synth_relu(10000, 4096, seed=4)
+        km = KMNC([mins], [maxs], 1000)
+        pinned = torch.from_numpy(act).pin_memory().numpy()
+        km.buckets([act[:8]])
+        a_dev = E.to_device(act, dev)
+        lo, jp = km._dev_stats
+        bucket = torch.empty((10000, 4096), dtype=torch.int16, device=dev)
+        score = torch.empty(10000, dtype=torch.int32, device=dev)
+        n_units, metric, dtype = 10000, "kmnc_inputs_profiled_per_sec", "f32 compare, i16 bucket ids"
+        workload = "C4: KMNC 10000 x 4096 ReLU traces, 1000 sections (seed 4); compact bucket ids + scores"
+        step_device = lambda: lib.tip_kmnc(E._p(a_dev), 0, 10000, 4096, E._p(lo), E._p(jp), 0, 1000, E._p(bucket), 3,
+                                           E._p(score), E._stream())
+        step_e2e = lambda: km.buckets([pinned])
+        h2d, d2h = int(act.nbytes), 10000 * 4096 * 2 + 10000 * 4
+        nbytes = act.nbytes + 10000 * 4096 * 2 + 2 * 4096 * 4 + 10000 * 4
+
+        def roofline(ms):
+            return {"kernel": "kmnc_vec4_kernel", "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src}
+
+        def cpu():
+            n_s, k_s = 2000, 50    # the dense N x D x k profile of the reference is 41 GB at k=1000
+            t0 = time.perf_counter()
+            np_oracle.kmnc_oracle([mins], [maxs], k_s, [act[:n_s]])
+            dt = time.perf_counter() - t0
+            per_section = dt / (n_s * k_s)
+            return {"value": 1.0 / (per_section * 1000), "unit": "inputs/s", "cores": 1, "kind": "port",
+                    "sample": f"{n_s} inputs at sections={k_s} ({dt:.2f} s), cost scaled linearly to 1000 sections "
+                              "(the reference loops over sections, neuron_coverage.py:90-93)"}
+    else:   # c1
+        from simple_tip_b200.core.apfd import apfd_from_order
+        from simple_tip_b200.core.deepgini import DeepGini
+
+        p, truth = np_oracle.synth_softmax(10000, 10, seed=1)
+        pinned = torch.from_numpy(p).pin_memory().numpy()
+        p_dev = E.to_device(p, dev)
+        pred_d = torch.empty(10000, dtype=torch.int32, device=dev)
+        gini_d = torch.empty(10000, dtype=torch.float32, device=dev)
+        n_units, metric, dtype = 10000, "deepgini_inputs_prioritized_per_sec", "f32"
+        workload = "C1: DeepGini on 10000 x 10 softmax outputs (seed 1) + APFD"
+        step_device = lambda: lib.tip_deepgini(E._p(p_dev), 0, 10000, 10, E._p(pred_d), E._p(gini_d), E._stream())
+        step_e2e = lambda: DeepGini.calculate(pinned)
+        h2d, d2h = int(p.nbytes), 10000 * 8
+        nbytes = p.nbytes + 10000 * 8
+        pred, gini = DeepGini.calculate(p)
+        wp, wg = np_oracle.deepgini_oracle(p)
+        fault = wp != truth
+        extra["apfd"] = {"ours": float(apfd_from_order(fault, np.argsort(-gini))),
+                         "oracle": float(np_oracle.apfd_oracle(fault, np.argsort(-wg))),
+                         "scores_bit_identical": bool(np.array_equal(gini, wg) and np.array_equal(pred, wp))}
+
+        def roofline(ms):
+            return {"kernel": "gini_small_kernel", "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "note": "480 KB problem: launch latency, not bandwidth"}
+
+        def cpu():
+            t0 = time.perf_counter()
+            for _ in range(200):
+                np_oracle.deepgini_oracle(p)
+            dt = (time.perf_counter() - t0) / 200
+            return {"value": 10000 / dt, "unit": "inputs/s", "cores": 1, "kind": "port",
+                    "sample": "whole 10000 x 10 batch, NumPy expressions of deepgini.py:33-34, mean of 200 runs"}
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+        step_e2e()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = _lib.launch_count()
+    t_dev = timed(step_device, args.steps)
+    launches = _lib.launch_count() - l0
+    t_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
+    line = {"metric": metric, "value": n_units * args.steps / (t_dev * 1e-3), "unit": "inputs/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": workload, "l2": "flushed between steps (256 MiB write)",
+                       "timing": "per-step CUDA events, summed"},
+            "e2e": {"value": n_units * args.steps / (t_e2e * 1e-3), "unit": "inputs/s", "ms_per_step": t_e2e / args.steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline(t_dev / args.steps)}
+    line.update(extra)
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -302,9 +467,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"],
+                    help="c2 (default) = the configuration the headline metric is quoted on; c1/c3/c4 = the other "
+                         "single-GPU BASELINE.json configurations, same JSON shape")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "c2":
+        assert args.gpus == 1, "secondary workloads are single-GPU"
+        run_secondary(args)
     else:
         run_ours(args)
 

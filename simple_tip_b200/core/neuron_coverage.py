@@ -83,8 +83,12 @@ class KMNC(CoverageMethod):
         from .. import _lib
         from .. import engine as E
 
-        act = flatten_layers(activations) if not isinstance(activations, np.ndarray) else \
-            activations.reshape((activations.shape[0], -1))
+        if isinstance(activations, np.ndarray):
+            act = activations.reshape((activations.shape[0], -1))
+        elif len(activations) == 1:          # one layer: no concatenation copy (keeps a pinned buffer pinned)
+            act = np.reshape(activations[0], (activations[0].shape[0], -1))
+        else:
+            act = flatten_layers(activations)
         stat_dt = self._jumps.dtype
         if stat_dt not in (np.float32, np.float64):
             raise TypeError(f"KMNC statistics must be float32/float64 after NumPy promotion, got {stat_dt}")
@@ -106,7 +110,16 @@ class KMNC(CoverageMethod):
         _lib.check(lib.tip_kmnc(E._p(a_dev), E.tip_dtype(act.dtype), n, d, E._p(lo_dev), E._p(jump_dev),
                                 E.tip_dtype(stat_dt), self.sections, E._p(bucket),
                                 _lib.TIP_I16 if small else _lib.TIP_I32, E._p(score), E._stream()), "tip_kmnc")
-        return score.cpu().numpy(), bucket.cpu().numpy()
+        # D2H into cached pinned buffers (the bucket ids are the bulk of the traffic of this call)
+        key = (n, d, bucket.dtype)
+        if getattr(self, "_host_key", None) != key:
+            self._host_bucket = torch.empty((n, d), dtype=bucket.dtype, pin_memory=True)
+            self._host_score = torch.empty(n, dtype=torch.int32, pin_memory=True)
+            self._host_key = key
+        self._host_bucket.copy_(bucket, non_blocking=True)
+        self._host_score.copy_(score, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._host_score.numpy().copy(), self._host_bucket.numpy().copy()
 
     def __call__(self, activations: List[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
         score, bucket = self.buckets(activations)
