@@ -143,28 +143,29 @@ __device__ __forceinline__ T np_leaf_sumsq_g8(const T* __restrict__ x, const T* 
     for (int i = 0; i < n; i++) res = R::add(res, term(i));
     return res;
   }
-  T r = term(sub);
-  int i = 8;
+  // A leaf has at most 128 elements = 16 steps of the stride-8 accumulator this lane owns.  All
+  // loads/squares are issued up front (one memory round trip), then added in NumPy's order: this
+  // code sits at the end of a chain of dependent loads, latency is all that matters.
   const int lim = n - (n % 8);
-  // loads/squares are independent of the (ordered) accumulation: issue them in batches so a leaf
-  // costs one or two memory round trips instead of one per step (this code runs at the end of a
-  // chain of dependent loads, latency is all that matters)
-  for (; i + 56 < lim; i += 64) {
-    T t[8];
+  T t[16];
 #pragma unroll
-    for (int u = 0; u < 8; u++) t[u] = term(i + 8 * u + sub);
+  for (int u = 0; u < 16; u++) {
+    const int idx = 8 * u + sub;
+    t[u] = idx < lim ? term(idx) : (T)0;
+  }
+  T tail[7];
 #pragma unroll
-    for (int u = 0; u < 8; u++) r = R::add(r, t[u]);
-  }
-  for (; i + 24 < lim; i += 32) {
-    const T t0 = term(i + sub), t1 = term(i + 8 + sub), t2 = term(i + 16 + sub), t3 = term(i + 24 + sub);
-    r = R::add(R::add(R::add(R::add(r, t0), t1), t2), t3);
-  }
-  for (; i < lim; i += 8) r = R::add(r, term(i + sub));
+  for (int u = 0; u < 7; u++) tail[u] = lim + u < n ? term(lim + u) : (T)0;
+  T r = t[0];
+#pragma unroll
+  for (int u = 1; u < 16; u++)
+    if (8 * u < lim) r = R::add(r, t[u]);          // uniform condition: lim is a multiple of 8
   r = R::add(r, __shfl_xor_sync(gmask, r, 1));
   r = R::add(r, __shfl_xor_sync(gmask, r, 2));
   r = R::add(r, __shfl_xor_sync(gmask, r, 4));
-  for (; i < n; i++) r = R::add(r, term(i));
+#pragma unroll
+  for (int u = 0; u < 7; u++)
+    if (lim + u < n) r = R::add(r, tail[u]);
   return r;
 }
 
