@@ -207,14 +207,15 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
 // (Keeping the rare paths out of line was tried and is far slower: taking the address of the
 // register tile demotes it to local memory.  Code size is what matters here: the four unrolled
 // chunk bodies of a tile have to stay inside the instruction cache.)
-template <int MODE, bool EXCL>
+template <int MODE, bool EXCL, int SLOTS = kCandSlots, int STRIDE = kEpiThreads>
 __device__ __forceinline__ void epi_chunk(const PairArgs& args, EpiState& st, const EpiShared& sh, uint32_t (&r)[32],
                                           int cbase, bool partial, bool dump_tile, int dump_row, int dump_col) {
   const float kInf = __int_as_float(0x7f800000);
   if (MODE == MODE_DUMP) {
     if (dump_tile) {
 #pragma unroll
-      for (int j = 0; j < 32; j++) args.dump[(int64_t)dump_row * 256 + dump_col + j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 32; j++)
+        if (dump_col + j < 256) args.dump[(int64_t)dump_row * 256 + dump_col + j] = __uint_as_float(r[j]);
     }
   } else if (MODE == MODE_NN) {
     if (partial || (EXCL && cbase < st.ex_hi && cbase + 32 > st.ex_lo)) {
@@ -247,24 +248,31 @@ __device__ __forceinline__ void epi_chunk(const PairArgs& args, EpiState& st, co
       // exact per-column mask of the chunk: the re-rank then touches only rows inside the window
       uint32_t mask = 0;
 #pragma unroll
-      for (int j = 0; j < 32; j++) mask |= (__uint_as_float(r[j]) <= st.thr) ? (1u << j) : 0u;
-      if (st.n_staged == kCandSlots) {         // compact against the (tighter) current threshold
+      for (int gi = 0; gi < 4; gi++) {
+        if (gmin[gi] <= st.thr) {        // usually one group of 8 columns holds the value(s) inside the window
+          uint32_t mg = 0;
+#pragma unroll
+          for (int j = 0; j < 8; j++) mg |= (__uint_as_float(r[8 * gi + j]) <= st.thr) ? (1u << j) : 0u;
+          mask |= mg << (8 * gi);
+        }
+      }
+      if (st.n_staged == SLOTS) {              // compact against the (tighter) current threshold
         int keep = 0;
-        for (int k = 0; k < kCandSlots; k++) {
-          const float sv = sh.cand_val[k * kEpiThreads + sh.etid];
+        for (int k = 0; k < SLOTS; k++) {
+          const float sv = sh.cand_val[k * STRIDE + sh.etid];
           if (sv <= st.thr) {
-            sh.cand_val[keep * kEpiThreads + sh.etid] = sv;
-            sh.cand_col[keep * kEpiThreads + sh.etid] = sh.cand_col[k * kEpiThreads + sh.etid];
-            sh.cand_mask[keep * kEpiThreads + sh.etid] = sh.cand_mask[k * kEpiThreads + sh.etid];
+            sh.cand_val[keep * STRIDE + sh.etid] = sv;
+            sh.cand_col[keep * STRIDE + sh.etid] = sh.cand_col[k * STRIDE + sh.etid];
+            sh.cand_mask[keep * STRIDE + sh.etid] = sh.cand_mask[k * STRIDE + sh.etid];
             keep++;
           }
         }
         st.n_staged = keep;
       }
-      if (st.n_staged < kCandSlots) {
-        sh.cand_val[st.n_staged * kEpiThreads + sh.etid] = mn;
-        sh.cand_col[st.n_staged * kEpiThreads + sh.etid] = cbase;
-        sh.cand_mask[st.n_staged * kEpiThreads + sh.etid] = mask;
+      if (st.n_staged < SLOTS) {
+        sh.cand_val[st.n_staged * STRIDE + sh.etid] = mn;
+        sh.cand_col[st.n_staged * STRIDE + sh.etid] = cbase;
+        sh.cand_mask[st.n_staged * STRIDE + sh.etid] = mask;
         st.n_staged++;
       } else {                                 // staging full of live chunks: emit directly
         const int pos = atomicAdd(args.cand_cnt + st.row, 1);
@@ -532,37 +540,49 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // =============================================================================================
 // Resident-query variant for short traces (packed width <= 9 K-steps, e.g. D = 128):
-// 256 query rows stay in shared memory for a whole work item and only 128-row train tiles are
-// streamed, so the L2 -> SM traffic per 256 x 128 output tile is the train tile alone
-// (36.9 KB at D = 128, against 147 KB per 128 x 256 tile in the streaming kernel above, which is
-// L2-bandwidth-bound at that size).  The packed row is consumed as full 64-element chunks
-// (128-byte swizzle) plus 16-element panels (32-byte swizzle) so no padding is fetched.
-// TMEM: 2 buffers x 2 query halves x 128 columns.  Epilogue as above (one query row per thread).
+// 256 query rows stay in shared memory for a whole work item and 192-row train tiles are
+// streamed (2-stage ring), so the L2 -> SM traffic per 256 x 192 output tile is the train tile
+// alone (55.3 KB at D = 128).  The packed row is consumed as full 64-element chunks (128-byte
+// swizzle) plus 16-element panels (32-byte swizzle) so no padding is fetched.
+// MMA shape M128 x N192 x K16: per instruction the tensor pipe reads 4 KB of A and 6 KB of B from
+// shared memory for 96 cycles of work (107 B/clk, under the 128 B/clk shared-memory bandwidth that
+// the earlier M128 x N128 version sat on), and the single issuing thread (~45 cycles per
+// instruction) needs a third fewer instructions per flop.
+// TMEM: query half h accumulates in columns [256 h, 256 h + 192); the halves ping-pong — while the
+// tensor pipe fills half h of tile t, the epilogue warps of half 1-h drain their accumulator.
+// Epilogue: 16 warps = 4 lane quadrants x 2 query halves x 2 column halves; one query row x 96
+// columns per thread (3 chunks of 32, TMEM loads double-buffered).  (N = 256 with 8 epilogue warps
+// was measured epilogue-bound: a lone warp per scheduler cannot hide the tcgen05.ld latency.)
 // =============================================================================================
 constexpr int RS_BM = 256;
-constexpr int RS_BN = 128;
+constexpr int RS_BN = 192;
 constexpr int kRsMaxK16 = 9;
-constexpr uint32_t kIdescN128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(RS_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr int kRsEpiThreads = 512;            // 16 epilogue warps
+constexpr int kRsThreads = 64 + kRsEpiThreads;
+constexpr int kRsStages = 2;
+constexpr uint32_t kIdescRs = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(RS_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 struct RsGeom {
-  int nfull, rem, stages;
+  int nfull, rem;
   uint32_t a_bytes, b_bytes;
 };
 
-__host__ __device__ inline RsGeom rs_geom(int k16) {
-  RsGeom g;
-  g.nfull = k16 / 4;
-  g.rem = k16 % 4;
-  g.a_bytes = (uint32_t)(g.nfull * RS_BM * 128 + g.rem * RS_BM * 32);
-  g.b_bytes = (uint32_t)(g.nfull * RS_BN * 128 + g.rem * RS_BN * 32);
-  g.stages = 3;
-  return g;
+__host__ __device__ constexpr RsGeom rs_geom(int k16) {
+  return RsGeom{k16 / 4, k16 % 4, (uint32_t)((k16 / 4) * RS_BM * 128 + (k16 % 4) * RS_BM * 32),
+                (uint32_t)((k16 / 4) * RS_BN * 128 + (k16 % 4) * RS_BN * 32)};
 }
 constexpr int kRsBarBytes = 256;
-__host__ inline int rs_smem_bytes(int k16) {
-  const RsGeom g = rs_geom(k16);
-  return (int)(g.a_bytes + g.stages * g.b_bytes) + 1024 + kRsBarBytes + kCandBytes;
+constexpr int kSmemMax = 232448;   // 227 KB per CTA on sm_100
+// candidate staging slots per query that still fit next to the operand buffers (3 at K16 = 9)
+__host__ __device__ constexpr int rs_slots(int k16) {
+  const int left = kSmemMax - 1024 - kRsBarBytes - (int)(rs_geom(k16).a_bytes + kRsStages * rs_geom(k16).b_bytes);
+  const int s = left / (kRsEpiThreads * 12);
+  return s > kCandSlots ? kCandSlots : s;
 }
+__host__ __device__ constexpr int rs_smem_bytes(int k16) {
+  return (int)(rs_geom(k16).a_bytes + kRsStages * rs_geom(k16).b_bytes) + 1024 + kRsBarBytes + rs_slots(k16) * kRsEpiThreads * 12;
+}
+static_assert(rs_slots(kRsMaxK16) >= 2 && rs_smem_bytes(kRsMaxK16) <= kSmemMax, "resident kernel does not fit");
 
 __device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t addr) {
   // K-major, 32-byte swizzle: rows of 32 B, 8-row groups 256 B apart
@@ -570,7 +590,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t addr) {
 }
 
 template <int MODE, int K16, bool EXCL>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kRsThreads, 1)
 pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAt,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBt, const PairArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -578,7 +598,8 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   constexpr int NFULL = K16 / 4, REM = K16 % 4;
-  const RsGeom geo = rs_geom(K16);
+  constexpr RsGeom geo = rs_geom(K16);
+  constexpr int SLOTS = rs_slots(K16);
   int tl_tile = 0;
 #define TL(slot)                                                                              \
   do {                                                                                        \
@@ -586,11 +607,11 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       args.timeline[(int64_t)tl_tile * 16 + (slot)] = clock64();                              \
   } while (0)
   const uint32_t a_base = base;
-  const uint32_t a_rem = a_base + (uint32_t)geo.nfull * RS_BM * 128;
+  const uint32_t a_rem = a_base + (uint32_t)NFULL * RS_BM * 128;
   const uint32_t b_base = a_base + geo.a_bytes;
-  const uint32_t tiles_bytes = geo.a_bytes + (uint32_t)geo.stages * geo.b_bytes;
+  constexpr uint32_t tiles_bytes = geo.a_bytes + (uint32_t)kRsStages * geo.b_bytes;
   const uint32_t bar0 = base + tiles_bytes;
-  // barriers: 0 a_full, 1 a_empty, 2..4 b_full, 5..7 b_empty, 8..9 tfull, 10..11 tempty
+  // barriers: 0 a_full, 1 a_empty, 2..3 b_full, 4..5 b_empty, 6..7 tfull[half], 8..9 tempty[half]
   auto bar = [&](int i) { return bar0 + 8u * i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tiles_bytes + 8 * 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -598,8 +619,8 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmAt); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBt);
     mbar_init(bar(0), 1); mbar_init(bar(1), 1);
-    for (int s = 0; s < 3; s++) { mbar_init(bar(2 + s), 1); mbar_init(bar(5 + s), 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(bar(8 + a), 1); mbar_init(bar(10 + a), kEpiThreads / 32); }
+    for (int s = 0; s < kRsStages; s++) { mbar_init(bar(2 + s), 1); mbar_init(bar(4 + s), 1); }
+    for (int h = 0; h < 2; h++) { mbar_init(bar(6 + h), 1); mbar_init(bar(8 + h), kRsEpiThreads / 64); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -621,32 +642,33 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
         const tip_work_item it = args.items[w];
         const int ntiles = (it.col1 - it.col0 + RS_BN - 1) / RS_BN;
-        // train tiles of the new item are prefetched while the previous item still owns the
-        // query buffer; the queries follow as soon as the MMA warp releases it
-        const int a_at = min(geo.stages - 1, ntiles);
+        if (ntiles <= 0) continue;   // padding entry of a balanced work list
+        // the first train tile of the new item is prefetched while the previous item still owns
+        // the query buffer; the queries follow as soon as the MMA warp releases it
+        const int a_at = min(kRsStages - 1, ntiles);
         for (int t = 0; t <= ntiles; t++) {
           if (t == a_at) {
             mbar_wait(bar(1), a_phase ^ 1u);
             mbar_expect_tx(bar(0), geo.a_bytes);
-            for (int c = 0; c < geo.nfull; c++) tma_load_2d(a_base + (uint32_t)c * RS_BM * 128, &tmA, bar(0), c * 64, it.q_row0);
-            for (int p = 0; p < geo.rem; p++)
-              tma_load_2d(a_rem + (uint32_t)p * RS_BM * 32, &tmAt, bar(0), geo.nfull * 64 + p * 16, it.q_row0);
+            for (int c = 0; c < NFULL; c++) tma_load_2d(a_base + (uint32_t)c * RS_BM * 128, &tmA, bar(0), c * 64, it.q_row0);
+            for (int p = 0; p < REM; p++)
+              tma_load_2d(a_rem + (uint32_t)p * RS_BM * 32, &tmAt, bar(0), NFULL * 64 + p * 16, it.q_row0);
             a_phase ^= 1u;
           }
           if (t == ntiles) break;
           TL(8);
-          mbar_wait(bar(5 + stage), phase ^ 1u);
+          mbar_wait(bar(4 + stage), phase ^ 1u);
           TL(9);
           mbar_expect_tx(bar(2 + stage), geo.b_bytes);
           const uint32_t b_dst = b_base + (uint32_t)stage * geo.b_bytes;
           const int row = it.col0 + t * RS_BN;
-          for (int c = 0; c < geo.nfull; c++) tma_load_2d(b_dst + (uint32_t)c * RS_BN * 128, &tmB, bar(2 + stage), c * 64, row);
-          for (int p = 0; p < geo.rem; p++)
-            tma_load_2d(b_dst + (uint32_t)(geo.nfull * RS_BN * 128 + p * RS_BN * 32), &tmBt, bar(2 + stage),
-                        geo.nfull * 64 + p * 16, row);
+          for (int c = 0; c < NFULL; c++) tma_load_2d(b_dst + (uint32_t)c * RS_BN * 128, &tmB, bar(2 + stage), c * 64, row);
+          for (int p = 0; p < REM; p++)
+            tma_load_2d(b_dst + (uint32_t)(NFULL * RS_BN * 128 + p * RS_BN * 32), &tmBt, bar(2 + stage),
+                        NFULL * 64 + p * 16, row);
           TL(10);
           tl_tile++;
-          if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
+          if (++stage == kRsStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -655,75 +677,82 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================= MMA issuer =================
     // The whole warp runs this loop (warp-uniform control flow keeps descriptors and barrier
     // addresses in uniform registers); one elected lane issues tcgen05.mma / commit.  The 2*K16
-    // MMAs of a tile are straight-line code: a single thread's dependent instruction stream is
-    // the critical path of this kernel (measured: ~45 cycles per issue at best).
+    // MMAs of a tile are straight-line code: a single thread's dependent instruction stream costs
+    // ~45 cycles per issue, against 96 cycles of tensor work per M128 x N192 x K16 instruction.
     const bool leader = elect_one();
-    int stage = 0, acc = 0;
-    uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+    int stage = 0;
+    uint32_t phase = 0, t_phase = 0, a_phase = 0;
     for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
       const tip_work_item it = args.items[w];
       const int ntiles = (it.col1 - it.col0 + RS_BN - 1) / RS_BN;
+      if (ntiles <= 0) continue;
       mbar_wait(bar(0), a_phase);
       a_phase ^= 1u;
       for (int t = 0; t < ntiles; t++) {
         if (leader) TL(0);
-        mbar_wait(bar(10 + acc), acc_phase ^ 1u);
-        if (leader) TL(1);
         mbar_wait(bar(2 + stage), phase);
-        if (leader) TL(2);
-        tc_fence_after();
+        if (leader) TL(1);
         const uint32_t b_src = b_base + (uint32_t)stage * geo.b_bytes;
-        if (leader) {
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256 + h * RS_BN);
+        for (int h = 0; h < 2; h++) {
+          mbar_wait(bar(8 + h), t_phase ^ 1u);   // epilogue has drained half h of the previous tile
+          tc_fence_after();
+          if (leader) {
+            TL(2 + 9 * h);   // slots 2 and 11
+            const uint32_t d_tmem = tmem_base + (uint32_t)(h * 256);
 #pragma unroll
             for (int c = 0; c < NFULL; c++) {
               const uint64_t adesc = smem_desc(a_base + (uint32_t)c * RS_BM * 128 + (uint32_t)h * 128 * 128);
               const uint64_t bdesc = smem_desc(b_src + (uint32_t)c * RS_BN * 128);
 #pragma unroll
               for (int k = 0; k < 4; k++) {
-                if (c == 0 && k == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdescN128);
-                else umma_bf16_acc(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdescN128);
+                if (c == 0 && k == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdescRs);
+                else umma_bf16_acc(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdescRs);
               }
             }
 #pragma unroll
             for (int p = 0; p < REM; p++) {
               const uint64_t adesc = smem_desc_sw32(a_rem + (uint32_t)p * RS_BM * 32 + (uint32_t)h * 128 * 32);
               const uint64_t bdesc = smem_desc_sw32(b_src + (uint32_t)(NFULL * RS_BN * 128 + p * RS_BN * 32));
-              if (NFULL == 0 && p == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdescN128);
-              else umma_bf16_acc(d_tmem, adesc, bdesc, kIdescN128);
+              if (NFULL == 0 && p == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdescRs);
+              else umma_bf16_acc(d_tmem, adesc, bdesc, kIdescRs);
             }
+            umma_commit(bar(6 + h));
+            if (h == 1) {
+              umma_commit(bar(4 + stage));
+              if (t == ntiles - 1) umma_commit(bar(1));   // query buffer free once this item's MMAs retire
+            }
+            TL(3 + 9 * h);   // slots 3 and 12
           }
-          umma_commit(bar(5 + stage));
-          umma_commit(bar(8 + acc));
-          TL(3);
-          if (t == ntiles - 1) umma_commit(bar(1));   // query buffer free once this item's MMAs retire
+          __syncwarp();
         }
-        __syncwarp();
         tl_tile++;
-        if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++stage == kRsStages) { stage = 0; phase ^= 1u; }
+        t_phase ^= 1u;
       }
     }
   } else {
-    // ================= epilogue: warps 2..9, query half = (warp-2)/4, lane quadrant = warp%4 ====
+    // ===== epilogue: warps 2..17; lane quadrant = warp % 4 (hardware rule), query half and column
+    // half from the warp's index among the epilogue warps =====
+    const int e = warp - 2;
     const int quad = warp & 3;
-    const int mhalf = (warp - 2) >> 2;
+    const int mhalf = (e >> 2) & 1;
+    const int chalf = e >> 3;
+    constexpr int CW = RS_BN / 2;          // columns per thread and tile
     const int row_local = mhalf * 128 + quad * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mhalf * RS_BN);
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mhalf * 256 + chalf * CW);
+    const bool tl_thread = (threadIdx.x == 64);   // first epilogue thread of (half 0, columns 0..95)
     EpiShared sh;
     sh.cand_val = reinterpret_cast<float*>(smem + tiles_bytes + kRsBarBytes);
-    sh.cand_col = reinterpret_cast<int*>(sh.cand_val + kCandSlots * kEpiThreads);
-    sh.cand_mask = reinterpret_cast<uint32_t*>(sh.cand_col + kCandSlots * kEpiThreads);
+    sh.cand_col = reinterpret_cast<int*>(sh.cand_val + SLOTS * kRsEpiThreads);
+    sh.cand_mask = reinterpret_cast<uint32_t*>(sh.cand_col + SLOTS * kRsEpiThreads);
     sh.etid = threadIdx.x - 64;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t t_phase = 0;
     const float kInf = __int_as_float(0x7f800000);
     for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
       const tip_work_item it = args.items[w];
       const int ntiles = (it.col1 - it.col0 + RS_BN - 1) / RS_BN;
+      if (ntiles <= 0) continue;
       EpiState st;
       st.valid_row = row_local < it.q_rows;
       st.row = (int64_t)it.q_row0 + row_local;
@@ -745,34 +774,31 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
       }
       for (int t = 0; t < ntiles; t++) {
-        if (threadIdx.x == 64) TL(4);
-        mbar_wait(bar(8 + acc), acc_phase);
-        if (threadIdx.x == 64) TL(5);
+        if (tl_thread) TL(4);
+        mbar_wait(bar(6 + mhalf), t_phase);
+        if (tl_thread) TL(5);
         tc_fence_after();
-        const int col_base = it.col0 + t * RS_BN;
-        const bool partial = col_base + RS_BN > it.col1;
+        const int tcol = t * RS_BN + chalf * CW;          // first column of this thread, item-relative
+        const int col_base = it.col0 + tcol;
+        const bool partial = col_base + CW > it.col1;
         const bool dump = (w == 0 && t < 2);
         uint32_t seen_bits = 0x7f800000u;
         if (MODE == MODE_NN && st.valid_row) seen_bits = ld_volatile_u32(args.row_min_bits + st.row);
-        const uint32_t taddr = lane_addr + (uint32_t)(acc * 256);
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr, ra);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {   // unrolled: measured faster than rolled for this kernel
-          tmem_wait_ld();
-          tmem_ld32(taddr + 64 * h + 32, rb);
-          epi_chunk<MODE, EXCL>(args, st, sh, ra, col_base + 64 * h, partial, dump, row_local, t * RS_BN + 64 * h);
-          tmem_wait_ld();
-          if (h == 0) {
-            tmem_ld32(taddr + 64, ra);
-          } else {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(10 + acc));
-            if (threadIdx.x == 64) TL(6);
-          }
-          epi_chunk<MODE, EXCL>(args, st, sh, rb, col_base + 64 * h + 32, partial, dump, row_local, t * RS_BN + 64 * h + 32);
-        }
+        tmem_wait_ld();
+        tmem_ld32(taddr + 32, rb);
+        epi_chunk<MODE, EXCL, SLOTS, kRsEpiThreads>(args, st, sh, ra, col_base, partial, dump, row_local, tcol);
+        tmem_wait_ld();
+        tmem_ld32(taddr + 64, ra);
+        epi_chunk<MODE, EXCL, SLOTS, kRsEpiThreads>(args, st, sh, rb, col_base + 32, partial, dump, row_local, tcol + 32);
+        tmem_wait_ld();
+        // accumulator columns of this warp are in registers: hand them back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(8 + mhalf));
+        if (tl_thread) TL(6);
+        epi_chunk<MODE, EXCL, SLOTS, kRsEpiThreads>(args, st, sh, ra, col_base + 64, partial, dump, row_local, tcol + 64);
         if (MODE == MODE_NN && st.valid_row) {
           const float mine = fmaxf(st.best + st.nx, 0.f);
           const float seen = __uint_as_float(seen_bits);
@@ -782,9 +808,8 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
           }
         }
-        if (threadIdx.x == 64) { TL(7); tl_tile++; }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (tl_thread) { TL(7); tl_tile++; }
+        t_phase ^= 1u;
       }
       if (MODE == MODE_NN && st.valid_row) {
         const float seen = __uint_as_float(ld_volatile_u32(args.row_min_bits + st.row));
@@ -793,11 +818,11 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
         }
         for (int k = 0; k < st.n_staged; k++) {
-          if (sh.cand_val[k * kEpiThreads + sh.etid] <= st.thr) {
+          if (sh.cand_val[k * kRsEpiThreads + sh.etid] <= st.thr) {
             const int pos = atomicAdd(args.cand_cnt + st.row, 1);
             if (pos < args.cap) {
-              args.cand_idx[(st.row * args.cap + pos) * 2] = sh.cand_col[k * kEpiThreads + sh.etid];
-              args.cand_idx[(st.row * args.cap + pos) * 2 + 1] = (int)sh.cand_mask[k * kEpiThreads + sh.etid];
+              args.cand_idx[(st.row * args.cap + pos) * 2] = sh.cand_col[k * kRsEpiThreads + sh.etid];
+              args.cand_idx[(st.row * args.cap + pos) * 2 + 1] = (int)sh.cand_mask[k * kRsEpiThreads + sh.etid];
             }
           }
         }
@@ -893,12 +918,12 @@ static int launch_pair_rs(const void* q_pack, int64_t m, const void* t_pack, int
   if ((rc = make_map(&mat, q_pack, m, pitch, RS_BM, 16)) != TIP_OK) return rc;
   if ((rc = make_map(&mb, t_pack, n, pitch, RS_BN, 64)) != TIP_OK) return rc;
   if ((rc = make_map(&mbt, t_pack, n, pitch, RS_BN, 16)) != TIP_OK) return rc;
-  const int smem = rs_smem_bytes(kRsMaxK16);
   static bool attr_set[kRsMaxK16 + 1] = {};   // per template instantiation
   if (!attr_set[args.k16]) {
 #define TIP_RS_ATTR(K)                                                                                   \
   case K:                                                                                                \
-    TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_rs_kernel<MODE, K, EXCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_rs_kernel<MODE, K, EXCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        rs_smem_bytes(K)));                                              \
     break;
     switch (args.k16) {
       TIP_RS_ATTR(1) TIP_RS_ATTR(2) TIP_RS_ATTR(3) TIP_RS_ATTR(4) TIP_RS_ATTR(5)
@@ -912,7 +937,7 @@ static int launch_pair_rs(const void* q_pack, int64_t m, const void* t_pack, int
   const int smem_k = rs_smem_bytes(args.k16);
 #define TIP_RS_CASE(K)                                                                                   \
   case K:                                                                                                \
-    pair_rs_kernel<MODE, K, EXCL><<<grid, kThreads, smem_k, st>>>(ma, mat, mb, mbt, args);               \
+    pair_rs_kernel<MODE, K, EXCL><<<grid, kRsThreads, smem_k, st>>>(ma, mat, mb, mbt, args);               \
     break;
   switch (args.k16) {
     TIP_RS_CASE(1) TIP_RS_CASE(2) TIP_RS_CASE(3) TIP_RS_CASE(4) TIP_RS_CASE(5)

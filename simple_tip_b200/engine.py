@@ -175,6 +175,84 @@ def build_other_class_items(q_off: np.ndarray, t_off: np.ndarray, row_tile: int,
     return np.concatenate(out) if out else np.zeros((0, 6), dtype=np.int32)
 
 
+def query_tiles(q_off: np.ndarray, ranges_per_class, t_off: Optional[np.ndarray], row_tile: int, mixed: bool):
+    """Query tiles of one search stage as (first row, rows, train ranges, flag) tuples.
+    mixed=False: class-aligned tiles (a tile never crosses a class boundary) scanning the ranges of
+    their class.  mixed=True (DSA's other-class stage with few queries per class): tiles cut
+    regardless of class boundaries; a tile that mixes classes scans every train row and each query
+    masks its own class in the epilogue (flag bit 0)."""
+    q_off = np.asarray(q_off, dtype=np.int64)
+    tiles = []
+    if not mixed:
+        for c, ranges in enumerate(ranges_per_class):
+            rs = [(int(lo), int(hi)) for lo, hi in ranges if int(hi) > int(lo)]
+            if not rs:
+                continue
+            for r0 in range(int(q_off[c]), int(q_off[c + 1]), row_tile):
+                tiles.append((r0, min(row_tile, int(q_off[c + 1]) - r0), rs, 0))
+        return tiles
+    t_off = np.asarray(t_off, dtype=np.int64)
+    m, n = int(q_off[-1]), int(t_off[-1])
+    for r0 in range(0, m, row_tile):
+        nr = min(row_tile, m - r0)
+        c0 = int(np.searchsorted(q_off, r0, side="right") - 1)
+        c1 = int(np.searchsorted(q_off, r0 + nr - 1, side="right") - 1)
+        if c0 == c1:
+            rs = [(lo, hi) for lo, hi in ((0, int(t_off[c0])), (int(t_off[c0 + 1]), n)) if hi > lo]
+            flag = 0
+        else:
+            rs, flag = ([(0, n)] if n > 0 else []), 1
+        if rs:
+            tiles.append((r0, nr, rs, flag))
+    return tiles
+
+
+def build_balanced_items(tiles, col_tile: int, n_cta: int, item_cost: float = 0.75) -> np.ndarray:
+    """Work list for the persistent resident-query kernel, balanced for its static schedule
+    (CTA b runs items b, b + G, b + 2G, ...; G = min(n_cta, #items)).  The (query tile x train tile)
+    pairs are linearised query-tile-major and cut into G contiguous chunks of equal cost, so every
+    CTA streams the same number of train tiles (+-1) and loads as few query tiles as possible;
+    a chunk becomes one item per (query tile, train range) it touches.  `item_cost` is the price
+    of starting an item (query-tile load + pipeline refill) in train-tile units."""
+    segs = []          # (q_row0, q_rows, lo, hi, flag, ntiles)
+    for r0, nr, ranges, flag in tiles:
+        for lo, hi in ranges:
+            nt = -(-(int(hi) - int(lo)) // col_tile)
+            if nt > 0:
+                segs.append((int(r0), int(nr), int(lo), int(hi), int(flag), nt))
+    if not segs:
+        return np.zeros((0, 6), dtype=np.int32)
+    total = sum(sg[5] for sg in segs)
+    g = int(min(n_cta, total))
+    # Cost axis: every segment costs item_cost up front, then 1 per train tile.  A tile belongs to
+    # the CTA whose equal share of the axis holds the tile's centre; consecutive tiles of a
+    # segment with the same owner form one item.
+    cost_total = total + item_cost * len(segs)
+    per_cta = [[] for _ in range(g)]
+    pos = 0.0
+    for r0, nr, lo, hi, flag, nt in segs:
+        pos += item_cost
+        owner = np.minimum(((pos + np.arange(nt) + 0.5) * (g / cost_total)).astype(np.int64), g - 1)
+        cuts = np.flatnonzero(np.diff(owner)) + 1
+        starts = np.concatenate(([0], cuts))
+        ends = np.concatenate((cuts, [nt]))
+        for t0, t1 in zip(starts, ends):
+            per_cta[int(owner[t0])].append((r0, nr, lo + int(t0) * col_tile, min(hi, lo + int(t1) * col_tile), 0, flag))
+        pos += nt
+    per_cta = [lst for lst in per_cta if lst]
+    per_cta.sort(key=len, reverse=True)       # CTAs with more items first: rounds stay dense prefixes
+    g = len(per_cta)
+    rounds = len(per_cta[0])
+    out = []
+    empty = (0, 0, 0, 0, 0, 0)                # col0 == col1: the kernel skips it
+    for r in range(rounds):
+        row = [lst[r] for lst in per_cta if len(lst) > r]
+        if r + 1 < rounds:
+            row += [empty] * (g - len(row))   # keep item index = round * G + CTA
+        out.extend(row)
+    return np.asarray(out, dtype=np.int32).reshape(-1, 6)
+
+
 def count_tile_pairs(q_off: np.ndarray, ranges_per_class, row_tile: int = _lib.ROW_TILE,
                      col_tile: int = _lib.COL_TILE) -> int:
     total = 0
@@ -323,18 +401,21 @@ class NnEngine:
             key = (mode, np.asarray(q_off, dtype=np.int64).tobytes())
             plan = self._item_cache.get(key)
             if plan is None:       # host planning + upload once per (mode, class histogram)
-                if self.row_tile == 256:    # resident-query kernel: long items amortise the query load
-                    span_of = lambda pairs: span_tiles_for(pairs, self.sms, per_sm=3, lo=12, hi=64)
+                populated = int(np.count_nonzero(np.diff(np.asarray(q_off))))
+                # few queries per class: tile across class boundaries (full tiles), per-query masking;
+                # many: class-aligned tiles never touch their own class's rows
+                mixed = mode == _lib.RANGE_OTHER_CLASSES and m < 2 * self.row_tile * max(1, populated)
+                if self.row_tile == 256:
+                    # resident-query kernel: one or two long items per CTA, equal tile counts
+                    tiles = query_tiles(q_off, ranges, self.class_off, self.row_tile, mixed)
+                    items = build_balanced_items(tiles, self.col_tile, self.sms)
                 else:
                     span_of = lambda pairs: span_tiles_for(pairs, self.sms)
-                populated = int(np.count_nonzero(np.diff(np.asarray(q_off))))
-                if mode == _lib.RANGE_OTHER_CLASSES and m < 2 * self.row_tile * max(1, populated):
-                    # few queries per class: tile across class boundaries (full tiles), per-query masking
-                    items = build_other_class_items(q_off, self.class_off, self.row_tile, self.col_tile, span_of)
-                else:
-                    # many queries per class: class-aligned tiles never touch their own class's rows
-                    pairs = count_tile_pairs(q_off, ranges, self.row_tile, self.col_tile)
-                    items, _ = build_items(q_off, ranges, span_of(pairs), self.row_tile, self.col_tile)
+                    if mixed:
+                        items = build_other_class_items(q_off, self.class_off, self.row_tile, self.col_tile, span_of)
+                    else:
+                        pairs = count_tile_pairs(q_off, ranges, self.row_tile, self.col_tile)
+                        items, _ = build_items(q_off, ranges, span_of(pairs), self.row_tile, self.col_tile)
                 flops = 2.0 * self.d * sum(int(q_off[c + 1] - q_off[c]) * sum(int(hi) - int(lo) for lo, hi in ranges[c])
                                            for c in range(self.num_classes))
                 flagged = bool(items.shape[0] and (items[:, 5] & 1).any())

@@ -33,7 +33,7 @@ def _torch():
                                                 (64, 1, 2), (120, 1, 2), (5, 1, 2), (300, 1, 0), (2048, 1, 0),
                                                 (10, 3, 0), (256, 3, 0), (40, 3, 1), (40, 3, 2)])
 def test_pair_probe_matches_packed_matmul(d, segments, variant):
-    """variant 1 = streaming kernel (128 x 256 tiles), 2 = resident-query kernel (256 x 128 tiles,
+    """variant 1 = streaming kernel (128 x 256 tiles), 2 = resident-query kernel (256 x 192 tiles,
     128-byte-swizzled chunks + 32-byte-swizzled tail panels), 0 = whatever tip_nn_filter picks."""
     torch = _torch()
     from simple_tip_b200 import _lib

@@ -122,6 +122,56 @@ def test_other_class_items_cover_every_pair_exactly_once():
             assert np.array_equal(cover, want)
 
 
+def test_balanced_items_cover_every_pair_once_and_balance_the_static_schedule():
+    """Work list of the resident-query kernel: equal train-tile counts per CTA under the kernel's
+    `item = CTA + round * G` schedule, padding entries (col0 == col1) only to keep that indexing."""
+    cases = [(np.array([0, 300, 300, 1000]), np.array([0, 5000, 5600, 9000]), 148),
+             (np.arange(0, 1001, 10), np.arange(0, 16001, 160), 148),           # 100 classes of 10 queries
+             (np.array([0, 7]), np.array([0, 50]), 148),
+             (np.arange(0, 10001, 1000), np.arange(0, 60001, 6000), 148),       # C2 histogram
+             (np.array([0, 5000, 5000, 5001]), np.array([0, 10, 4000, 4100]), 7)]
+    for q_off, t_off, n_cta in cases:
+        m, n = int(q_off[-1]), int(t_off[-1])
+        classes = len(q_off) - 1
+        q_class = np.repeat(np.arange(classes), np.diff(q_off))
+        for mode, mixed in (("same", False), ("other", False), ("other", True)):
+            ranges = [[(t_off[c], t_off[c + 1])] if mode == "same" else [(0, t_off[c]), (t_off[c + 1], t_off[-1])]
+                      for c in range(classes)]
+            tiles = E.query_tiles(q_off, ranges, t_off, 256, mixed)
+            items = E.build_balanced_items(tiles, 256, n_cta)
+            live = items[items[:, 3] > items[:, 2]]
+            total_tiles = int(np.sum(-(-(live[:, 3] - live[:, 2]) // 256)))
+            cover = np.zeros((m, n), dtype=np.int32)
+            for q0, rows, c0, c1, _, flag in live:
+                assert 1 <= rows <= 256
+                block = np.ones((rows, c1 - c0), dtype=np.int32)
+                if flag & 1:
+                    for r in range(rows):
+                        c = q_class[q0 + r]
+                        lo, hi = max(t_off[c], c0), min(t_off[c + 1], c1)
+                        if hi > lo:
+                            block[r, lo - c0:hi - c0] = 0
+                else:
+                    assert len(set(q_class[q0:q0 + rows])) == 1
+                cover[q0:q0 + rows, c0:c1] += block
+            want = np.zeros((m, n), dtype=np.int32)
+            for c in range(classes):
+                for lo, hi in ranges[c]:
+                    want[q_off[c]:q_off[c + 1], lo:hi] = 1
+            assert np.array_equal(cover, want), (mode, mixed)
+            if items.shape[0] == 0:
+                continue
+            # the kernel's schedule: grid = min(#items, #SMs), CTA b takes items b, b + grid, ...
+            grid = min(items.shape[0], n_cta)
+            load = np.zeros(grid, dtype=np.int64)
+            for i, it in enumerate(items):
+                load[i % grid] += -(-(it[3] - it[2]) // 256)
+            if total_tiles >= 4 * n_cta:
+                assert load.max() <= np.ceil(total_tiles / grid) + 3, (load.max(), total_tiles / grid)
+                assert load.min() >= np.floor(total_tiles / grid) - 3
+    assert E.build_balanced_items([], 256, 148).shape == (0, 6)
+
+
 def test_shard_rows_partition_preserves_class_order():
     labels = np.random.default_rng(1).integers(0, 5, size=1003)
     parts = [E.shard_rows(labels, 5, r, 4) for r in range(4)]

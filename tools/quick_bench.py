@@ -59,6 +59,8 @@ def main():
     mn, med = timed(lambda: sa(xte, pte), n=5)
     print(f"DSA C2 end-to-end (host numpy in/out): min {mn:.3f} ms median {med:.3f} ms")
     t0 = time.time(); sa(xte, pte); print(f"  wall {1e3 * (time.time() - t0):.3f} ms")
+    if os.environ.get("QUICK_DSA_ONLY"):
+        return
 
     xtr, _, xte, _, _ = np_oracle.synth_clusters(60000, 10000, 256, 10, seed=3, spread=1.0)
     t0 = time.time()

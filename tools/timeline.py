@@ -36,20 +36,22 @@ for mode in (_lib.RANGE_OTHER_CLASSES, _lib.RANGE_SAME_CLASS):
     d = lambda a, b: t[:, a] - t[:, b]
     def st(name, v):
         print(f"  {name:42s} mean {v.mean():8.0f}  p50 {np.median(v):8.0f}  p90 {np.percentile(v, 90):8.0f}  max {v.max():8.0f}")
-    st("MMA: wait TMEM empty (1-0)", d(1, 0))
-    st("MMA: wait operands (2-1)", d(2, 1))
-    st("MMA: issue + commits (3-2)", d(3, 2))
+    st("MMA: wait train tile (1-0)", d(1, 0))
+    st("MMA: wait TMEM half 0 empty (2-1)", d(2, 1))
+    st("MMA: issue half 0 + commit (3-2)", d(3, 2))
+    st("MMA: wait TMEM half 1 empty (11-3)", d(11, 3))
+    st("MMA: issue half 1 + commits (12-11)", d(12, 11))
     st("MMA: tile period (0[t+1]-0[t])", t[1:, 0] - t[:-1, 0])
-    st("EPI: wait accumulator (5-4)", d(5, 4))
-    st("EPI: accumulator ready -> TMEM release (6-5)", d(6, 5))
-    st("EPI: release -> tile end (7-6)", d(7, 6))
-    st("EPI: tile period", t[1:, 4] - t[:-1, 4])
-    st("commit(tfull) -> EPI sees it (5-3)", d(5, 3))
-    st("EPI release -> MMA wakes ((1)[t+2]-(6)[t])", t[2:, 1] - t[:-2, 6])
+    st("EPI h0: wait accumulator (5-4)", d(5, 4))
+    st("EPI h0: accumulator ready -> TMEM release (6-5)", d(6, 5))
+    st("EPI h0: release -> tile end (7-6)", d(7, 6))
+    st("EPI h0: tile period", t[1:, 4] - t[:-1, 4])
+    st("commit(tfull0) -> EPI sees it (5-3)", d(5, 3))
+    st("EPI release -> MMA h0 of next tile starts ((2)[t+1]-(6)[t])", t[1:, 2] - t[:-1, 6])
     st("TMA: wait stage empty (9-8)", d(9, 8))
     st("TMA: issue (10-9)", d(10, 9))
     print("  first 6 tiles (relative cycles):")
     for i in range(min(6, n)):
-        print("   ", " ".join(f"{int(v - t0):7d}" for v in t[i, :11]))
+        print("   ", " ".join(f"{int(v - t0):7d}" for v in t[i, :13]))
     rel = (t[:, 6] - t[:, 5])
     print("  EPI ready->release per tile:", " ".join(f"{int(v)}" for v in rel[:170]))
