@@ -192,7 +192,7 @@ def run_ours(args):
         # steady-state path of DSA.__call__: the search replayed as CUDA graph(s); sharded runs replay
         # one graph per stage with eager NCCL all-reduces in between
         plan = E.dsa_plan(eng, n_test, q_off, x_sorted.dtype, sa.use_filter, comm)
-        plan.x.copy_(x_sorted)
+        plan.load_sorted(x_sorted)
 
     def step_eager():
         a, b, _ = E.dsa_distances(eng, x_sorted, q_class, q_off, comm)

@@ -102,17 +102,20 @@ int tip_kmnc(const void* act, int act_dtype, int64_t n, int64_t d, const void* m
  *   tail(query) = [1,1,1,0...]; tail(train) = bf16 3-way split of norm_coef*|v|^2
  * so that one K-loop accumulates  norm_coef*|y|^2 + s * <x, y>  in fp32 TMEM.
  * sqnorm[rows] receives |h(v)|^2 (segments==1) or |v|^2 (segments==3) as fp32.
+ * rounderr[rows] (may be NULL) receives the Euclidean norm of what the packed operand drops,
+ * |v - h(v)| (segments==1) or |v - h - l| (segments==3), rounded up: the per-row input-rounding
+ * term of tip_nn_filter's error window.
  * tip_pair_pitch returns the packed row pitch in elements (multiple of 64). */
 int64_t tip_pair_pitch(int64_t d, int segments);
 int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d, const float* center,
                   int role, int segments, float scale, float norm_coef, void* dst_bf16,
-                  float* sqnorm, void* stream);
+                  float* sqnorm, float* rounderr, void* stream);
 
 /* Query side of tip_nn_filter in one launch: packs the queries (segments = 1, no scaling) and
  * resets the per-query filter state (row_min_bits = +inf, cand_cnt = 0). */
 int tip_nn_query_prep(const void* q, int dtype, int64_t m, int64_t d, const float* center,
-                      void* q_pack, float* q_sqnorm, uint32_t* row_min_bits, int32_t* cand_cnt,
-                      void* stream);
+                      void* q_pack, float* q_sqnorm, float* q_rounderr, uint32_t* row_min_bits,
+                      int32_t* cand_cnt, void* stream);
 
 /* ---- nearest-neighbour candidate filter (tcgen05 + TMA) ------------------------------
  * q_pack: m x pitch, t_pack: n x pitch (tip_pair_prep, scale=-2, norm_coef=1).
@@ -124,14 +127,17 @@ int tip_nn_query_prep(const void* q, int dtype, int64_t m, int64_t d, const floa
  * counts appends (may exceed cap: overflow -> tip_nn_rerank falls back to an exact scan).
  * row_min_bits[m] (uint32 float bits, initialised to +inf = 0x7f800000 by the caller) carries
  * the running minimum across items/CTAs.  t_rmax = max_j |h(y_j)| over the train rows.
+ * q_rounderr[m] / t_errmax = max_j rounderr(y_j) (tip_pair_prep) give the window its measured
+ * input-rounding term |d_bf16 - d| <= rounderr(x) + rounderr(y); with q_rounderr == NULL the
+ * a-priori bound 2^-9 (|h(x)| + |h(y)|) is used instead (about twice as wide).
  * q_class[m] / class_off[C+1] (may be NULL if no item sets flag bit 0): for flagged items a query of
  * class c ignores train rows [class_off[c], class_off[c+1]) — DSA's other-class search over
  * query tiles that mix classes (surprise.py:622-629). */
 int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const void* t_pack,
                   int64_t n, int64_t d, int64_t pitch, const tip_work_item* items,
                   int32_t n_items, const int32_t* q_class, const int32_t* class_off, float t_rmax,
-                  uint32_t* row_min_bits, int32_t* cand_idx, int32_t* cand_cnt, int32_t cap,
-                  void* stream);
+                  const float* q_rounderr, float t_errmax, uint32_t* row_min_bits, int32_t* cand_idx,
+                  int32_t* cand_cnt, int32_t cap, void* stream);
 
 /* Tile geometry tip_nn_filter uses for traces of width d: work items must start on query rows
  * that are multiples of nothing in particular but cover at most *q_rows rows (128, or 256 for
@@ -149,7 +155,9 @@ int tip_nn_filter_tile(int64_t d, int32_t* q_rows, int32_t* t_rows);
  * (ties: lowest t_gid); optional out_gid[m] = t_gid of the winner (-1 if none) and
  * out_rows[m x d] = a copy of the winning train rows (DSA's stage-2 queries, surprise.py:648).
  * work: scratch of tip_nn_rerank_work_bytes(m, dtype) bytes (queue of queries that need the
- * exhaustive scan + the per-slice partial winners of that scan).
+ * exhaustive scan + the per-slice partial winners of that scan).  The caller zero-fills it once;
+ * every call leaves the two words it relies on (queue length work[0], completion counter
+ * work[1 + m]) at zero again, so the buffer can be reused by the next call on the same stream.
  * stats[0] += exhaustive rows, stats[1] += candidate entries walked. */
 int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype);
 int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n, int64_t d,
@@ -157,6 +165,13 @@ int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n,
                   const int32_t* q_class, const int32_t* class_off, int32_t n_classes, int mode,
                   const int32_t* t_gid, void* out_dist, int32_t* out_pos, int32_t* out_gid,
                   void* out_rows, int32_t* work, int64_t* stats, void* stream);
+
+/* DSA result packing (surprise.py:576-611 scatter by index): for i < m,
+ *   out[0*n_total + j] = dist_a[i], out[1*n_total + j] = dist_b[i], out[2*n_total + j] = gid[i]
+ * with j = idx[i] (idx == NULL: j = i); dist_* in `dtype` (TIP_F32/TIP_F64) are widened to double
+ * exactly, gid (int32) likewise.  Columns not named by idx are left untouched. */
+int tip_dsa_pack_out(const void* dist_a, const void* dist_b, int dtype, const int32_t* gid,
+                     const int32_t* idx, int64_t m, int64_t n_total, double* out, void* stream);
 
 /* dst[i,:] = src[pos[i],:]  (rows of `row_bytes` bytes; pos < 0 -> zero row) */
 int tip_gather_rows(const void* src, int64_t row_bytes, const int32_t* pos, int64_t m, void* dst,
@@ -188,10 +203,13 @@ int tip_pair_probe(const void* q_pack, int64_t m, const void* t_pack, int64_t n,
                    int segments, int64_t pitch, int variant, float* out, void* stream);
 
 /* bring-up: while buf != NULL, block 0 of the resident-query filter kernel records clock64()
- * stamps (16 int64 slots per train tile, up to `tiles` tiles): 0..3 MMA warp (before/after the
- * TMEM-empty wait, after the operand wait, after issue), 4..7 one epilogue thread (before/after
- * the accumulator wait, at TMEM release, at tile end), 8..10 TMA producer. */
+ * stamps (16 int64 slots per train tile, up to `tiles` tiles): MMA warp 0/1 before/after the
+ * train-tile wait, 2/3 and 11/12 start/end of the issue of query half 0 and 1; 4..7 one epilogue
+ * thread (before/after the accumulator wait, at TMEM release, at tile end), 8..10 TMA producer. */
 int tip_debug_timeline(long long* buf, int32_t tiles);
+/* bring-up: while buf != NULL, every CTA of the resident-query filter kernel writes
+ * {globaltimer ns at start, at end, train tiles, work items} to buf[4*blockIdx.x ...]. */
+int tip_debug_cta_clock(long long* buf);
 
 #ifdef __cplusplus
 }

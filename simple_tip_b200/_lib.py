@@ -35,19 +35,21 @@ _SIGNATURES = {
     "tip_deepgini": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, _vp]),
     "tip_kmnc": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, C.c_int, _i32, _vp, C.c_int, _vp, _vp]),
     "tip_pair_pitch": (_i64, [_i64, C.c_int]),
-    "tip_pair_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, C.c_int, C.c_int, _f32, _f32, _vp, _vp, _vp]),
-    "tip_nn_filter": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _i32,
-                                _vp]),
+    "tip_pair_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, C.c_int, C.c_int, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "tip_nn_filter": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _f32, _vp, _vp,
+                                _vp, _i32, _vp]),
     "tip_nn_rerank_work_bytes": (_i64, [_i64, C.c_int]),
-    "tip_nn_query_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tip_nn_query_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tip_nn_rerank": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, C.c_int,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tip_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "tip_dsa_pack_out": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _i64, _i64, _vp, _vp]),
     "tip_whiten": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "tip_kde_lse": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),
     "tip_kde_combine": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "tip_nn_filter_tile": (C.c_int, [_i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "tip_debug_timeline": (C.c_int, [_vp, _i32]),
+    "tip_debug_cta_clock": (C.c_int, [_vp]),
     "tip_pair_probe": (C.c_int, [_vp, _i64, _vp, _i64, _i64, C.c_int, _i64, C.c_int, _vp, _vp]),
 }
 

@@ -49,6 +49,8 @@ struct PairArgs {
   const int32_t* class_off;
   const float* q_sqnorm;
   float rmax, eps2, gamma;  // error-window constants
+  const float* q_err;       // measured input-rounding norms |x~ - bf16(x~)| per query (or nullptr: a-priori bound)
+  float t_err;              // max over the train rows of the same
   uint32_t* row_min_bits;
   int32_t* cand_idx;
   int32_t* cand_cnt;
@@ -61,6 +63,8 @@ struct PairArgs {
   // bring-up: per-tile clock64 stamps of block 0 (16 slots per tile), or nullptr
   long long* timeline;
   int timeline_tiles;
+  // bring-up: per-CTA {globaltimer at start, at end, tiles, items} of the resident kernel, or nullptr
+  long long* cta_clock;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------
@@ -451,7 +455,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         st.nx = args.q_sqnorm[st.row];
         const float r = sqrtf(st.nx) + args.rmax;
-        st.e2 = args.eps2 * r;
+        st.e2 = args.q_err ? 2.f * (args.q_err[st.row] + args.t_err + 1.2e-7f * r) * 1.00001f : args.eps2 * r;
         st.g = args.gamma * r * r;
         st.s_ref = __uint_as_float(ld_volatile_u32(args.row_min_bits + st.row));
         st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
@@ -633,6 +637,8 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  auto global_ns = [] { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
+  if (args.cta_clock && threadIdx.x == 0) args.cta_clock[blockIdx.x * 4] = global_ns();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -768,7 +774,7 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         st.nx = args.q_sqnorm[st.row];
         const float r = sqrtf(st.nx) + args.rmax;
-        st.e2 = args.eps2 * r;
+        st.e2 = args.q_err ? 2.f * (args.q_err[st.row] + args.t_err + 1.2e-7f * r) * 1.00001f : args.eps2 * r;
         st.g = args.gamma * r * r;
         st.s_ref = __uint_as_float(ld_volatile_u32(args.row_min_bits + st.row));
         st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
@@ -832,6 +838,17 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (args.cta_clock && threadIdx.x == 0) {
+    long long tiles = 0, items = 0;
+    for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+      const int nt = (args.items[w].col1 - args.items[w].col0 + RS_BN - 1) / RS_BN;
+      tiles += nt > 0 ? nt : 0;
+      items += nt > 0;
+    }
+    args.cta_clock[blockIdx.x * 4 + 1] = global_ns();
+    args.cta_clock[blockIdx.x * 4 + 2] = tiles;
+    args.cta_clock[blockIdx.x * 4 + 3] = items;
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -960,17 +977,22 @@ using namespace tip;
 
 static long long* g_timeline = nullptr;
 static int g_timeline_tiles = 0;
+static long long* g_cta_clock = nullptr;
 extern "C" int tip_debug_timeline(long long* buf, int32_t tiles) {
   g_timeline = buf;
   g_timeline_tiles = tiles;
+  return TIP_OK;
+}
+extern "C" int tip_debug_cta_clock(long long* buf) {
+  g_cta_clock = buf;
   return TIP_OK;
 }
 
 extern "C" int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const void* t_pack, int64_t n,
                              int64_t d, int64_t pitch, const tip_work_item* items, int32_t n_items,
                              const int32_t* q_class, const int32_t* class_off, float t_rmax,
-                             uint32_t* row_min_bits, int32_t* cand_idx, int32_t* cand_cnt, int32_t cap,
-                             void* stream) {
+                             const float* q_rounderr, float t_errmax, uint32_t* row_min_bits, int32_t* cand_idx,
+                             int32_t* cand_cnt, int32_t cap, void* stream) {
   TIP_REQUIRE(q_pack && q_sqnorm && t_pack && items && row_min_bits && cand_idx && cand_cnt, "null pointer");
   TIP_REQUIRE(cap >= 1 && n_items >= 0, "cap / n_items");
   TIP_REQUIRE(pitch == tip_pair_pitch(d, 1), "pitch does not match tip_pair_pitch(d, 1)");
@@ -978,6 +1000,8 @@ extern "C" int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t 
   PairArgs a{};
   a.items = items; a.n_items = n_items; a.k16 = k16_of(d, 1); a.m = m;
   a.q_sqnorm = q_sqnorm; a.rmax = t_rmax;
+  a.q_err = q_rounderr; a.t_err = t_errmax;
+  TIP_REQUIRE(!q_rounderr || t_errmax >= 0.f, "t_errmax");
   a.q_class = q_class; a.class_off = class_off;
   // eps' = (2^-9 + 2^-23)/(1 - that): bf16 rounding of the centred traces (triangle inequality);
   // gamma: fp32 accumulation over K products + norm rounding, assuming nothing better than
@@ -986,6 +1010,7 @@ extern "C" int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t 
   a.gamma = (float)(a.k16 * 16 + 16) * 1.1920929e-7f;
   a.row_min_bits = row_min_bits; a.cand_idx = cand_idx; a.cand_cnt = cand_cnt; a.cap = cap;
   a.timeline = g_timeline; a.timeline_tiles = g_timeline_tiles;
+  a.cta_clock = g_cta_clock;
   const bool excl = q_class != nullptr && class_off != nullptr;   // per-query own-class masking compiled in only then
   if (a.k16 <= kRsMaxK16)
     return excl ? launch_pair_rs<MODE_NN, true>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream)

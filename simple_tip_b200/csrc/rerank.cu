@@ -10,8 +10,10 @@
 // Two kernels: (1) one WARP per query walks its short candidate list (the work per query is a
 // handful of rows, so the kernel is a chain of dependent memory latencies: many queries in
 // flight matter, not threads per query); queries without a usable list (0 or > cap entries, or
-// no filter at all) are appended to a work list; (2) one BLOCK per listed query scans its class
-// range exhaustively — the reference-grade fallback, normally empty.
+// no filter at all) are appended to a work list; (2) the listed queries' class ranges are scanned
+// exhaustively — the reference-grade fallback, normally empty, in which case every block of the
+// second kernel returns at once.  The last block to finish merges the per-slice winners and
+// re-arms the queue (work[0] and the completion counter are 0 on entry and on exit).
 // Both also emit the winner's original index and (optionally) copy the winning train row, which
 // is the query of DSA's second stage (surprise.py:627-629, 648).
 #include <algorithm>
@@ -155,15 +157,40 @@ struct ScanScratch {
 
 template <typename T>
 __device__ __forceinline__ ScanScratch<T> scan_scratch(const RerankArgs<T>& a) {
-  // layout after the queue (1 + m ints): [cap] T dist (8-byte aligned), [cap] gid, [cap] pos
+  // layout after the queue (1 + m ints) and the completion counter (1 int):
+  // [cap] T dist (8-byte aligned), [cap] gid, [cap] pos
   const int64_t cap = a.m + kScanUnitTarget;
-  uintptr_t base = reinterpret_cast<uintptr_t>(a.work + 1 + a.m);
+  uintptr_t base = reinterpret_cast<uintptr_t>(a.work + 2 + a.m);
   base = (base + 7) & ~(uintptr_t)7;
   ScanScratch<T> sc;
   sc.dist = reinterpret_cast<T*>(base);
   sc.gid = reinterpret_cast<int32_t*>(sc.dist + cap);
   sc.pos = sc.gid + cap;
   return sc;
+}
+
+template <typename T>
+__device__ __forceinline__ void rerank_merge(const RerankArgs<T>& a, int queued) {
+  // executed by the last block of rerank_scan_kernel (kScanThreads threads)
+  const int S = scan_slices(queued);
+  const ScanScratch<T> sc = scan_scratch(a);
+  const int lane = threadIdx.x & 31;
+  constexpr int kWarps = kScanThreads / 32;
+  for (int w = threadIdx.x >> 5; w < queued; w += kWarps) {
+    Best<T> best{Rn<T>::inf(), 0x7fffffff, -1};
+    for (int sl = lane; sl < S; sl += 32) {
+      const int64_t u = (int64_t)w * S + sl;
+      best = merge(best, sc.dist[u], sc.gid[u], sc.pos[u]);
+    }
+    for (int o = 1; o < 32; o <<= 1) {
+      const T od = __shfl_xor_sync(0xffffffffu, best.dist, o);
+      const int og = __shfl_xor_sync(0xffffffffu, best.gid, o);
+      const int op = __shfl_xor_sync(0xffffffffu, best.pos, o);
+      best = merge(best, od, og, op);
+    }
+    if (lane == 0 && a.stats) atomicAdd(a.stats + 0, 1ULL);
+    write_result(a, a.work[1 + w], best, lane, 32);
+  }
 }
 
 template <typename T>
@@ -206,40 +233,29 @@ __global__ void __launch_bounds__(kScanThreads) rerank_scan_kernel(const RerankA
     }
     __syncthreads();
   }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) rerank_merge_kernel(const RerankArgs<T> a) {
-  const int queued = a.work[0];
-  const int S = scan_slices(queued);
-  const ScanScratch<T> sc = scan_scratch(a);
-  const int lane = threadIdx.x & 31;
-  for (int w = blockIdx.x * 8 + (threadIdx.x >> 5); w < queued; w += gridDim.x * 8) {
-    Best<T> best{Rn<T>::inf(), 0x7fffffff, -1};
-    for (int sl = lane; sl < S; sl += 32) {
-      const int64_t u = (int64_t)w * S + sl;
-      best = merge(best, sc.dist[u], sc.gid[u], sc.pos[u]);
-    }
-    for (int o = 1; o < 32; o <<= 1) {
-      const T od = __shfl_xor_sync(0xffffffffu, best.dist, o);
-      const int og = __shfl_xor_sync(0xffffffffu, best.gid, o);
-      const int op = __shfl_xor_sync(0xffffffffu, best.pos, o);
-      best = merge(best, od, og, op);
-    }
-    if (lane == 0 && a.stats) atomicAdd(a.stats + 0, 1ULL);
-    write_result(a, a.work[1 + w], best, lane, 32);
+  // completion: the last block merges the slices of every queued query and re-arms the queue
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.work + 1 + a.m, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  rerank_merge(a, queued);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.work[0] = 0;
+    a.work[1 + a.m] = 0;
   }
 }
 
 template <typename T>
 static int launch_rerank(const RerankArgs<T>& a, cudaStream_t st) {
-  TIP_CHECK_CUDA(cudaMemsetAsync(a.work, 0, sizeof(int32_t), st));
+  // precondition (and postcondition): work[0] == 0 and work[1 + m] == 0
   const int64_t blocks = (a.m + 7) / 8;
   rerank_list_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a);
   TIP_LAUNCH_CHECK();
   rerank_scan_kernel<T><<<sm_count() * 8, kScanThreads, 0, st>>>(a);
-  TIP_LAUNCH_CHECK();
-  rerank_merge_kernel<T><<<std::max(1, std::min(sm_count(), (int)((a.m + 7) / 8))), 256, 0, st>>>(a);
   TIP_LAUNCH_CHECK();
   return TIP_OK;
 }
@@ -251,7 +267,7 @@ using namespace tip;
 extern "C" int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype) {
   if (m < 0) return -1;
   const int64_t cap = m + kScanUnitTarget;
-  return (1 + m) * 4 + 8 + cap * ((dtype == TIP_F64 ? 8 : 4) + 8);
+  return (2 + m) * 4 + 8 + cap * ((dtype == TIP_F64 ? 8 : 4) + 8);
 }
 
 extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n, int64_t d,

@@ -364,15 +364,15 @@ __global__ void __launch_bounds__(256) pair_prep_kernel(const T* __restrict__ sr
                                                         const float* __restrict__ center, int role,
                                                         int segments, float scale, float norm_coef,
                                                         __nv_bfloat16* __restrict__ dst, int64_t pitch,
-                                                        float* __restrict__ sqnorm, uint32_t* __restrict__ row_min,
-                                                        int32_t* __restrict__ cand_cnt) {
+                                                        float* __restrict__ sqnorm, float* __restrict__ rounderr,
+                                                        uint32_t* __restrict__ row_min, int32_t* __restrict__ cand_cnt) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int d16 = (d + 15) & ~15;
   const T* x = src + row * (int64_t)d;
   __nv_bfloat16* out = dst + row * pitch;
-  double acc = 0.0;
+  double acc = 0.0, err = 0.0;   // err: squared norm of what the bf16 operand drops (v - h, exact in fp32)
   for (int c = lane; c < d16; c += 32) {
     float v = 0.f;
     if (c < d) {
@@ -383,9 +383,13 @@ __global__ void __launch_bounds__(256) pair_prep_kernel(const T* __restrict__ sr
     const float hf = __bfloat162float(h);
     if (segments == 1) {
       acc += (double)hf * (double)hf;
+      const float res = __fsub_rn(v, hf);
+      err += (double)res * (double)res;
       out[c] = role == TIP_ROLE_TRAIN ? __float2bfloat16_rn(scale * hf) : h;
     } else {
       const __nv_bfloat16 l = __float2bfloat16_rn(__fsub_rn(v, hf));
+      const float res = __fsub_rn(__fsub_rn(v, hf), __bfloat162float(l));
+      err += (double)res * (double)res;
       acc += (double)v * (double)v;
       if (role == TIP_ROLE_TRAIN) {
         const __nv_bfloat16 sh = __float2bfloat16_rn(scale * hf);
@@ -400,6 +404,7 @@ __global__ void __launch_bounds__(256) pair_prep_kernel(const T* __restrict__ sr
     }
   }
   acc = warp_sum(acc);
+  if (rounderr) err = warp_sum(err);
   const float nrm = (float)acc;
   const int tail = segments * d16;
   // tail block + zero padding up to the pitch
@@ -421,6 +426,7 @@ __global__ void __launch_bounds__(256) pair_prep_kernel(const T* __restrict__ sr
   }
   if (lane == 0) {
     if (sqnorm) sqnorm[row] = nrm;
+    if (rounderr) rounderr[row] = (float)sqrt(err) * 1.000001f;   // rounded up
     if (row_min) row_min[row] = 0x7f800000u;   // +inf: no distance seen yet (tip_nn_filter)
     if (cand_cnt) cand_cnt[row] = 0;
   }
@@ -592,8 +598,8 @@ extern "C" int64_t tip_pair_pitch(int64_t d, int segments) {
 }
 
 static int pair_prep_impl(const void* src, int dtype, int64_t rows, int64_t d, const float* center, int role,
-                          int segments, float scale, float norm_coef, void* dst, float* sqnorm, uint32_t* row_min,
-                          int32_t* cand_cnt, void* stream) {
+                          int segments, float scale, float norm_coef, void* dst, float* sqnorm, float* rounderr,
+                          uint32_t* row_min, int32_t* cand_cnt, void* stream) {
   TIP_REQUIRE(src && dst, "null pointer");
   TIP_REQUIRE(segments == 1 || segments == 3, "segments must be 1 or 3");
   TIP_REQUIRE(role == TIP_ROLE_QUERY || role == TIP_ROLE_TRAIN, "role");
@@ -607,11 +613,11 @@ static int pair_prep_impl(const void* src, int dtype, int64_t rows, int64_t d, c
   if (dtype == TIP_F32)
     pair_prep_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)src, rows, (int)d, center, role, segments,
                                                              scale, norm_coef, (__nv_bfloat16*)dst, pitch, sqnorm,
-                                                             row_min, cand_cnt);
+                                                             rounderr, row_min, cand_cnt);
   else if (dtype == TIP_F64)
     pair_prep_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double*)src, rows, (int)d, center, role,
                                                               segments, scale, norm_coef, (__nv_bfloat16*)dst, pitch,
-                                                              sqnorm, row_min, cand_cnt);
+                                                              sqnorm, rounderr, row_min, cand_cnt);
   else
     TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
   TIP_LAUNCH_CHECK();
@@ -619,16 +625,49 @@ static int pair_prep_impl(const void* src, int dtype, int64_t rows, int64_t d, c
 }
 
 extern "C" int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d, const float* center, int role,
-                             int segments, float scale, float norm_coef, void* dst, float* sqnorm, void* stream) {
-  return pair_prep_impl(src, dtype, rows, d, center, role, segments, scale, norm_coef, dst, sqnorm, nullptr, nullptr,
-                        stream);
+                             int segments, float scale, float norm_coef, void* dst, float* sqnorm, float* rounderr,
+                             void* stream) {
+  return pair_prep_impl(src, dtype, rows, d, center, role, segments, scale, norm_coef, dst, sqnorm, rounderr, nullptr,
+                        nullptr, stream);
 }
 
 extern "C" int tip_nn_query_prep(const void* q, int dtype, int64_t m, int64_t d, const float* center, void* q_pack,
-                                 float* q_sqnorm, uint32_t* row_min_bits, int32_t* cand_cnt, void* stream) {
+                                 float* q_sqnorm, float* q_rounderr, uint32_t* row_min_bits, int32_t* cand_cnt,
+                                 void* stream) {
   TIP_REQUIRE(q_sqnorm && row_min_bits && cand_cnt, "null pointer");
-  return pair_prep_impl(q, dtype, m, d, center, TIP_ROLE_QUERY, 1, 1.0f, 0.0f, q_pack, q_sqnorm, row_min_bits,
-                        cand_cnt, stream);
+  return pair_prep_impl(q, dtype, m, d, center, TIP_ROLE_QUERY, 1, 1.0f, 0.0f, q_pack, q_sqnorm, q_rounderr,
+                        row_min_bits, cand_cnt, stream);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dsa_pack_out_kernel(const T* __restrict__ da, const T* __restrict__ db,
+                                                           const int32_t* __restrict__ gid,
+                                                           const int32_t* __restrict__ idx, int64_t m,
+                                                           int64_t n_total, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  const int64_t j = idx ? idx[i] : i;
+  if (j < 0 || j >= n_total) return;
+  out[j] = (double)da[i];
+  out[n_total + j] = (double)db[i];
+  out[2 * n_total + j] = (double)gid[i];
+}
+
+extern "C" int tip_dsa_pack_out(const void* dist_a, const void* dist_b, int dtype, const int32_t* gid,
+                                const int32_t* idx, int64_t m, int64_t n_total, double* out, void* stream) {
+  TIP_REQUIRE(dist_a && dist_b && gid && out, "null pointer");
+  TIP_REQUIRE(m >= 0 && n_total >= 0, "shape");
+  if (m == 0) return TIP_OK;
+  const unsigned blocks = (unsigned)((m + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TIP_F32)
+    dsa_pack_out_kernel<float><<<blocks, 256, 0, st>>>((const float*)dist_a, (const float*)dist_b, gid, idx, m, n_total, out);
+  else if (dtype == TIP_F64)
+    dsa_pack_out_kernel<double><<<blocks, 256, 0, st>>>((const double*)dist_a, (const double*)dist_b, gid, idx, m, n_total, out);
+  else
+    TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
 }
 
 extern "C" int tip_gather_rows(const void* src, int64_t row_bytes, const int32_t* pos, int64_t m, void* dst,

@@ -55,11 +55,12 @@ def test_pair_probe_matches_packed_matmul(d, segments, variant):
     tp = torch.empty((256, pitch), dtype=torch.bfloat16, device=dev)
     qs = torch.empty(256, dtype=torch.float32, device=dev)
     ts = torch.empty(256, dtype=torch.float32, device=dev)
+    qe = torch.empty(256, dtype=torch.float32, device=dev)
     scale, coef = (-2.0, 1.0) if segments == 1 else (1.0, -0.5)
     _lib.check(lib.tip_pair_prep(E._p(q), _lib.TIP_F32, 256, d, E._p(center), _lib.ROLE_QUERY, segments, 1.0, 0.0,
-                                 E._p(qp), E._p(qs), E._stream()), "prep q")
+                                 E._p(qp), E._p(qs), E._p(qe), E._stream()), "prep q")
     _lib.check(lib.tip_pair_prep(E._p(t), _lib.TIP_F32, 256, d, E._p(center), _lib.ROLE_TRAIN, segments, scale, coef,
-                                 E._p(tp), E._p(ts), E._stream()), "prep t")
+                                 E._p(tp), E._p(ts), None, E._stream()), "prep t")
     out_full = torch.zeros((256, 256), dtype=torch.float32, device=dev)
     _lib.check(lib.tip_pair_probe(E._p(qp), 256, E._p(tp), 256, d, segments, pitch, variant, E._p(out_full),
                                   E._stream()), "probe")
@@ -73,6 +74,13 @@ def test_pair_probe_matches_packed_matmul(d, segments, variant):
     # and the packed operands mean what tip_pair_prep documents
     vq = (q - center).to(torch.float64)
     vt = (t - center).to(torch.float64)
+    # rounderr = Euclidean norm of what the packed query drops (input to tip_nn_filter's window)
+    d16 = (d + 15) // 16 * 16
+    v32 = (q - center)
+    kept = qp[:, :d].to(torch.float32) if segments == 1 else qp[:, :d].to(torch.float32) + qp[:, d16:d16 + d].to(torch.float32)
+    want_err = (v32.to(torch.float64) - kept.to(torch.float64)).norm(dim=1)
+    got_err = qe[:rows].to(torch.float64)
+    assert bool(((got_err >= want_err * (1 - 1e-6)) & (got_err <= want_err * (1 + 1e-5) + 1e-12)).all())
     if segments == 1:
         d2 = ((vq[:, None, :] - vt[None, :, :]) ** 2).sum(-1)
         approx = out.to(torch.float64) + qs.to(torch.float64)[:, None]

@@ -50,7 +50,7 @@ eng = E.NnEngine(t_sorted, class_off, gid)
 torch.cuda.synchronize()
 dist.barrier()
 plan = E.dsa_plan(eng, args.tests, q_off, x.dtype, True, comm)
-plan.x.copy_(x)
+plan.load_sorted(x)
 for _ in range(2):
     plan.run()
 times = []

@@ -1,0 +1,44 @@
+"""Per-CTA start/end times (globaltimer) of the resident-query filter kernel at C2 (bring-up tool)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from oracle import np_oracle  # noqa: E402
+from simple_tip_b200 import _lib  # noqa: E402
+from simple_tip_b200 import engine as E  # noqa: E402
+from simple_tip_b200.core.surprise import DSA  # noqa: E402
+
+xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(60000, 10000, 128, 10, seed=2)
+sa = DSA(xtr, ytr)
+eng = sa._engine
+order, q_off = E.class_layout(pte, 10)
+x = E.to_device(xte, eng.dev).index_select(0, torch.from_numpy(order).to(eng.dev))
+qc = torch.from_numpy(pte[order].astype(np.int32)).to(eng.dev)
+lib = _lib.load()
+w = eng.gather(eng.search(x, qc, q_off, _lib.RANGE_SAME_CLASS)[1])
+for mode, q in ((_lib.RANGE_OTHER_CLASSES, w), (_lib.RANGE_SAME_CLASS, x)):
+    for _ in range(2):
+        eng.search(q, qc, q_off, mode)
+    buf = torch.zeros((256, 4), dtype=torch.int64, device=eng.dev)
+    lib.tip_debug_cta_clock(C.c_void_p(buf.data_ptr()))
+    eng.search(q, qc, q_off, mode)
+    torch.cuda.synchronize()
+    lib.tip_debug_cta_clock(None)
+    t = buf.cpu().numpy()
+    t = t[t[:, 1] > 0]
+    t0 = t[:, 0].min()
+    start, end = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3
+    dur = end - start
+    print(f"mode {mode}: {len(t)} CTAs; kernel span {end.max():.1f} us; CTA start skew max {start.max():.1f} us; "
+          f"CTA duration min {dur.min():.1f} p50 {np.median(dur):.1f} p90 {np.percentile(dur, 90):.1f} max {dur.max():.1f} us")
+    print(f"  tiles per CTA min {t[:, 2].min()} max {t[:, 2].max()}; items per CTA max {t[:, 3].max()}")
+    for k in np.unique(t[:, 3]):
+        sel = t[:, 3] == k
+        print(f"  CTAs with {k} item(s): n={sel.sum()} duration p50 {np.median(dur[sel]):.1f} max {dur[sel].max():.1f} us; "
+              f"ns/tile p50 {np.median(dur[sel] * 1e3 / t[sel, 2]):.0f}")
+    slow = np.argsort(-dur)[:5]
+    print("  slowest CTAs (idx, us, tiles, items):", [(int(i), round(float(dur[i]), 1), int(t[i, 2]), int(t[i, 3])) for i in slow])
