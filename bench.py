@@ -385,7 +385,7 @@ def run_secondary(args):
         nbytes = act.nbytes + 10000 * 4096 * 2 + 2 * 4096 * 4 + 10000 * 4
 
         def roofline(ms):
-            return {"kernel": "kmnc_vec4_kernel", "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+            return {"kernel": "kmnc_strip_kernel", "bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src}
 
         def cpu():

@@ -130,6 +130,13 @@ int tip_nn_query_prep(const void* q, int dtype, int64_t m, int64_t d, const floa
  * q_rounderr[m] / t_errmax = max_j rounderr(y_j) (tip_pair_prep) give the window its measured
  * input-rounding term |d_bf16 - d| <= rounderr(x) + rounderr(y); with q_rounderr == NULL the
  * a-priori bound 2^-9 (|h(x)| + |h(y)|) is used instead (about twice as wide).
+ * Scheduling: CTA b of the G = min(n_items, #SMs) persistent CTAs runs items b, b + G, ... below
+ * n_static; items [n_static, n_items) are a shared pool that CTAs drain through sched_counter
+ * once their static share is done — the pool evens out CTAs whose
+ * tiles turn out slower.  sched_counter points to TWO int32 that are zero on entry; the kernel
+ * leaves them zero (one call at a time per counter pair).  n_static == n_items (sched_counter may
+ * be NULL) is a purely static run;
+ * pools need the resident-query kernel (d <= 128).  Items with col0 == col1 are skipped.
  * q_class[m] / class_off[C+1] (may be NULL if no item sets flag bit 0): for flagged items a query of
  * class c ignores train rows [class_off[c], class_off[c+1]) — DSA's other-class search over
  * query tiles that mix classes (surprise.py:622-629). */
@@ -137,7 +144,8 @@ int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t m, const vo
                   int64_t n, int64_t d, int64_t pitch, const tip_work_item* items,
                   int32_t n_items, const int32_t* q_class, const int32_t* class_off, float t_rmax,
                   const float* q_rounderr, float t_errmax, uint32_t* row_min_bits, int32_t* cand_idx,
-                  int32_t* cand_cnt, int32_t cap, void* stream);
+                  int32_t* cand_cnt, int32_t cap, int32_t n_static, int32_t* sched_counter,
+                  void* stream);
 
 /* Tile geometry tip_nn_filter uses for traces of width d: work items must start on query rows
  * that are multiples of nothing in particular but cover at most *q_rows rows (128, or 256 for

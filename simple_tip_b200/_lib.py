@@ -37,7 +37,7 @@ _SIGNATURES = {
     "tip_pair_pitch": (_i64, [_i64, C.c_int]),
     "tip_pair_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, C.c_int, C.c_int, _f32, _f32, _vp, _vp, _vp, _vp]),
     "tip_nn_filter": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _f32, _vp, _vp,
-                                _vp, _i32, _vp]),
+                                _vp, _i32, _i32, _vp, _vp]),
     "tip_nn_rerank_work_bytes": (_i64, [_i64, C.c_int]),
     "tip_nn_query_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tip_nn_rerank": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, C.c_int,

@@ -42,6 +42,10 @@ enum { MODE_NN = 0, MODE_LSE = 1, MODE_DUMP = 2 };
 struct PairArgs {
   const tip_work_item* items;
   int n_items;
+  // resident kernel: items [0, n_static) are scheduled statically (CTA b runs b, b + G, ...), items
+  // [n_static, n_items) form a pool that CTAs drain through the atomic counter once they run dry
+  int n_static;
+  int* sched_counter;
   int k16;  // number of K=16 MMA steps per tile (packed width / 16)
   int64_t m;
   // MODE_NN
@@ -615,9 +619,21 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t b_base = a_base + geo.a_bytes;
   constexpr uint32_t tiles_bytes = geo.a_bytes + (uint32_t)kRsStages * geo.b_bytes;
   const uint32_t bar0 = base + tiles_bytes;
-  // barriers: 0 a_full, 1 a_empty, 2..3 b_full, 4..5 b_empty, 6..7 tfull[half], 8..9 tempty[half]
+  // barriers: 0 a_full, 1 a_empty, 2..3 b_full, 4..5 b_empty, 6..7 tfull[half], 8..9 tempty[half],
+  // 10..11 sched_full[slot], 12..13 sched_empty[slot]; then the TMEM base and the 2-slot item ring
   auto bar = [&](int i) { return bar0 + 8u * i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tiles_bytes + 8 * 12);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tiles_bytes + 8 * 16);
+  volatile int* sched_ring = reinterpret_cast<volatile int*>(smem + tiles_bytes + 8 * 17);
+  // Item hand-out: the TMA thread decides which item comes next (static stride first, then the
+  // shared pool) and publishes its index; the MMA warp and the 16 epilogue warps consume it.
+  auto next_item = [&](int k) -> int {     // consumers: k-th item of this CTA, or -1
+    const int slot = k & 1;
+    mbar_wait(bar(10 + slot), (uint32_t)(k >> 1) & 1u);
+    const int idx = sched_ring[slot];
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar(12 + slot));
+    return idx;
+  };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -625,6 +641,7 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(bar(0), 1); mbar_init(bar(1), 1);
     for (int s = 0; s < kRsStages; s++) { mbar_init(bar(2 + s), 1); mbar_init(bar(4 + s), 1); }
     for (int h = 0; h < 2; h++) { mbar_init(bar(6 + h), 1); mbar_init(bar(8 + h), kRsEpiThreads / 64); }
+    for (int s = 0; s < 2; s++) { mbar_init(bar(10 + s), 1); mbar_init(bar(12 + s), 1 + kRsEpiThreads / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -645,15 +662,32 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
-      for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+      long long n_tiles_done = 0, n_items_done = 0;
+      int w_static = blockIdx.x;
+      int prev_q0 = -1, prev_qn = -1;   // query tile currently resident (consecutive items may share it)
+      for (int k = 0;; k++) {
+        int w;
+        if (w_static < args.n_static) { w = w_static; w_static += gridDim.x; }
+        else if (args.sched_counter) {
+          w = args.n_static + atomicAdd(args.sched_counter, 1);
+          if (w >= args.n_items) w = -1;
+        } else w = -1;
+        const int slot = k & 1;
+        mbar_wait(bar(12 + slot), ((uint32_t)(k >> 1) & 1u) ^ 1u);
+        sched_ring[slot] = w;
+        mbar_arrive(bar(10 + slot));
+        if (w < 0) break;
         const tip_work_item it = args.items[w];
         const int ntiles = (it.col1 - it.col0 + RS_BN - 1) / RS_BN;
         if (ntiles <= 0) continue;   // padding entry of a balanced work list
+        n_tiles_done += ntiles; n_items_done++;
+        const bool new_a = it.q_row0 != prev_q0 || it.q_rows != prev_qn;
+        prev_q0 = it.q_row0; prev_qn = it.q_rows;
         // the first train tile of the new item is prefetched while the previous item still owns
         // the query buffer; the queries follow as soon as the MMA warp releases it
         const int a_at = min(kRsStages - 1, ntiles);
         for (int t = 0; t <= ntiles; t++) {
-          if (t == a_at) {
+          if (t == a_at && new_a) {
             mbar_wait(bar(1), a_phase ^ 1u);
             mbar_expect_tx(bar(0), geo.a_bytes);
             for (int c = 0; c < NFULL; c++) tma_load_2d(a_base + (uint32_t)c * RS_BM * 128, &tmA, bar(0), c * 64, it.q_row0);
@@ -677,6 +711,12 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == kRsStages) { stage = 0; phase ^= 1u; }
         }
       }
+      if (args.cta_clock) {
+        args.cta_clock[blockIdx.x * 4 + 2] = n_tiles_done;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        args.cta_clock[blockIdx.x * 4 + 3] = n_items_done | ((long long)smid << 32);
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -688,12 +728,22 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0, t_phase = 0, a_phase = 0;
-    for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+    int prev_q0 = -1, prev_qn = -1;
+    for (int k = 0;; k++) {
+      const int w = next_item(k);
+      if (w < 0) break;
       const tip_work_item it = args.items[w];
       const int ntiles = (it.col1 - it.col0 + RS_BN - 1) / RS_BN;
       if (ntiles <= 0) continue;
-      mbar_wait(bar(0), a_phase);
-      a_phase ^= 1u;
+      if (it.q_row0 != prev_q0 || it.q_rows != prev_qn) {
+        // a different query tile: release the resident one (free once the MMAs issued so far
+        // retire), then wait for the new one
+        if (prev_qn >= 0 && leader) umma_commit(bar(1));
+        __syncwarp();
+        prev_q0 = it.q_row0; prev_qn = it.q_rows;
+        mbar_wait(bar(0), a_phase);
+        a_phase ^= 1u;
+      }
       for (int t = 0; t < ntiles; t++) {
         if (leader) TL(0);
         mbar_wait(bar(2 + stage), phase);
@@ -724,10 +774,7 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               else umma_bf16_acc(d_tmem, adesc, bdesc, kIdescRs);
             }
             umma_commit(bar(6 + h));
-            if (h == 1) {
-              umma_commit(bar(4 + stage));
-              if (t == ntiles - 1) umma_commit(bar(1));   // query buffer free once this item's MMAs retire
-            }
+            if (h == 1) umma_commit(bar(4 + stage));
             TL(3 + 9 * h);   // slots 3 and 12
           }
           __syncwarp();
@@ -755,7 +802,10 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     sh.etid = threadIdx.x - 64;
     uint32_t t_phase = 0;
     const float kInf = __int_as_float(0x7f800000);
-    for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+    bool first_item = true;
+    for (int k = 0;; k++) {
+      const int w = next_item(k);
+      if (w < 0) break;
       const tip_work_item it = args.items[w];
       const int ntiles = (it.col1 - it.col0 + RS_BN - 1) / RS_BN;
       if (ntiles <= 0) continue;
@@ -779,6 +829,8 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         st.s_ref = __uint_as_float(ld_volatile_u32(args.row_min_bits + st.row));
         st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
       }
+      const bool dump_item = first_item;
+      first_item = false;
       for (int t = 0; t < ntiles; t++) {
         if (tl_thread) TL(4);
         mbar_wait(bar(6 + mhalf), t_phase);
@@ -787,7 +839,7 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tcol = t * RS_BN + chalf * CW;          // first column of this thread, item-relative
         const int col_base = it.col0 + tcol;
         const bool partial = col_base + CW > it.col1;
-        const bool dump = (w == 0 && t < 2);
+        const bool dump = (dump_item && blockIdx.x == 0 && t < 2);
         uint32_t seen_bits = 0x7f800000u;
         if (MODE == MODE_NN && st.valid_row) seen_bits = ld_volatile_u32(args.row_min_bits + st.row);
         uint32_t ra[32], rb[32];
@@ -838,16 +890,13 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (args.cta_clock && threadIdx.x == 0) {
-    long long tiles = 0, items = 0;
-    for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
-      const int nt = (args.items[w].col1 - args.items[w].col0 + RS_BN - 1) / RS_BN;
-      tiles += nt > 0 ? nt : 0;
-      items += nt > 0;
+  if (args.cta_clock && threadIdx.x == 0) args.cta_clock[blockIdx.x * 4 + 1] = global_ns();
+  if (args.sched_counter && threadIdx.x == 0) {
+    // every CTA has drawn its last pool index by now: the last one out re-arms the counters
+    if (atomicAdd(args.sched_counter + 1, 1) == (int)gridDim.x - 1) {
+      args.sched_counter[0] = 0;
+      args.sched_counter[1] = 0;
     }
-    args.cta_clock[blockIdx.x * 4 + 1] = global_ns();
-    args.cta_clock[blockIdx.x * 4 + 2] = tiles;
-    args.cta_clock[blockIdx.x * 4 + 3] = items;
   }
   if (warp == 1) {
     tc_fence_after();
@@ -992,13 +1041,18 @@ extern "C" int tip_nn_filter(const void* q_pack, const float* q_sqnorm, int64_t 
                              int64_t d, int64_t pitch, const tip_work_item* items, int32_t n_items,
                              const int32_t* q_class, const int32_t* class_off, float t_rmax,
                              const float* q_rounderr, float t_errmax, uint32_t* row_min_bits, int32_t* cand_idx,
-                             int32_t* cand_cnt, int32_t cap, void* stream) {
+                             int32_t* cand_cnt, int32_t cap, int32_t n_static, int32_t* sched_counter,
+                             void* stream) {
   TIP_REQUIRE(q_pack && q_sqnorm && t_pack && items && row_min_bits && cand_idx && cand_cnt, "null pointer");
   TIP_REQUIRE(cap >= 1 && n_items >= 0, "cap / n_items");
   TIP_REQUIRE(pitch == tip_pair_pitch(d, 1), "pitch does not match tip_pair_pitch(d, 1)");
   if (n_items == 0) return TIP_OK;
   PairArgs a{};
   a.items = items; a.n_items = n_items; a.k16 = k16_of(d, 1); a.m = m;
+  TIP_REQUIRE(n_static >= 0 && n_static <= n_items, "n_static");
+  TIP_REQUIRE(sched_counter != nullptr || n_static == n_items, "a pool of dynamic items needs sched_counter");
+  a.n_static = n_static; a.sched_counter = n_static < n_items ? sched_counter : nullptr;
+  TIP_REQUIRE(a.k16 <= kRsMaxK16 || n_static == n_items, "dynamic items need the resident-query kernel (d <= 128)");
   a.q_sqnorm = q_sqnorm; a.rmax = t_rmax;
   a.q_err = q_rounderr; a.t_err = t_errmax;
   TIP_REQUIRE(!q_rounderr || t_errmax >= 0.f, "t_errmax");
@@ -1034,7 +1088,7 @@ extern "C" int tip_kde_lse(const void* q_pack, int64_t m, const void* t_pack, in
   TIP_REQUIRE(pitch == tip_pair_pitch(d, 3), "pitch does not match tip_pair_pitch(d, 3)");
   if (n_items == 0) return TIP_OK;
   PairArgs a{};
-  a.items = items; a.n_items = n_items; a.k16 = k16_of(d, 3); a.m = m;
+  a.items = items; a.n_items = n_items; a.n_static = n_items; a.k16 = k16_of(d, 3); a.m = m;
   a.part_max = part_max; a.part_sum = part_sum;
   return launch_pair<MODE_LSE>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
 }
@@ -1051,7 +1105,7 @@ extern "C" int tip_pair_probe(const void* q_pack, int64_t m, const void* t_pack,
   tip_work_item h{0, (int32_t)std::min<int64_t>(m, rs ? RS_BM : BM), 0, (int32_t)std::min<int64_t>(n, 256), 0, 0};
   TIP_CHECK_CUDA(cudaMemcpyAsync(d_item, &h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   PairArgs a{};
-  a.items = d_item; a.n_items = 1; a.k16 = k16; a.m = m; a.dump = out;
+  a.items = d_item; a.n_items = 1; a.n_static = 1; a.k16 = k16; a.m = m; a.dump = out;
   if (rs) return launch_pair_rs<MODE_DUMP>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
   return launch_pair<MODE_DUMP>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
 }

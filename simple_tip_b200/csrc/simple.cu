@@ -341,6 +341,122 @@ __global__ void __launch_bounds__(256) kmnc_vec4_kernel(const float* __restrict_
   }
 }
 
+// Column-strip variant of the above for the hot configuration (many samples): a block owns a strip
+// of 1024 neurons and a group of samples; every thread keeps the statistics of its four neurons in
+// registers and walks down the samples with kStripRows independent 16-byte loads in flight, so the
+// inner loop is load -> ~18 ALU instructions per value -> 8-byte store with no index arithmetic and
+// no statistics traffic.  Per-sample counts: warp shuffle -> shared memory -> one atomic per
+// (sample, strip).
+constexpr int kStripRows = 8;
+
+// Section estimate without conversion instructions (F2I / I2F / MUFU run on the quarter-rate XU
+// pipe): e = (a - lo) / jump - 1/2 rounded to an integer by adding 1.5 * 2^23, clamped to
+// [0, k-1] while still in that biased float form, whose low mantissa bits are the integer.  The
+// estimate only has to be right most of the time: a section is accepted only after the exact test
+// against the two NumPy-rounded thresholds  min + jumps*i  (neuron_coverage.py:73-79, 87-91).
+struct KmncFast {
+  int i;
+  bool ok;
+};
+__device__ __forceinline__ KmncFast kmnc_fast(float a, float lo, float jump, float inv, float top) {
+  constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
+  float m = __fadd_rn(__fmaf_rn(__fsub_rn(a, lo), inv, -0.5f), kMagic);
+  m = fminf(fmaxf(m, kMagic), top);       // top = kMagic + (k - 1); NaN -> kMagic
+  const float fi = __fsub_rn(m, kMagic);
+  const float t0 = __fadd_rn(lo, __fmul_rn(jump, fi));
+  const float t1 = __fadd_rn(lo, __fmul_rn(jump, __fadd_rn(fi, 1.0f)));
+  KmncFast r;
+  r.i = __float_as_int(m) - 0x4B400000;
+  r.ok = a >= t0 && a < t1;               // the caller vetoes neurons whose jump is not positive
+  return r;
+}
+
+// one sample row x four neurons of this thread: sections, optional store, number of covered neurons
+// dead[c] = -1 for a neuron that can never be covered (jump <= 0 or NaN: constant / inverted range),
+// else 0: OR-ed into the section index, and such neurons never take the slow path.
+template <typename TB>
+__device__ __forceinline__ int kmnc_strip_row(const float4 v, const float4 lo, const float4 jp, const float4 inv,
+                                              const int4 dead, float top, int k, TB* __restrict__ bp) {
+  const KmncFast f0 = kmnc_fast(v.x, lo.x, jp.x, inv.x, top);
+  const KmncFast f1 = kmnc_fast(v.y, lo.y, jp.y, inv.y, top);
+  const KmncFast f2 = kmnc_fast(v.z, lo.z, jp.z, inv.z, top);
+  const KmncFast f3 = kmnc_fast(v.w, lo.w, jp.w, inv.w, top);
+  int i0 = f0.i | dead.x, i1 = f1.i | dead.y, i2 = f2.i | dead.z, i3 = f3.i | dead.w;
+  const bool all_ok = (f0.ok || dead.x) && (f1.ok || dead.y) && (f2.ok || dead.z) && (f3.ok || dead.w);
+  if (!all_ok) {   // section edge, out of range, NaN
+    if (!(f0.ok || dead.x)) i0 = kmnc_bucket_slow(v.x, lo.x, jp.x, k);
+    if (!(f1.ok || dead.y)) i1 = kmnc_bucket_slow(v.y, lo.y, jp.y, k);
+    if (!(f2.ok || dead.z)) i2 = kmnc_bucket_slow(v.z, lo.z, jp.z, k);
+    if (!(f3.ok || dead.w)) i3 = kmnc_bucket_slow(v.w, lo.w, jp.w, k);
+  }
+  if (bp) {
+    if (sizeof(TB) == 2) {
+      *reinterpret_cast<short4*>(bp) = make_short4((short)i0, (short)i1, (short)i2, (short)i3);
+    } else {
+      *reinterpret_cast<int4*>(bp) = make_int4(i0, i1, i2, i3);
+    }
+  }
+  return (i0 >= 0) + (i1 >= 0) + (i2 >= 0) + (i3 >= 0);
+}
+
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+template <typename TB>
+__global__ void __launch_bounds__(256) kmnc_strip_kernel(const float* __restrict__ act, int64_t n, int64_t d,
+                                                         const float* __restrict__ mins,
+                                                         const float* __restrict__ jumps, int k,
+                                                         TB* __restrict__ bucket, int32_t* __restrict__ score,
+                                                         int nstrips, int rows_per_block) {
+  const int lane = threadIdx.x & 31;
+  const int strip = blockIdx.x % nstrips;
+  const int64_t rg = blockIdx.x / nstrips;
+  const int64_t d4 = d >> 2;
+  const int64_t j = (int64_t)strip * 256 + threadIdx.x;   // float4 column
+  const unsigned live = __ballot_sync(0xffffffffu, j < d4);   // lanes of this warp that own columns
+  if (j >= d4) return;                                         // no block-wide barriers below
+  const bool leader = lane == __ffs(live) - 1;
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(mins) + j);
+  const float4 jp = __ldg(reinterpret_cast<const float4*>(jumps) + j);
+  const float4 inv = make_float4(1.0f / jp.x, 1.0f / jp.y, 1.0f / jp.z, 1.0f / jp.w);   // inf/NaN -> slow path
+  const float top = 12582912.0f + (float)(k - 1);
+  const int4 dead = make_int4(jp.x > 0.f ? 0 : -1, jp.y > 0.f ? 0 : -1, jp.z > 0.f ? 0 : -1, jp.w > 0.f ? 0 : -1);
+  const int64_t row0 = rg * rows_per_block;
+  const int64_t row1 = min(n, row0 + (int64_t)rows_per_block);
+  const float4* src = reinterpret_cast<const float4*>(act) + row0 * d4 + j;
+  TB* dst = bucket ? bucket + row0 * d + (j << 2) : nullptr;
+  int32_t* sc = score + row0;
+  int64_t r = row0;
+  for (; r + kStripRows <= row1; r += kStripRows) {
+    float4 v[kStripRows];
+#pragma unroll
+    for (int u = 0; u < kStripRows; u++) v[u] = ld_stream_f4(src + u * d4);
+#pragma unroll
+    for (int u = 0; u < kStripRows; u++) {
+      int cnt = kmnc_strip_row<TB>(v[u], lo, jp, inv, dead, top, k, dst ? dst + u * d : nullptr);
+      cnt = __reduce_add_sync(live, cnt);
+      if (leader && cnt) atomicAdd(sc + u, cnt);
+    }
+    src += kStripRows * d4;
+    if (dst) dst += kStripRows * d;
+    sc += kStripRows;
+  }
+  for (; r < row1; r++) {
+    const float4 v = ld_stream_f4(src);
+    int cnt = kmnc_strip_row<TB>(v, lo, jp, inv, dead, top, k, dst);
+    cnt = __reduce_add_sync(live, cnt);
+    if (leader && cnt) atomicAdd(sc, cnt);
+    src += d4;
+    if (dst) dst += d;
+    sc++;
+  }
+}
+
 template <typename TA, typename TS>
 static int launch_kmnc(const void* act, int64_t n, int64_t d, const void* mins, const void* jumps, int k,
                        void* bucket, int bucket_dtype, int32_t* score, cudaStream_t st) {
@@ -569,6 +685,24 @@ extern "C" int tip_kmnc(const void* act, int act_dtype, int64_t n, int64_t d, co
                          (bucket == nullptr || ((uintptr_t)bucket & 15) == 0);
     if (aligned) {
       TIP_CHECK_CUDA(cudaMemsetAsync(score, 0, (size_t)n * sizeof(int32_t), st));
+      const int64_t nstrips = ((d >> 2) + 255) / 256;
+      if (n >= 4 * kStripRows && nstrips <= 65535 && sections <= (1 << 22)) {
+        // enough samples to amortise the per-block statistics load: column-strip kernel
+        int64_t rpb = (n * nstrips + (int64_t)sm_count() * 16 - 1) / ((int64_t)sm_count() * 16);
+        rpb = std::max<int64_t>(kStripRows, (rpb + kStripRows - 1) / kStripRows * kStripRows);
+        const int64_t blocks = nstrips * ((n + rpb - 1) / rpb);
+        TIP_REQUIRE(blocks < (1LL << 31), "too many blocks");
+        if (bucket == nullptr || bucket_dtype == TIP_I16)
+          kmnc_strip_kernel<int16_t><<<(unsigned)blocks, 256, 0, st>>>((const float*)act, n, d, (const float*)mins,
+                                                                      (const float*)jumps, sections, (int16_t*)bucket,
+                                                                      score, (int)nstrips, (int)rpb);
+        else
+          kmnc_strip_kernel<int32_t><<<(unsigned)blocks, 256, 0, st>>>((const float*)act, n, d, (const float*)mins,
+                                                                      (const float*)jumps, sections, (int32_t*)bucket,
+                                                                      score, (int)nstrips, (int)rpb);
+        TIP_LAUNCH_CHECK();
+        return TIP_OK;
+      }
       const int64_t chunks = n * (((d >> 2) + 31) >> 5);
       const int grid = (int)std::min<int64_t>((chunks + 7) / 8, (int64_t)sm_count() * 8);
       if (bucket == nullptr || bucket_dtype == TIP_I16)

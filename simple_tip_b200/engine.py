@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -26,6 +27,9 @@ import torch
 
 from . import _lib
 
+POOL_FRAC = float(os.environ.get("B200TIP_POOL_FRAC", "0.2"))   # share of the filter's work handed out dynamically
+POOL_MIN_TILES = 32       # tiles per CTA below which work lists stay purely static
+POOL_TILES = int(os.environ.get("B200TIP_POOL_TILES", "4"))      # train tiles per dynamic item
 DEFAULT_CAP = 64          # candidate chunks per query (short traces)
 DEFAULT_CAP_LONG = 256    # long traces: distances concentrate, more rows fall inside the window
 
@@ -207,13 +211,21 @@ def query_tiles(q_off: np.ndarray, ranges_per_class, t_off: Optional[np.ndarray]
     return tiles
 
 
-def build_balanced_items(tiles, col_tile: int, n_cta: int, item_cost: float = 0.75) -> np.ndarray:
-    """Work list for the persistent resident-query kernel, balanced for its static schedule
-    (CTA b runs items b, b + G, b + 2G, ...; G = min(n_cta, #items)).  The (query tile x train tile)
-    pairs are linearised query-tile-major and cut into G contiguous chunks of equal cost, so every
-    CTA streams the same number of train tiles (+-1) and loads as few query tiles as possible;
-    a chunk becomes one item per (query tile, train range) it touches.  `item_cost` is the price
-    of starting an item (query-tile load + pipeline refill) in train-tile units."""
+def build_balanced_items(tiles, col_tile: int, n_cta: int, item_cost: float = 0.75, pool_frac: float = 0.0,
+                         pool_tiles: int = 4) -> Tuple[np.ndarray, int]:
+    """Work list for the persistent resident-query kernel.  Returns (items [n, 6], n_static).
+
+    Static part, balanced for the kernel's schedule (CTA b runs items b, b + G, b + 2G, ...;
+    G = min(n_cta, #items)): the (query tile x train tile) pairs are linearised query-tile-major
+    and cut into G contiguous chunks of equal cost, so every CTA streams the same number of train
+    tiles (+-1) and loads as few query tiles as possible; a chunk becomes one item per (query tile,
+    train range) it touches.  `item_cost` is the price of starting an item (query-tile load +
+    pipeline refill) in train-tile units.
+
+    Dynamic part: the last `pool_frac` of every chunk is cut off and split into items of at most
+    `pool_tiles` train tiles that follow the static items in the array; CTAs pull them through an
+    atomic counter when their static share is done, which absorbs run-time differences between
+    CTAs (data-dependent candidate handling) that no static cut can foresee."""
     segs = []          # (q_row0, q_rows, lo, hi, flag, ntiles)
     for r0, nr, ranges, flag in tiles:
         for lo, hi in ranges:
@@ -221,36 +233,67 @@ def build_balanced_items(tiles, col_tile: int, n_cta: int, item_cost: float = 0.
             if nt > 0:
                 segs.append((int(r0), int(nr), int(lo), int(hi), int(flag), nt))
     if not segs:
-        return np.zeros((0, 6), dtype=np.int32)
+        return np.zeros((0, 6), dtype=np.int32), 0
     total = sum(sg[5] for sg in segs)
     g = int(min(n_cta, total))
     # Cost axis: every segment costs item_cost up front, then 1 per train tile.  A tile belongs to
     # the CTA whose equal share of the axis holds the tile's centre; consecutive tiles of a
-    # segment with the same owner form one item.
+    # segment with the same owner form one piece.
     cost_total = total + item_cost * len(segs)
-    per_cta = [[] for _ in range(g)]
+    per_cta = [[] for _ in range(g)]           # pieces: (segment index, first tile, one past last tile)
     pos = 0.0
-    for r0, nr, lo, hi, flag, nt in segs:
+    for si, (r0, nr, lo, hi, flag, nt) in enumerate(segs):
         pos += item_cost
         owner = np.minimum(((pos + np.arange(nt) + 0.5) * (g / cost_total)).astype(np.int64), g - 1)
         cuts = np.flatnonzero(np.diff(owner)) + 1
         starts = np.concatenate(([0], cuts))
         ends = np.concatenate((cuts, [nt]))
         for t0, t1 in zip(starts, ends):
-            per_cta[int(owner[t0])].append((r0, nr, lo + int(t0) * col_tile, min(hi, lo + int(t1) * col_tile), 0, flag))
+            per_cta[int(owner[t0])].append((si, int(t0), int(t1)))
         pos += nt
-    per_cta = [lst for lst in per_cta if lst]
+
+    def as_item(si, t0, t1):
+        r0, nr, lo, hi, flag, _ = segs[si]
+        return (r0, nr, lo + t0 * col_tile, min(hi, lo + t1 * col_tile), 0, flag)
+
+    pool, tails = [], []
+    if pool_frac > 0.0 and total >= POOL_MIN_TILES * g:   # short launches: the item-start cost outweighs the tail
+        for lst in per_cta:
+            give = int(round(pool_frac * sum(t1 - t0 for _, t0, t1 in lst)))
+            tail = []
+            while give > 0 and lst:
+                si, t0, t1 = lst[-1]
+                take = min(give, t1 - t0)
+                tail.append((si, t1 - take, t1))
+                give -= take
+                if take == t1 - t0:
+                    lst.pop()
+                else:
+                    lst[-1] = (si, t0, t1 - take)
+            mine = []
+            for si, t0, t1 in reversed(tail):             # keep the train order inside a chunk
+                for p0 in range(t0, t1, pool_tiles):
+                    mine.append(as_item(si, p0, min(t1, p0 + pool_tiles)))
+            tails.append(mine)
+        # Pool order: round-robin over the chunks.  CTAs arrive at the pool at about the same time and
+        # take one item per round, so a CTA's successive draws tend to be successive pieces of one
+        # chunk's tail — same query tile, which the kernel then keeps resident.
+        for r in range(max((len(tl) for tl in tails), default=0)):
+            pool.extend(tl[r] for tl in tails if len(tl) > r)
+    per_cta = [[as_item(*pc) for pc in lst] for lst in per_cta if lst]
     per_cta.sort(key=len, reverse=True)       # CTAs with more items first: rounds stay dense prefixes
     g = len(per_cta)
-    rounds = len(per_cta[0])
+    rounds = len(per_cta[0]) if per_cta else 0
     out = []
     empty = (0, 0, 0, 0, 0, 0)                # col0 == col1: the kernel skips it
     for r in range(rounds):
         row = [lst[r] for lst in per_cta if len(lst) > r]
-        if r + 1 < rounds:
+        if r + 1 < rounds or pool:
             row += [empty] * (g - len(row))   # keep item index = round * G + CTA
         out.extend(row)
-    return np.asarray(out, dtype=np.int32).reshape(-1, 6)
+    n_static = len(out)
+    out.extend(pool)
+    return np.asarray(out, dtype=np.int32).reshape(-1, 6), n_static
 
 
 def count_tile_pairs(q_off: np.ndarray, ranges_per_class, row_tile: int = _lib.ROW_TILE,
@@ -355,6 +398,7 @@ class NnEngine:
         self._plans = {}
         self._work = {}
         self._inputs = {}
+        self.sched_counter = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.last_cand_cnt_by_mode = {}
         if self.n > 0:
             self.center = self.t.mean(dim=0, dtype=torch.float64).to(torch.float32).contiguous()
@@ -436,8 +480,10 @@ class NnEngine:
                 if self.row_tile == 256:
                     # resident-query kernel: one or two long items per CTA, equal tile counts
                     tiles = query_tiles(q_off, ranges, self.class_off, self.row_tile, mixed)
-                    items = build_balanced_items(tiles, self.col_tile, self.sms)
+                    items, n_static = build_balanced_items(tiles, self.col_tile, self.sms, pool_frac=POOL_FRAC,
+                                                           pool_tiles=POOL_TILES)
                 else:
+                    n_static = None
                     span_of = lambda pairs: span_tiles_for(pairs, self.sms)
                     if mixed:
                         items = build_other_class_items(q_off, self.class_off, self.row_tile, self.col_tile, span_of)
@@ -447,11 +493,13 @@ class NnEngine:
                 flops = 2.0 * self.d * sum(int(q_off[c + 1] - q_off[c]) * sum(int(hi) - int(lo) for lo, hi in ranges[c])
                                            for c in range(self.num_classes))
                 flagged = bool(items.shape[0] and (items[:, 5] & 1).any())
-                plan = (torch.from_numpy(items).to(self.dev) if items.shape[0] else None, items.shape[0], flops, flagged)
+                n_static = items.shape[0] if n_static is None else n_static
+                plan = (torch.from_numpy(items).to(self.dev) if items.shape[0] else None, items.shape[0], flops, flagged,
+                        n_static)
                 if len(self._item_cache) > 64:
                     self._item_cache.clear()
                 self._item_cache[key] = plan
-            items_dev, n_items, flops, flagged = plan
+            items_dev, n_items, flops, flagged, n_static = plan
             if n_items > 0:
                 q_pack = torch.empty((m, self.pitch), dtype=torch.bfloat16, device=self.dev)
                 q_sq = torch.empty(m, dtype=torch.float32, device=self.dev)
@@ -470,7 +518,9 @@ class NnEngine:
                                              _p(items_dev), n_items, _p(q_class if flagged else None),
                                              _p(self.class_off_dev if flagged else None), self.rmax,
                                              _p(q_err), self.errmax, _p(row_min), _p(cand_idx),
-                                             _p(cand_cnt), self.cap, _stream()), "tip_nn_filter")
+                                             _p(cand_cnt), self.cap, n_static,
+                                             _p(self.sched_counter if n_static < n_items else None),
+                                             _stream()), "tip_nn_filter")
                 if ev is not None:
                     ev[1].record()
                     name = "nn_filter_same_class" if mode == _lib.RANGE_SAME_CLASS else "nn_filter_other_classes"

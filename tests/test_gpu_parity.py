@@ -163,7 +163,8 @@ def test_kmnc_known_answer_from_reference_tests():
     assert np.all(KMNC(mins, maxs, 2)(out)[0] == np.array([11, 13]))
 
 
-@pytest.mark.parametrize("n,d,k", [(2000, 4096, 1000), (513, 1001, 50), (64, 4096, 10000)])
+@pytest.mark.parametrize("n,d,k", [(2000, 4096, 1000), (513, 1001, 50), (64, 4096, 10000), (301, 1000, 7),
+                                   (33, 4, 2)])
 def test_kmnc_large_vs_c_oracle(n, d, k):
     from src.core.neuron_coverage import KMNC
 

@@ -124,7 +124,8 @@ def test_other_class_items_cover_every_pair_exactly_once():
 
 def test_balanced_items_cover_every_pair_once_and_balance_the_static_schedule():
     """Work list of the resident-query kernel: equal train-tile counts per CTA under the kernel's
-    `item = CTA + round * G` schedule, padding entries (col0 == col1) only to keep that indexing."""
+    `item = CTA + round * G` schedule for the static items (padding entries, col0 == col1, only keep
+    that indexing), plus an optional pool of short items handed out dynamically."""
     cases = [(np.array([0, 300, 300, 1000]), np.array([0, 5000, 5600, 9000]), 148),
              (np.arange(0, 1001, 10), np.arange(0, 16001, 160), 148),           # 100 classes of 10 queries
              (np.array([0, 7]), np.array([0, 50]), 148),
@@ -134,11 +135,15 @@ def test_balanced_items_cover_every_pair_once_and_balance_the_static_schedule():
         m, n = int(q_off[-1]), int(t_off[-1])
         classes = len(q_off) - 1
         q_class = np.repeat(np.arange(classes), np.diff(q_off))
-        for mode, mixed in (("same", False), ("other", False), ("other", True)):
+        for mode, mixed, pool_frac in (("same", False, 0.0), ("other", False, 0.0), ("other", True, 0.0),
+                                       ("same", False, 0.2), ("other", False, 0.2), ("other", True, 0.2)):
             ranges = [[(t_off[c], t_off[c + 1])] if mode == "same" else [(0, t_off[c]), (t_off[c + 1], t_off[-1])]
                       for c in range(classes)]
             tiles = E.query_tiles(q_off, ranges, t_off, 256, mixed)
-            items = E.build_balanced_items(tiles, 256, n_cta)
+            items, n_static = E.build_balanced_items(tiles, 256, n_cta, pool_frac=pool_frac, pool_tiles=4)
+            assert 0 <= n_static <= items.shape[0] and (pool_frac > 0 or n_static == items.shape[0])
+            pool = items[n_static:]
+            assert np.all(pool[:, 3] > pool[:, 2]) and np.all(-(-(pool[:, 3] - pool[:, 2]) // 256) <= 4)
             live = items[items[:, 3] > items[:, 2]]
             total_tiles = int(np.sum(-(-(live[:, 3] - live[:, 2]) // 256)))
             cover = np.zeros((m, n), dtype=np.int32)
@@ -158,18 +163,21 @@ def test_balanced_items_cover_every_pair_once_and_balance_the_static_schedule():
             for c in range(classes):
                 for lo, hi in ranges[c]:
                     want[q_off[c]:q_off[c + 1], lo:hi] = 1
-            assert np.array_equal(cover, want), (mode, mixed)
+            assert np.array_equal(cover, want), (mode, mixed, pool_frac)
             if items.shape[0] == 0:
                 continue
-            # the kernel's schedule: grid = min(#items, #SMs), CTA b takes items b, b + grid, ...
+            # the kernel's static schedule: grid = min(#items, #SMs), CTA b takes items b, b + grid, ...
             grid = min(items.shape[0], n_cta)
             load = np.zeros(grid, dtype=np.int64)
-            for i, it in enumerate(items):
+            for i, it in enumerate(items[:n_static]):
                 load[i % grid] += -(-(it[3] - it[2]) // 256)
-            if total_tiles >= 4 * n_cta:
-                assert load.max() <= np.ceil(total_tiles / grid) + 3, (load.max(), total_tiles / grid)
-                assert load.min() >= np.floor(total_tiles / grid) - 3
-    assert E.build_balanced_items([], 256, 148).shape == (0, 6)
+            static_tiles = int(load.sum())
+            if total_tiles >= E.POOL_MIN_TILES * n_cta:
+                assert load.max() <= np.ceil(static_tiles / grid) + 3, (load.max(), static_tiles / grid)
+                assert load.min() >= np.floor(static_tiles / grid) - 3
+                if pool_frac > 0:
+                    assert 0.1 * total_tiles <= total_tiles - static_tiles <= 0.3 * total_tiles
+    assert E.build_balanced_items([], 256, 148)[0].shape == (0, 6)
 
 
 def test_shard_rows_partition_preserves_class_order():

@@ -30,15 +30,16 @@ for mode, q in ((_lib.RANGE_OTHER_CLASSES, w), (_lib.RANGE_SAME_CLASS, x)):
     lib.tip_debug_cta_clock(None)
     t = buf.cpu().numpy()
     t = t[t[:, 1] > 0]
+    items = t[:, 3] & 0xffffffff
+    smid = t[:, 3] >> 32
     t0 = t[:, 0].min()
     start, end = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3
     dur = end - start
     print(f"mode {mode}: {len(t)} CTAs; kernel span {end.max():.1f} us; CTA start skew max {start.max():.1f} us; "
           f"CTA duration min {dur.min():.1f} p50 {np.median(dur):.1f} p90 {np.percentile(dur, 90):.1f} max {dur.max():.1f} us")
-    print(f"  tiles per CTA min {t[:, 2].min()} max {t[:, 2].max()}; items per CTA max {t[:, 3].max()}")
-    for k in np.unique(t[:, 3]):
-        sel = t[:, 3] == k
-        print(f"  CTAs with {k} item(s): n={sel.sum()} duration p50 {np.median(dur[sel]):.1f} max {dur[sel].max():.1f} us; "
-              f"ns/tile p50 {np.median(dur[sel] * 1e3 / t[sel, 2]):.0f}")
-    slow = np.argsort(-dur)[:5]
-    print("  slowest CTAs (idx, us, tiles, items):", [(int(i), round(float(dur[i]), 1), int(t[i, 2]), int(t[i, 3])) for i in slow])
+    print(f"  tiles per CTA min {t[:, 2].min()} p50 {np.median(t[:, 2]):.0f} max {t[:, 2].max()}; items per CTA min {items.min()} max {items.max()}")
+    print(f"  ns per tile: min {np.min(dur * 1e3 / t[:, 2]):.0f} p50 {np.median(dur * 1e3 / t[:, 2]):.0f} max {np.max(dur * 1e3 / t[:, 2]):.0f}")
+    slow = np.argsort(-dur)[:8]
+    print("  slowest CTAs (cta, smid, us, tiles, items):", [(int(i), int(smid[i]), round(float(dur[i]), 1), int(t[i, 2]), int(items[i])) for i in slow])
+    fast = np.argsort(dur)[:8]
+    print("  fastest CTAs (cta, smid, us, tiles, items):", [(int(i), int(smid[i]), round(float(dur[i]), 1), int(t[i, 2]), int(items[i])) for i in fast])
