@@ -202,7 +202,7 @@ def run_ours(args):
         if plan is None:
             return step_eager()
         out = plan.run()
-        return out[0] / out[1]
+        return out[3] if out.shape[0] == 4 else out[0] / out[1]
 
     def step_e2e():
         return sa(xte_host, pte)
@@ -284,7 +284,7 @@ def run_ours(args):
                                       "per-stage CUDA graphs + eager NCCL all-reduces") if plan is not None else "eager launches"},
                 "e2e": {"value": e2e, "unit": "inputs/s", "ms_per_step": tot_e2e_ms / args.steps,
                         "h2d_bytes_per_step": int(xte.nbytes + pte.shape[0] * 4),
-                        "d2h_bytes_per_step": int(3 * n_test * 4)},
+                        "d2h_bytes_per_step": int(4 * n_test * 8)},   # dist_a, dist_b, winner index, dsa as float64
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(xtr, ytr, xte, pte)

@@ -166,18 +166,26 @@ int tip_nn_filter_tile(int64_t d, int32_t* q_rows, int32_t* t_rows);
  * exhaustive scan + the per-slice partial winners of that scan).  The caller zero-fills it once;
  * every call leaves the two words it relies on (queue length work[0], completion counter
  * work[1 + m]) at zero again, so the buffer can be reused by the next call on the same stream.
- * stats[0] += exhaustive rows, stats[1] += candidate entries walked. */
+ * stats[0] += exhaustive rows, stats[1] += candidate entries walked.
+ * next_*: optional (all NULL, or pack + sqnorm + row_min_bits + cand_cnt given): the winning rows are
+ * also emitted as the packed queries and reset filter state of a following tip_nn_filter call —
+ * exactly what tip_nn_query_prep(out_rows, center = next_center) would write — so DSA's second
+ * stage (whose queries are stage 1's winners, surprise.py:627-629) needs no pack launch. */
 int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype);
 int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n, int64_t d,
                   const int32_t* cand_idx, const int32_t* cand_cnt, int32_t cap,
                   const int32_t* q_class, const int32_t* class_off, int32_t n_classes, int mode,
                   const int32_t* t_gid, void* out_dist, int32_t* out_pos, int32_t* out_gid,
-                  void* out_rows, int32_t* work, int64_t* stats, void* stream);
+                  void* out_rows, int32_t* work, int64_t* stats, const float* next_center,
+                  void* next_pack, float* next_sqnorm, float* next_rounderr,
+                  uint32_t* next_row_min_bits, int32_t* next_cand_cnt, void* stream);
 
 /* DSA result packing (surprise.py:576-611 scatter by index): for i < m,
- *   out[0*n_total + j] = dist_a[i], out[1*n_total + j] = dist_b[i], out[2*n_total + j] = gid[i]
- * with j = idx[i] (idx == NULL: j = i); dist_* in `dtype` (TIP_F32/TIP_F64) are widened to double
- * exactly, gid (int32) likewise.  Columns not named by idx are left untouched. */
+ *   out[0*n_total + j] = dist_a[i], out[1*n_total + j] = dist_b[i], out[2*n_total + j] = gid[i],
+ *   out[3*n_total + j] = dist_a[i] / dist_b[i]  (IEEE division in `dtype`, surprise.py:595)
+ * with j = idx[i] (idx == NULL: j = i); values in `dtype` (TIP_F32/TIP_F64) are widened to double
+ * exactly, gid (int32) likewise.  out holds 4*n_total doubles; columns not named by idx are left
+ * untouched. */
 int tip_dsa_pack_out(const void* dist_a, const void* dist_b, int dtype, const int32_t* gid,
                      const int32_t* idx, int64_t m, int64_t n_total, double* out, void* stream);
 

@@ -372,18 +372,21 @@ class DSA(SA):
                 if len(self.class_matrix[c]) == self.train_predictions.shape[0]:
                     raise ValueError("zero-size array to reduction operation minimum which has no identity")
         if order.size == 0:
-            self.last_winner_index = np.full(n_total, -1, dtype=np.int64)
-            self.last_dist_a = np.full(n_total, np.nan, dtype=self._compute_dtype)
-            self.last_dist_b = np.full(n_total, np.nan, dtype=self._compute_dtype)
+            self._last_raw = np.full((3, n_total), np.nan)
+            self._last_raw[2] = -1.0
             return np.full(shape=n_total, fill_value=np.nan)
         if fused:
             # steady state: upload the permutation, replay, one D2H copy into pinned memory
             plan = E.dsa_plan(eng, int(order.size), q_off, x_all.dtype, self.use_filter, None, n_total=n_total)
-            plan.idx.copy_(torch.from_numpy(order.astype(np.int32)), non_blocking=True)
+            np.copyto(plan.idx_host.numpy(), order, casting="unsafe")      # pinned staging: async H2D
+            plan.idx.copy_(plan.idx_host, non_blocking=True)
             plan.graph.replay()
             plan.out_host.copy_(plan.out, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return self._finish(plan.out_host.numpy())
+            # the division already happened on the device in the trace dtype (surprise.py:595);
+            # last_dist_a / last_dist_b / last_winner_index read this buffer on demand
+            self._last_raw = plan.out_host.numpy()
+            return self._last_raw[3].copy()
         idx = torch.from_numpy(order).to(dev, non_blocking=True)
         if self.use_graphs:
             # sharded training sets replay one graph per stage with eager NCCL all-reduces in between
@@ -404,10 +407,22 @@ class DSA(SA):
 
     def _finish(self, res: np.ndarray) -> np.ndarray:
         """res[3, n]: dist_a, dist_b, winner index as float64 (exact widenings) in the caller's order."""
+        self._last_raw = res
         a = res[0].astype(self._compute_dtype)
         b = res[1].astype(self._compute_dtype)
-        self.last_winner_index = res[2].astype(np.int64)
-        self.last_dist_a, self.last_dist_b = a, b
         with np.errstate(divide="ignore", invalid="ignore"):
             # the reference divides in the input dtype and widens on store (surprise.py:595,611)
             return (a / b).astype(np.float64)
+
+    # Results of the most recent call (exact widenings of the device values; valid until the next call)
+    @property
+    def last_dist_a(self) -> np.ndarray:
+        return self._last_raw[0].astype(self._compute_dtype)
+
+    @property
+    def last_dist_b(self) -> np.ndarray:
+        return self._last_raw[1].astype(self._compute_dtype)
+
+    @property
+    def last_winner_index(self) -> np.ndarray:
+        return self._last_raw[2].astype(np.int64)

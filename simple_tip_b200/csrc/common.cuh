@@ -46,6 +46,7 @@ template <> struct Rn<float> {
   static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
   static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
   static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
   static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
 };
 template <> struct Rn<double> {
@@ -53,6 +54,7 @@ template <> struct Rn<double> {
   static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
   static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
   static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
   static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 };
 

@@ -69,6 +69,15 @@ struct RerankArgs {
   T* out_rows;        // nullable: m x d copy of the winning train rows
   int32_t* work;      // work[0] = number of queued queries, work[1..] = their rows
   unsigned long long* stats;
+  // optional: the winning rows packed as the queries of the next tip_nn_filter call (what
+  // tip_nn_query_prep would produce from out_rows), so DSA's second stage needs no pack launch
+  const float* next_center;
+  __nv_bfloat16* next_pack;
+  int64_t next_pitch;
+  float* next_sqnorm;
+  float* next_rounderr;
+  uint32_t* next_row_min;
+  int32_t* next_cand_cnt;
 };
 
 template <typename T>
@@ -79,10 +88,40 @@ __device__ __forceinline__ void write_result(const RerankArgs<T>& a, int64_t row
     a.out_pos[row] = b.pos;
     if (a.out_gid) a.out_gid[row] = b.pos >= 0 ? (a.t_gid ? a.t_gid[b.pos] : b.pos) : -1;
   }
+  const T* src = a.t + (int64_t)(b.pos < 0 ? 0 : b.pos) * a.d;
   if (a.out_rows) {
     T* dst = a.out_rows + row * (int64_t)a.d;
-    const T* src = a.t + (int64_t)(b.pos < 0 ? 0 : b.pos) * a.d;
     for (int i = lane; i < a.d; i += nlanes) dst[i] = b.pos >= 0 ? src[i] : (T)0;
+  }
+  if (a.next_pack) {
+    // same arithmetic as pair_prep_kernel (query role, one segment): centre in fp32, round to bf16,
+    // |h|^2 and the dropped part's norm accumulated in double; nlanes == 32 here
+    __nv_bfloat16* out = a.next_pack + row * a.next_pitch;
+    const int d16 = (a.d + 15) & ~15;
+    double acc = 0.0, err = 0.0;
+    for (int c = lane; c < d16; c += 32) {
+      float v = 0.f;
+      if (c < a.d) {
+        const T xv = b.pos >= 0 ? src[c] : (T)0;
+        const float ctr = a.next_center ? a.next_center[c] : 0.f;
+        v = sizeof(T) == 8 ? (float)((double)xv - (double)ctr) : __fsub_rn((float)xv, ctr);
+      }
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const float hf = __bfloat162float(h);
+      const float res = __fsub_rn(v, hf);
+      acc += (double)hf * (double)hf;
+      err += (double)res * (double)res;
+      out[c] = h;
+    }
+    acc = warp_sum(acc);
+    err = warp_sum(err);
+    for (int c = d16 + lane; c < a.next_pitch; c += 32) out[c] = __float2bfloat16_rn(c - d16 < 3 ? 1.f : 0.f);
+    if (lane == 0) {
+      a.next_sqnorm[row] = (float)acc;
+      if (a.next_rounderr) a.next_rounderr[row] = (float)sqrt(err) * 1.000001f;
+      a.next_row_min[row] = 0x7f800000u;
+      a.next_cand_cnt[row] = 0;
+    }
   }
 }
 
@@ -274,24 +313,31 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
                              const int32_t* cand_idx, const int32_t* cand_cnt, int32_t cap, const int32_t* q_class,
                              const int32_t* class_off, int32_t n_classes, int mode, const int32_t* t_gid,
                              void* out_dist, int32_t* out_pos, int32_t* out_gid, void* out_rows, int32_t* work,
-                             int64_t* stats, void* stream) {
+                             int64_t* stats, const float* next_center, void* next_pack, float* next_sqnorm,
+                             float* next_rounderr, uint32_t* next_row_min_bits, int32_t* next_cand_cnt,
+                             void* stream) {
   TIP_REQUIRE(q && t && out_dist && out_pos && work, "null pointer");
   TIP_REQUIRE(class_off && n_classes >= 1, "class offsets");
   TIP_REQUIRE(m >= 0 && m < (1LL << 31) - 8 && n >= 0 && n < (1LL << 31) && d >= 1 && d < (1LL << 31), "shape");
   TIP_REQUIRE(mode == TIP_RANGE_SAME_CLASS || mode == TIP_RANGE_OTHER_CLASSES, "mode");
   TIP_REQUIRE(cand_cnt == nullptr || (cand_idx != nullptr && cap >= 1), "candidate buffers");
+  TIP_REQUIRE(next_pack == nullptr || (next_sqnorm && next_row_min_bits && next_cand_cnt),
+              "next-stage query state: pack, sqnorm, row_min_bits and cand_cnt go together");
   if (m == 0) return TIP_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  const int64_t next_pitch = tip_pair_pitch(d, 1);
   if (dtype == TIP_F32) {
     RerankArgs<float> a{(const float*)q, (const float*)t, m, n, (int)d, cand_idx, cand_cnt, cap, q_class, class_off,
                         n_classes, mode, t_gid, (float*)out_dist, out_pos, out_gid, (float*)out_rows, work,
-                        (unsigned long long*)stats};
+                        (unsigned long long*)stats, next_center, (__nv_bfloat16*)next_pack, next_pitch, next_sqnorm,
+                        next_rounderr, next_row_min_bits, next_cand_cnt};
     return launch_rerank<float>(a, st);
   }
   if (dtype == TIP_F64) {
     RerankArgs<double> a{(const double*)q, (const double*)t, m, n, (int)d, cand_idx, cand_cnt, cap, q_class,
                          class_off, n_classes, mode, t_gid, (double*)out_dist, out_pos, out_gid, (double*)out_rows,
-                         work, (unsigned long long*)stats};
+                         work, (unsigned long long*)stats, next_center, (__nv_bfloat16*)next_pack, next_pitch,
+                         next_sqnorm, next_rounderr, next_row_min_bits, next_cand_cnt};
     return launch_rerank<double>(a, st);
   }
   TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");

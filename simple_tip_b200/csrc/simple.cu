@@ -782,9 +782,11 @@ __global__ void __launch_bounds__(256) dsa_pack_out_kernel(const T* __restrict__
   if (i >= m) return;
   const int64_t j = idx ? idx[i] : i;
   if (j < 0 || j >= n_total) return;
-  out[j] = (double)da[i];
-  out[n_total + j] = (double)db[i];
+  const T a = da[i], b = db[i];
+  out[j] = (double)a;
+  out[n_total + j] = (double)b;
   out[2 * n_total + j] = (double)gid[i];
+  out[3 * n_total + j] = (double)Rn<T>::div(a, b);   // dist_a / dist_b in the input dtype (surprise.py:595), IEEE RN
 }
 
 extern "C" int tip_dsa_pack_out(const void* dist_a, const void* dist_b, int dtype, const int32_t* gid,

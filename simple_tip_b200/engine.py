@@ -453,12 +453,31 @@ class NnEngine:
             return [[(off[c], off[c + 1])] for c in range(self.num_classes)]
         return [[(0, off[c]), (off[c + 1], off[-1])] for c in range(self.num_classes)]
 
+    def query_state(self, m: int):
+        """Filter-side state of m queries: packed bf16 operand, |h|^2, rounding-error norm, running
+        minimum bits, candidate count (what tip_nn_query_prep fills)."""
+        return (torch.empty((m, self.pitch), dtype=torch.bfloat16, device=self.dev),
+                torch.empty(m, dtype=torch.float32, device=self.dev),
+                torch.empty(m, dtype=torch.float32, device=self.dev),
+                torch.empty(m, dtype=torch.int32, device=self.dev),
+                torch.empty(m, dtype=torch.int32, device=self.dev))
+
+    def has_items(self, q_off: np.ndarray, mode: int) -> bool:
+        """True if a search of this mode would launch the filter for queries with this class histogram."""
+        if self.n == 0:
+            return False
+        ranges = self.ranges(mode)
+        return any(int(q_off[c + 1]) > int(q_off[c]) and any(int(hi) > int(lo) for lo, hi in ranges[c])
+                   for c in range(self.num_classes))
+
     def search(self, q: torch.Tensor, q_class: torch.Tensor, q_off: np.ndarray, mode: int, use_filter: bool = True,
-               want_rows: bool = False):
+               want_rows: bool = False, prepacked=None, next_query=None):
         """q: [m, d] queries grouped by class (q_off), q_class[m] int32.  Returns, per query, the
         exact NumPy-order distance to its nearest train row in the range selected by `mode`
         (NaN when the range is empty on this shard), that row's position (-1 when empty), its
-        original index, and (want_rows) a copy of the winning train rows."""
+        original index, and (want_rows) a copy of the winning train rows.
+        prepacked: query_state() already filled for q (by a previous search's next_query);
+        next_query: query_state() to fill with the winning rows as the next search's queries."""
         m = q.shape[0]
         out_dist = torch.empty(m, dtype=q.dtype, device=self.dev)
         out_pos = torch.empty(m, dtype=torch.int32, device=self.dev)
@@ -501,15 +520,14 @@ class NnEngine:
                 self._item_cache[key] = plan
             items_dev, n_items, flops, flagged, n_static = plan
             if n_items > 0:
-                q_pack = torch.empty((m, self.pitch), dtype=torch.bfloat16, device=self.dev)
-                q_sq = torch.empty(m, dtype=torch.float32, device=self.dev)
-                q_err = torch.empty(m, dtype=torch.float32, device=self.dev)
-                row_min = torch.empty(m, dtype=torch.int32, device=self.dev)
-                cand_cnt = torch.empty(m, dtype=torch.int32, device=self.dev)
+                if prepacked is not None:
+                    q_pack, q_sq, q_err, row_min, cand_cnt = prepacked
+                else:
+                    q_pack, q_sq, q_err, row_min, cand_cnt = self.query_state(m)
+                    _lib.check(lib.tip_nn_query_prep(_p(q), tip_dtype(q.dtype), m, self.d, _p(self.center), _p(q_pack),
+                                                     _p(q_sq), _p(q_err), _p(row_min), _p(cand_cnt), _stream()),
+                               "tip_nn_query_prep")
                 cand_idx = torch.empty((m, self.cap, 2), dtype=torch.int32, device=self.dev)
-                _lib.check(lib.tip_nn_query_prep(_p(q), tip_dtype(q.dtype), m, self.d, _p(self.center), _p(q_pack),
-                                                 _p(q_sq), _p(q_err), _p(row_min), _p(cand_cnt), _stream()),
-                           "tip_nn_query_prep")
                 ev = None
                 if PROFILE is not None:
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -526,10 +544,13 @@ class NnEngine:
                     name = "nn_filter_same_class" if mode == _lib.RANGE_SAME_CLASS else "nn_filter_other_classes"
                     PROFILE.append((name, flops, ev[0], ev[1]))
         work = self.work_buffer(m, q.dtype)
+        nq = [_p(t) for t in next_query] if next_query is not None else [None] * 5
         _lib.check(lib.tip_nn_rerank(_p(q), _p(self.t), tip_dtype(q.dtype), m, self.n, self.d, _p(cand_idx),
                                      _p(cand_cnt), self.cap, _p(q_class), _p(self.class_off_dev), self.num_classes,
                                      mode, _p(self.t_gid), _p(out_dist), _p(out_pos), _p(out_gid), _p(out_rows),
-                                     _p(work), _p(self.stats), _stream()), "tip_nn_rerank")
+                                     _p(work), _p(self.stats),
+                                     _p(self.center) if next_query is not None else None, *nq, _stream()),
+                   "tip_nn_rerank")
         self.last_cand_cnt = cand_cnt
         if cand_cnt is not None:
             self.last_cand_cnt_by_mode[mode] = (cand_cnt, cand_idx)
@@ -547,10 +568,15 @@ def dsa_distances(engine: NnEngine, x: torch.Tensor, q_class: torch.Tensor, q_of
                   comm: Optional[TrainShardComm] = None, use_filter: bool = True
                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """surprise.py:615-631 for class-sorted queries x: (dist_a, dist_b, winner original index)."""
-    dist_a, _, gid, winners = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter, want_rows=True)
-    if comm is not None and comm.world > 1:
+    sharded = comm is not None and comm.world > 1
+    # single shard: stage 1's re-rank also emits its winners as the packed queries of stage 2
+    fuse = use_filter and not sharded and engine.has_items(q_off, _lib.RANGE_OTHER_CLASSES)
+    state2 = engine.query_state(x.shape[0]) if fuse else None
+    dist_a, _, gid, winners = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter, want_rows=True,
+                                            next_query=state2)
+    if sharded:
         dist_a, gid, winners = comm.reduce_winners(dist_a, gid, winners)
-    dist_b = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter)[0]
+    dist_b = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter, prepacked=state2)[0]
     if comm is not None and comm.world > 1:
         dist_b = comm.reduce_min_nan(dist_b)
     return dist_a, dist_b, gid
@@ -561,8 +587,9 @@ class DsaPlan:
     gather into class-sorted order -> pack -> filter -> re-rank(+winner rows) -> pack -> filter ->
     re-rank -> scatter of (dist_a, dist_b, winner index) back to the caller's row order.
     Inputs: `x_in` [n_total, d] (the engine's landing buffer for host uploads) and `idx` [m]
-    (original row of every class-sorted query).  Output: `out` [3, n_total] float64 in the
-    caller's order (rows the reference never scores keep NaN / -1)."""
+    (original row of every class-sorted query).  Output: `out` [4, n_total] float64 in the
+    caller's order — dist_a, dist_b, winner index, dist_a / dist_b (divided in the trace dtype) —
+    where rows the reference never scores keep NaN / -1."""
 
     def __init__(self, engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool,
                  comm: Optional[TrainShardComm] = None, n_total: Optional[int] = None):
@@ -575,9 +602,10 @@ class DsaPlan:
         self.x_in = engine.input_buffer(self.n_total, dtype)
         self.idx = torch.arange(self.m, dtype=torch.int32, device=dev)
         self.x = torch.zeros((m, engine.d), dtype=dtype, device=dev)
-        self.out = torch.full((3, self.n_total), float("nan"), dtype=torch.float64, device=dev)
+        self.out = torch.full((4, self.n_total), float("nan"), dtype=torch.float64, device=dev)
         self.out[2].fill_(-1.0)
-        self.out_host = torch.empty((3, self.n_total), dtype=torch.float64).pin_memory()
+        self.out_host = torch.empty((4, self.n_total), dtype=torch.float64).pin_memory()
+        self.idx_host = torch.empty(self.m, dtype=torch.int32).pin_memory()
         q_class = np.repeat(np.arange(engine.num_classes, dtype=np.int32), np.diff(self.q_off))
         self.q_class = torch.from_numpy(q_class).to(dev)
         row_bytes = engine.d * self.x.element_size()
@@ -587,7 +615,7 @@ class DsaPlan:
                        "tip_gather_rows")
             a, b, gid = dsa_distances(engine, self.x, self.q_class, self.q_off, comm, use_filter)
             if self.n_total != self.m:         # which rows are unscored can change between calls
-                self.out[:2].fill_(float("nan"))
+                self.out.fill_(float("nan"))
                 self.out[2].fill_(-1.0)
             _lib.check(lib.tip_dsa_pack_out(_p(a), _p(b), tip_dtype(a.dtype), _p(gid), _p(self.idx), self.m,
                                             self.n_total, _p(self.out), _stream()), "tip_dsa_pack_out")
