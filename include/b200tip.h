@@ -166,7 +166,8 @@ int tip_nn_filter_tile(int64_t d, int32_t* q_rows, int32_t* t_rows);
  * exhaustive scan + the per-slice partial winners of that scan).  The caller zero-fills it once;
  * every call leaves the two words it relies on (queue length work[0], completion counter
  * work[1 + m]) at zero again, so the buffer can be reused by the next call on the same stream.
- * stats[0] += exhaustive rows, stats[1] += candidate entries walked.
+ * stats[0] += rows that took the exhaustive scan (stats[1] is reserved; candidate counts are in
+ * cand_cnt).
  * next_*: optional (all NULL, or pack + sqnorm + row_min_bits + cand_cnt given): the winning rows are
  * also emitted as the packed queries and reset filter state of a following tip_nn_filter call —
  * exactly what tip_nn_query_prep(out_rows, center = next_center) would write — so DSA's second

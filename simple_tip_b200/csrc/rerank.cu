@@ -126,13 +126,34 @@ __device__ __forceinline__ void write_result(const RerankArgs<T>& a, int64_t row
 }
 
 // ---- kernel 1: one warp per query, candidate lists ----------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) rerank_list_kernel(const RerankArgs<T> a) {
+// SMALL = traces of at most 128 elements (one leaf of NumPy's pairwise sum): every lane keeps the
+// query elements of the stride-8 accumulator it owns in registers — loaded once, in the same
+// round trip as the candidate count — and a candidate row costs 16 loads + 47 flops per lane.
+template <typename T, bool SMALL>
+__global__ void __launch_bounds__(256, (SMALL && sizeof(T) == 4) ? 4 : 1) rerank_list_kernel(const RerankArgs<T> a) {
+  using R = Rn<T>;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= a.m) return;
+  const int sub = lane & 7, grp = lane >> 3;
+  // The work per query is a chain of dependent loads; issue everything that does not depend on
+  // another load at once: the count, the class, the query row and (speculatively — the slots
+  // exist whatever the count) the first four candidate entries, one per 8-lane group.
   const int cnt = a.cand_cnt ? a.cand_cnt[row] : 0;
   const int cls = a.q_class ? a.q_class[row] : 0;
+  const bool spec = a.cand_cnt != nullptr && a.cap >= 4;
+  int2 first = make_int2(0, 0);
+  if (spec) first = *reinterpret_cast<const int2*>(a.cand_idx + (row * (int64_t)a.cap + grp) * 2);
+  const T* x = a.q + row * (int64_t)a.d;
+  const int n = a.d;
+  const int lim = n - (n % 8);
+  T xr[SMALL ? 16 : 1], xt[SMALL ? 7 : 1];
+  if (SMALL) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) xr[u] = 8 * u + sub < lim ? x[8 * u + sub] : (T)0;
+#pragma unroll
+    for (int u = 0; u < 7; u++) xt[u] = lim + u < n ? x[lim + u] : (T)0;
+  }
   if (cls < 0 || cls >= a.n_classes) {   // never scored by the reference either
     Best<T> none{Rn<T>::inf(), 0x7fffffff, -1};
     write_result(a, row, none, lane, 32);
@@ -143,25 +164,63 @@ __global__ void __launch_bounds__(256) rerank_list_kernel(const RerankArgs<T> a)
     return;
   }
   const int c0 = a.class_off[cls], c1 = a.class_off[cls + 1], cn = a.class_off[a.n_classes];
-  const int sub = lane & 7, grp = lane >> 3;
   const unsigned gmask = 0xFFu << (lane & 24);
-  const T* x = a.q + row * (int64_t)a.d;
   Best<T> best{Rn<T>::inf(), 0x7fffffff, -1};
   // entries are (first train row of a 32-row chunk, 32-bit mask of the rows inside the window);
   // the four 8-lane groups of the warp take entries round-robin and walk their mask bits
   for (int e0 = 0; e0 < cnt; e0 += 4) {
     const int e = e0 + grp;
     if (e < cnt) {
-      const int start = a.cand_idx[(row * (int64_t)a.cap + e) * 2];
-      unsigned cmask = (unsigned)a.cand_idx[(row * (int64_t)a.cap + e) * 2 + 1];
+      int2 ent = first;
+      if (!(spec && e0 == 0)) ent = *reinterpret_cast<const int2*>(a.cand_idx + (row * (int64_t)a.cap + e) * 2);
+      const int start = ent.x;
+      unsigned cmask = (unsigned)ent.y;
       while (cmask) {
         const int bit = __ffs(cmask) - 1;
         cmask &= cmask - 1;
         const int j = start + bit;
-        const bool in_range = a.mode == TIP_RANGE_SAME_CLASS ? (j >= c0 && j < c1) : (j >= 0 && j < cn && (j < c0 || j >= c1));
-        if (!in_range || j >= a.n) continue;
-        const T s = np_sumsq_g8<T>(x, a.t + (int64_t)j * a.d, a.d, sub, gmask);
-        consider(best, Rn<T>::sqrt(s), a.t_gid ? a.t_gid[j] : j, j);   // all 8 lanes agree
+        if (j < 0 || j >= a.n) continue;
+        // the filter only flags rows of the item's span, so the class-range test (which waits for
+        // class_off) practically never rejects: it is applied after the row has been fetched
+        const int gid = a.t_gid ? a.t_gid[j] : j;
+        const T* y = a.t + (int64_t)j * a.d;
+        T s;
+        if (SMALL) {
+          // NumPy's leaf (n <= 128): n < 8 sequential from 0; else the stride-8 accumulator of this
+          // lane, the tree ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) by xor-shuffles, then the tail
+          T yr[16], yt[7];
+#pragma unroll
+          for (int u = 0; u < 16; u++) yr[u] = 8 * u + sub < lim ? y[8 * u + sub] : (T)0;
+#pragma unroll
+          for (int u = 0; u < 7; u++) yt[u] = lim + u < n ? y[lim + u] : (T)0;
+          T r = (T)0;
+          if (lim > 0) {
+            T d0 = R::sub(xr[0], yr[0]);
+            r = R::mul(d0, d0);
+#pragma unroll
+            for (int u = 1; u < 16; u++) {
+              if (8 * u < lim) {          // uniform: lim is a multiple of 8
+                const T du = R::sub(xr[u], yr[u]);
+                r = R::add(r, R::mul(du, du));
+              }
+            }
+            r = R::add(r, __shfl_xor_sync(gmask, r, 1));
+            r = R::add(r, __shfl_xor_sync(gmask, r, 2));
+            r = R::add(r, __shfl_xor_sync(gmask, r, 4));
+          }
+#pragma unroll
+          for (int u = 0; u < 7; u++) {
+            if (lim + u < n) {
+              const T du = R::sub(xt[u], yt[u]);
+              r = R::add(r, R::mul(du, du));
+            }
+          }
+          s = r;
+        } else {
+          s = np_sumsq_g8<T>(x, y, a.d, sub, gmask);
+        }
+        const bool in_range = a.mode == TIP_RANGE_SAME_CLASS ? (j >= c0 && j < c1) : (j < cn && (j < c0 || j >= c1));
+        if (in_range) consider(best, Rn<T>::sqrt(s), gid, j);   // all 8 lanes agree
       }
     }
   }
@@ -172,7 +231,8 @@ __global__ void __launch_bounds__(256) rerank_list_kernel(const RerankArgs<T> a)
     const int op = __shfl_xor_sync(0xffffffffu, best.pos, o);
     best = merge(best, od, og, op);
   }
-  if (lane == 0 && a.stats) atomicAdd(a.stats + 1, (unsigned long long)cnt);
+  // (no global statistics here: one same-address atomic per query serialises in L2; candidate
+  // counts can be read from cand_cnt)
   write_result(a, row, best, lane, 32);
 }
 
@@ -292,7 +352,8 @@ template <typename T>
 static int launch_rerank(const RerankArgs<T>& a, cudaStream_t st) {
   // precondition (and postcondition): work[0] == 0 and work[1 + m] == 0
   const int64_t blocks = (a.m + 7) / 8;
-  rerank_list_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a);
+  if (a.d <= 128) rerank_list_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(a);
+  else rerank_list_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(a);
   TIP_LAUNCH_CHECK();
   rerank_scan_kernel<T><<<sm_count() * 8, kScanThreads, 0, st>>>(a);
   TIP_LAUNCH_CHECK();

@@ -554,15 +554,23 @@ __global__ void __launch_bounds__(256) pair_prep_kernel(const T* __restrict__ sr
 __global__ void __launch_bounds__(256) gather_rows_kernel(const unsigned char* __restrict__ src,
                                                           int64_t row_bytes, const int32_t* __restrict__ pos,
                                                           int64_t m, unsigned char* __restrict__ dst) {
+  if ((row_bytes & 15) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+    // flat index space over 16-byte pieces: every thread busy whatever the row length
+    const int64_t n16 = row_bytes >> 4;
+    const int64_t total = m * n16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* o4 = reinterpret_cast<uint4*>(dst);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+      const int64_t row = i / n16, col = i - row * n16;
+      const int32_t p = pos[row];
+      o4[i] = p < 0 ? make_uint4(0, 0, 0, 0) : s4[(int64_t)p * n16 + col];
+    }
+    return;
+  }
   for (int64_t row = blockIdx.x; row < m; row += gridDim.x) {
     const int32_t p = pos[row];
     unsigned char* o = dst + row * row_bytes;
-    if ((row_bytes & 15) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
-      const int64_t n16 = row_bytes >> 4;
-      const uint4* s = reinterpret_cast<const uint4*>(src + (int64_t)(p < 0 ? 0 : p) * row_bytes);
-      uint4* o4 = reinterpret_cast<uint4*>(o);
-      for (int64_t i = threadIdx.x; i < n16; i += 256) o4[i] = p < 0 ? make_uint4(0, 0, 0, 0) : s[i];
-    } else {
+    {
       const unsigned char* s = src + (int64_t)(p < 0 ? 0 : p) * row_bytes;
       for (int64_t i = threadIdx.x; i < row_bytes; i += 256) o[i] = p < 0 ? 0 : s[i];
     }
@@ -811,7 +819,8 @@ extern "C" int tip_gather_rows(const void* src, int64_t row_bytes, const int32_t
   TIP_REQUIRE(src && pos && dst, "null pointer");
   TIP_REQUIRE(row_bytes > 0 && m >= 0, "shape");
   if (m == 0) return TIP_OK;
-  const int grid = (int)std::min<int64_t>(m, (int64_t)sm_count() * 16);
+  const int64_t pieces = (row_bytes & 15) == 0 ? m * (row_bytes >> 4) : m * 256;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((pieces + 255) / 256, (int64_t)sm_count() * 16));
   gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)src, row_bytes, pos, m,
                                                             (unsigned char*)dst);
   TIP_LAUNCH_CHECK();
