@@ -161,7 +161,14 @@ def run_ours(args):
     os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    comm = None
+    comm = None          # N_train-sharded engine (collectives on the data path)
+    dist = None          # process group (timing barrier / max over ranks in every multi-GPU mode)
+    # How the global batch of 10000 x N test inputs is spread over N GPUs:
+    #   test  — every rank scores its own 10000 inputs against a replicated train set (30.7 MB at C2):
+    #           independent units, no data-path collective;
+    #   train — the train set is split 1/N per rank, every rank sees all 10000 x N inputs and the
+    #           per-shard minima / winner rows are all-reduced (the layout C5 needs: tools/c5_multi.py).
+    shard = args.shard if args.shard != "auto" else "test"
     if world > 1:
         import torch.distributed as dist
 
@@ -169,12 +176,17 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"      # NCCL would print its banner on stdout; the contract is ONE JSON line
 
         dist.init_process_group("nccl", device_id=dev)
-        comm = E.TrainShardComm()
+        if shard == "train":
+            comm = E.TrainShardComm()
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     cfg = dict(C2)
-    cfg["n_test"] = C2["n_test"] * world           # weak scaling: fixed (n_test x n_train / N) per GPU
+    cfg["n_test"] = C2["n_test"] * world           # weak scaling: 10000 test inputs (x 60000 / N or x 60000 train rows) per GPU
     xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(**cfg)
+    n_global = xte.shape[0]
+    if world > 1 and shard == "test":
+        sl = slice(rank * C2["n_test"], (rank + 1) * C2["n_test"])
+        xte, pte = np.ascontiguousarray(xte[sl]), np.ascontiguousarray(pte[sl])
     sa = DSA(xtr, ytr, comm=comm)
     eng = sa._engine
     n_test = xte.shape[0]
@@ -208,8 +220,8 @@ def run_ours(args):
         return sa(xte_host, pte)
 
     def barrier():
-        if comm is not None:
-            comm.dist.barrier()
+        if dist is not None:
+            dist.barrier()
         torch.cuda.synchronize()
 
     def timed(fn, steps, profile=False):
@@ -218,8 +230,8 @@ def run_ours(args):
         for _ in range(steps):
             flush.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            if comm is not None:
-                comm.dist.barrier()
+            if dist is not None:
+                dist.barrier()
             a.record()
             fn()
             b.record()
@@ -247,13 +259,13 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     tot = torch.tensor([sum(t_dev), sum(t_e2e)], dtype=torch.float64, device=dev)
-    if comm is not None:
-        comm.dist.all_reduce(tot, op=comm.dist.ReduceOp.MAX)
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     tot_dev_ms, tot_e2e_ms = [float(v) for v in tot.cpu()]
 
     if rank == 0:
-        value = n_test * args.steps / (tot_dev_ms * 1e-3)
-        e2e = n_test * args.steps / (tot_e2e_ms * 1e-3)
+        value = n_global * args.steps / (tot_dev_ms * 1e-3)
+        e2e = n_global * args.steps / (tot_e2e_ms * 1e-3)
         tflops_peak, hbm_peak, peak_src = _peaks()
         # dominant kernel: the stage-2 tcgen05 filter launch (other-class columns)
         roof = None
@@ -276,15 +288,20 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": "inputs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": tot_dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"C2: DSA {n_test} test x 60000 train x 128-d float32, 10 classes (seed 2)",
-                           "parallelism": f"N_train sharded over {world} GPU(s), test batch 10000 x {world}",
+                "config": {"workload": f"C2: DSA {n_global} test x 60000 train x 128-d float32, 10 classes (seed 2)",
+                           "parallelism": (f"N_train sharded over {world} GPU(s), every rank scores all 10000 x {world} "
+                                           "inputs; all-reduce of per-shard minima and winner rows" if comm is not None else
+                                           f"N_test sharded over {world} GPU(s): 10000 inputs per GPU, train set "
+                                           "replicated (30.7 MB), no data-path collective" if world > 1 else
+                                           "1 GPU"),
                            "filter": "bf16 tcgen05 candidate filter + exact fp32 re-rank (bit-identical to NumPy)",
                            "l2": "flushed between steps (256 MiB write)", "timing": "per-step CUDA events, summed",
                            "launch": ("CUDA-graph replay of the search" if comm is None else
                                       "per-stage CUDA graphs + eager NCCL all-reduces") if plan is not None else "eager launches"},
                 "e2e": {"value": e2e, "unit": "inputs/s", "ms_per_step": tot_e2e_ms / args.steps,
-                        "h2d_bytes_per_step": int(xte.nbytes + pte.shape[0] * 4),
-                        "d2h_bytes_per_step": int(4 * n_test * 8)},   # dist_a, dist_b, winner index, dsa as float64
+                        "h2d_bytes_per_step": int((xte.nbytes + pte.shape[0] * 4) * (world if comm is None else 1)),
+                        # dist_a, dist_b, winner index, dsa as float64, summed over the ranks
+                        "d2h_bytes_per_step": int(4 * n_test * 8 * (world if comm is None else 1))},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(xtr, ytr, xte, pte)
@@ -292,8 +309,8 @@ def run_ours(args):
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
-    if comm is not None:
-        comm.dist.destroy_process_group()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -467,6 +484,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "test", "train"],
+                    help="multi-GPU layout of C2: test = N_test sharded, train replicated (default: the train set is "
+                         "30.7 MB); train = N_train sharded with all-reduces of minima / winner rows (what C5 needs)")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"],
                     help="c2 (default) = the configuration the headline metric is quoted on; c1/c3/c4 = the other "
                          "single-GPU BASELINE.json configurations, same JSON shape")
