@@ -378,6 +378,9 @@ class DSA(SA):
         if fused:
             # steady state: upload the permutation, replay, one D2H copy into pinned memory
             plan = E.dsa_plan(eng, int(order.size), q_off, x_all.dtype, self.use_filter, None, n_total=n_total)
+            if plan.x_in.data_ptr() != x_all.data_ptr():
+                # the engine recycled its landing buffer since this plan was captured (many batch sizes)
+                plan.x_in.copy_(x_all)
             np.copyto(plan.idx_host.numpy(), order, casting="unsafe")      # pinned staging: async H2D
             plan.idx.copy_(plan.idx_host, non_blocking=True)
             plan.graph.replay()

@@ -398,6 +398,7 @@ class NnEngine:
         self._plans = {}
         self._work = {}
         self._inputs = {}
+        self._capture_refs = None     # while a plan is being captured: engine-owned tensors its graph reads
         self.sched_counter = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.last_cand_cnt_by_mode = {}
         if self.n > 0:
@@ -544,6 +545,12 @@ class NnEngine:
                     name = "nn_filter_same_class" if mode == _lib.RANGE_SAME_CLASS else "nn_filter_other_classes"
                     PROFILE.append((name, flops, ev[0], ev[1]))
         work = self.work_buffer(m, q.dtype)
+        if self._capture_refs is not None:
+            # cached tensors whose addresses get baked into the graph: the plan keeps them alive even
+            # if the engine's caches evict them later
+            self._capture_refs.extend(t for t in (work, self.sched_counter, self.t_pack, self.t, self.t_gid,
+                                                  self.class_off_dev, self.center,
+                                                  items_dev if (use_filter and self.n > 0) else None) if t is not None)
         nq = [_p(t) for t in next_query] if next_query is not None else [None] * 5
         _lib.check(lib.tip_nn_rerank(_p(q), _p(self.t), tip_dtype(q.dtype), m, self.n, self.d, _p(cand_idx),
                                      _p(cand_cnt), self.cap, _p(q_class), _p(self.class_off_dev), self.num_classes,
@@ -635,10 +642,12 @@ class DsaPlan:
         gc.collect()
         was_enabled = gc.isenabled()
         gc.disable()
+        engine._capture_refs = []
         try:
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.dist_a, self.dist_b, self.gid = body()
         finally:
+            self._keep_alive, engine._capture_refs = engine._capture_refs, None
             if was_enabled:
                 gc.enable()
 
@@ -672,10 +681,12 @@ class StagePlan:
         gc.collect()
         was_enabled = gc.isenabled()
         gc.disable()
+        engine._capture_refs = []
         try:
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.dist, _, self.gid, self.rows = engine.search(self.q, q_class, q_off, mode, use_filter, want_rows)
         finally:
+            self._keep_alive, engine._capture_refs = engine._capture_refs, None
             if was_enabled:
                 gc.enable()
 
