@@ -56,16 +56,21 @@ class DeepGini(_Base):
         from .. import _lib
         from .. import engine as E
 
-        p = np.asarray(nn_outputs)
+        if isinstance(nn_outputs, torch.Tensor) and nn_outputs.is_cuda:     # softmax outputs already in HBM
+            p = nn_outputs if nn_outputs.dtype in (torch.float32, torch.float64) else nn_outputs.to(torch.float32)
+            p_np_dtype = E.NP_DTYPE[p.dtype]
+        else:
+            p = np.asarray(nn_outputs)
+            if p.dtype not in (np.float32, np.float64):
+                p = p.astype(np.float64)
+            p_np_dtype = p.dtype
         assert p.ndim == 2, "nn_outputs must be (samples, classes)"
-        if p.dtype not in (np.float32, np.float64):
-            p = p.astype(np.float64)
         dev = E.require_cuda()
         lib = _lib.load()
         n, c = p.shape
         p_dev = E.to_device(p, dev)
         pred = torch.empty(n, dtype=torch.int32, device=dev)
         gini = torch.empty(n, dtype=p_dev.dtype, device=dev)
-        _lib.check(lib.tip_deepgini(E._p(p_dev), E.tip_dtype(p.dtype), n, c, E._p(pred), E._p(gini), E._stream()),
+        _lib.check(lib.tip_deepgini(E._p(p_dev), E.tip_dtype(p_np_dtype), n, c, E._p(pred), E._p(gini), E._stream()),
                    "tip_deepgini")
         return pred.cpu().numpy().astype(np.int64), gini.cpu().numpy()

@@ -76,14 +76,20 @@ class KMNC(CoverageMethod):
         lo = self._lo
         return [lo + self._jumps * i for i in range(self.sections + 1)]
 
-    def buckets(self, activations) -> Tuple[np.ndarray, np.ndarray]:
-        """(scores int32 [N], bucket ids [N, D] int16/int32; -1 = no section covered)."""
+    def buckets(self, activations, device_out: bool = False):
+        """(scores int32 [N], bucket ids [N, D] int16/int32; -1 = no section covered).
+        Activations may be NumPy arrays or device-resident torch tensors (one or a list);
+        device_out=True returns the two results as CUDA tensors (no D2H of the N x D bucket ids)."""
         import torch
 
         from .. import _lib
         from .. import engine as E
 
-        if isinstance(activations, np.ndarray):
+        dev_act = E.device_matrix(activations)
+        if dev_act is not None:
+            act = dev_act if dev_act.dtype in (torch.float32, torch.float64) else dev_act.to(torch.float32)
+            act = act.contiguous()
+        elif isinstance(activations, np.ndarray):
             act = activations.reshape((activations.shape[0], -1))
         elif len(activations) == 1:          # one layer: no concatenation copy (keeps a pinned buffer pinned)
             act = np.reshape(activations[0], (activations[0].shape[0], -1))
@@ -92,10 +98,11 @@ class KMNC(CoverageMethod):
         stat_dt = self._jumps.dtype
         if stat_dt not in (np.float32, np.float64):
             raise TypeError(f"KMNC statistics must be float32/float64 after NumPy promotion, got {stat_dt}")
-        if act.dtype not in (np.float32, np.float64):
+        if dev_act is None and act.dtype not in (np.float32, np.float64):
             act = act.astype(np.result_type(act.dtype, stat_dt))
             if act.dtype not in (np.float32, np.float64):
                 raise TypeError(f"unsupported activation dtype {act.dtype}")
+        act_np_dtype = E.NP_DTYPE[act.dtype] if dev_act is not None else act.dtype
         dev = E.require_cuda()
         lib = _lib.load()
         n, d = act.shape
@@ -107,9 +114,11 @@ class KMNC(CoverageMethod):
         small = self.sections <= np.iinfo(np.int16).max
         bucket = torch.empty((n, d), dtype=torch.int16 if small else torch.int32, device=dev)
         score = torch.empty(n, dtype=torch.int32, device=dev)
-        _lib.check(lib.tip_kmnc(E._p(a_dev), E.tip_dtype(act.dtype), n, d, E._p(lo_dev), E._p(jump_dev),
+        _lib.check(lib.tip_kmnc(E._p(a_dev), E.tip_dtype(act_np_dtype), n, d, E._p(lo_dev), E._p(jump_dev),
                                 E.tip_dtype(stat_dt), self.sections, E._p(bucket),
                                 _lib.TIP_I16 if small else _lib.TIP_I32, E._p(score), E._stream()), "tip_kmnc")
+        if device_out:
+            return score, bucket
         # D2H into cached pinned buffers (the bucket ids are the bulk of the traffic of this call)
         key = (n, d, bucket.dtype)
         if getattr(self, "_host_key", None) != key:

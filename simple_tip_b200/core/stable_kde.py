@@ -131,7 +131,10 @@ class StableGaussianKDE:
         from .. import engine as E
 
         eng = self._engine
-        if rows.dtype not in (np.float32, np.float64):
+        if isinstance(rows, torch.Tensor):            # device-resident traces
+            if rows.dtype not in (torch.float32, torch.float64):
+                rows = rows.to(torch.float32)
+        elif rows.dtype not in (np.float32, np.float64):
             rows = rows.astype(np.float64)
         m = rows.shape[0]
         if m == 0:

@@ -46,7 +46,16 @@ def _subsample_arrays(subsampling: Union[int, float], arrays: Tuple[np.ndarray, 
             "subsampling must be a float between 0 and 1 (share of training data),"
             "or a positive int declaring the number of samples")
     picked = np.random.RandomState(seed).choice(np.arange(n), k, replace=False)
-    return tuple(a[picked] for a in arrays)
+    return tuple(_take_rows(a, picked) for a in arrays)
+
+
+def _take_rows(a, rows: np.ndarray):
+    """a[rows] for NumPy arrays and for device-resident traces (torch tensors)."""
+    if isinstance(a, np.ndarray):
+        return a[rows]
+    import torch
+
+    return a.index_select(0, torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(a.device))
 
 
 def _subsample_array(subsampling, array: np.ndarray, seed: int) -> np.ndarray:
@@ -283,7 +292,10 @@ class LSA(SA):
         return tr_activations
 
     def __call__(self, activations, predictions=None, num_threads: int = 0) -> np.ndarray:
-        activations = _flatten_layers(activations)
+        from .. import engine as E
+
+        dev = E.device_matrix(activations)            # traces already in HBM stay there
+        activations = dev if dev is not None else _flatten_layers(activations)
         if self.kde is None:
             return np.zeros(shape=(activations.shape[0],))
         # column removal happens on the GPU (the kde knows which source columns it was fitted on)
@@ -306,8 +318,12 @@ class DSA(SA):
     def __init__(self, activations: Activations, predictions: Predictions, badge_size: int = 10,
                  subsampling: Union[int, float] = 1.0, subsampling_seed: int = 0, *, comm=None):
         super().__init__()
-        self.train_activations: np.ndarray = _flatten_layers(activations)
-        self.train_predictions: np.ndarray = _class_predictions(predictions)
+        from .. import engine as E
+
+        # traces may already live in HBM (torch CUDA tensors, e.g. from a forward hook): they stay there
+        dev_train = E.device_matrix(activations)
+        self.train_activations = dev_train if dev_train is not None else _flatten_layers(activations)
+        self.train_predictions: np.ndarray = _class_predictions(E.host_array(predictions))
         self.train_activations, self.train_predictions = _subsample_arrays(
             subsampling, (self.train_activations, self.train_predictions), subsampling_seed)
         self.num_classes = np.max(self.train_predictions) + 1
@@ -326,14 +342,17 @@ class DSA(SA):
         from .. import engine as E
 
         train = self.train_activations
-        if train.dtype not in (np.float32, np.float64):
-            train = train.astype(np.result_type(train.dtype, np.float32))
-        self._compute_dtype = train.dtype
+        if isinstance(train, np.ndarray):
+            if train.dtype not in (np.float32, np.float64):
+                train = train.astype(np.result_type(train.dtype, np.float32))
+            self._compute_dtype = train.dtype
+        else:       # device tensor: float64 stays, everything else is scored in float32
+            self._compute_dtype = np.dtype(np.float64) if str(train.dtype) == "torch.float64" else np.dtype(np.float32)
         labels = self.train_predictions
         gids = np.arange(train.shape[0])
         if self._comm is not None and self._comm.world > 1:
             keep = E.shard_rows(labels, int(self.num_classes), self._comm.rank, self._comm.world)
-            train, labels, gids = train[keep], labels[keep], gids[keep]
+            train, labels, gids = _take_rows(train, keep), labels[keep], gids[keep]
         self._engine = E.NnEngine.from_host(train, labels, int(self.num_classes), gids)
 
     def __call__(self, activations: Activations, predictions: Predictions, num_threads: int = None) -> np.ndarray:
@@ -341,13 +360,21 @@ class DSA(SA):
 
         from .. import engine as E
 
-        target_pred = _class_predictions(predictions)
-        target_ats = _flatten_layers(activations)
-        if target_ats.dtype != self._compute_dtype:
-            target_ats = target_ats.astype(np.result_type(target_ats.dtype, self._compute_dtype))
+        target_pred = _class_predictions(E.host_array(predictions))
+        torch_dtype = torch.float64 if self._compute_dtype == np.float64 else torch.float32
+        dev_ats = E.device_matrix(activations)        # traces already in HBM: no host round trip
+        if dev_ats is not None:
+            if dev_ats.dtype == torch.float64 and torch_dtype != torch.float64:
+                raise TypeError(f"test traces need the dtype of the training traces ({self._compute_dtype}), "
+                                "got float64")
+            target_ats = dev_ats.to(torch_dtype)
+        else:
+            target_ats = _flatten_layers(activations)
             if target_ats.dtype != self._compute_dtype:
-                raise TypeError("test traces need the dtype of the training traces "
-                                f"({self._compute_dtype}), got {target_ats.dtype}")
+                target_ats = target_ats.astype(np.result_type(target_ats.dtype, self._compute_dtype))
+                if target_ats.dtype != self._compute_dtype:
+                    raise TypeError("test traces need the dtype of the training traces "
+                                    f"({self._compute_dtype}), got {target_ats.dtype}")
         eng = self._engine
         dev = eng.dev
         n_total = target_pred.shape[0]
@@ -358,8 +385,9 @@ class DSA(SA):
         x_all = None
         if n_total:
             if fused:
-                x_all = eng.input_buffer(n_total, torch.float64 if target_ats.dtype == np.float64 else torch.float32)
-                x_all.copy_(torch.from_numpy(np.ascontiguousarray(target_ats)), non_blocking=True)
+                x_all = eng.input_buffer(n_total, torch_dtype)
+                x_all.copy_(target_ats if dev_ats is not None else torch.from_numpy(np.ascontiguousarray(target_ats)),
+                            non_blocking=True)
             else:
                 x_all = E.to_device(target_ats, dev)
         # class-grouped order; rows labelled >= num_classes are never scored by the reference

@@ -63,9 +63,36 @@ def tip_dtype(dt) -> int:
     raise TypeError(f"activation traces must be float32 or float64, got {dt}")
 
 
-def to_device(a: np.ndarray, dev: torch.device) -> torch.Tensor:
-    """Host -> HBM.  Pinned sources (e.g. views of torch pinned tensors) copy asynchronously."""
+def to_device(a, dev: torch.device) -> torch.Tensor:
+    """Host -> HBM.  Pinned sources (e.g. views of torch pinned tensors) copy asynchronously.
+    Traces that already live on the GPU (torch CUDA tensors) are used in place."""
+    if isinstance(a, torch.Tensor):
+        return a.to(dev, non_blocking=True).contiguous()
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+
+
+def device_matrix(layers) -> Optional[torch.Tensor]:
+    """Activation traces handed over as device tensors (one [N, ...] tensor or a list of them, the
+    form a forward hook produces): the flattened [N, D] matrix on the GPU, else None.  Mirrors
+    `_flatten_layers` (surprise.py:62-66) without leaving HBM."""
+    if isinstance(layers, torch.Tensor):
+        return layers.reshape(layers.shape[0], -1) if layers.is_cuda else None
+    if isinstance(layers, (list, tuple)) and len(layers) > 0 and all(isinstance(l, torch.Tensor) and l.is_cuda
+                                                                     for l in layers):
+        flat = [l.reshape(l.shape[0], -1) for l in layers]
+        return flat[0] if len(flat) == 1 else torch.cat(flat, dim=1)
+    return None
+
+
+def host_array(x) -> np.ndarray:
+    """Labels / predictions as a NumPy array whatever they came as (device tensors are copied)."""
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return x
+
+
+NP_DTYPE = {torch.float32: np.dtype(np.float32), torch.float64: np.dtype(np.float64),
+            torch.float16: np.dtype(np.float16), torch.bfloat16: None}
 
 
 # ------------------------------------------------------------------------------------------
@@ -422,6 +449,8 @@ class NnEngine:
         t = to_device(train, dev)
         idx = torch.from_numpy(order).to(dev)
         gid = idx if gids is None else torch.from_numpy(np.asarray(gids)[order]).to(dev)
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.to(torch.float32)          # device-resident bf16 / fp16 traces: exact widening
         return cls(t.index_select(0, idx), off, gid, cap)
 
     def work_buffer(self, m: int, dtype: torch.dtype) -> torch.Tensor:

@@ -402,3 +402,44 @@ def test_dsa_config5_shape_streaming_kernel():
     sa.use_filter = False
     assert np.array_equal(sa(xte, pte), got)
     assert np.array_equal(sa.last_winner_index, win)
+
+
+# ------------------------------------------------------------------------------------------
+# device-resident traces: torch CUDA tensors in, same bits out (no host round trip of the traces)
+# ------------------------------------------------------------------------------------------
+def test_device_resident_traces_give_the_same_bits():
+    torch = _torch()
+    from src.core.deepgini import DeepGini
+    from src.core.neuron_coverage import KMNC
+    from src.core.surprise import DSA, LSA
+
+    dev = torch.device("cuda", 0)
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(6000, 700, 128, 6, seed=11)
+    want = c_oracle.dsa(xtr, ytr, xte, pte)
+    # fit and score from HBM; layers arrive as a list of [N, ...] tensors like a forward hook yields them
+    tr_layers = [torch.from_numpy(xtr[:, :48]).to(dev).reshape(-1, 4, 12), torch.from_numpy(xtr[:, 48:]).to(dev)]
+    te_layers = [torch.from_numpy(xte[:, :48]).to(dev).reshape(-1, 4, 12), torch.from_numpy(xte[:, 48:]).to(dev)]
+    sa = DSA(tr_layers, torch.from_numpy(ytr).to(dev), subsampling=1.0)
+    got = sa(te_layers, torch.from_numpy(pte).to(dev))
+    assert np.array_equal(got, want["dsa"]) and np.array_equal(sa.last_winner_index, want["idx_a"])
+    # seeded sub-sampling picks the same rows on the device as on the host
+    a = DSA(xtr, ytr, subsampling=0.3, subsampling_seed=5)(xte, pte)
+    b = DSA(torch.from_numpy(xtr).to(dev), ytr, subsampling=0.3, subsampling_seed=5)(torch.from_numpy(xte).to(dev), pte)
+    assert np.array_equal(a, b)
+
+    xs, _, xt, _, _ = np_oracle.synth_clusters(2000, 300, 40, 3, seed=12)
+    lsa = LSA(xs)
+    assert np.array_equal(lsa(xt), lsa(torch.from_numpy(xt).to(dev)))
+
+    act, mins, maxs = np_oracle.synth_relu(300, 1024, seed=13)
+    km = KMNC([mins], [maxs], 50)
+    score, bucket = km.buckets([act])
+    score_d, bucket_d = km.buckets([torch.from_numpy(act).to(dev)], device_out=True)
+    assert score_d.is_cuda and np.array_equal(score_d.cpu().numpy(), score) and np.array_equal(bucket_d.cpu().numpy(), bucket)
+
+    rng = np.random.default_rng(14)
+    logits = rng.normal(size=(500, 10)).astype(np.float32) * 3
+    p = np.exp(logits) / np.exp(logits).sum(1, keepdims=True)
+    pred, gini = DeepGini.calculate(p)
+    pred_d, gini_d = DeepGini.calculate(torch.from_numpy(p).to(dev))
+    assert np.array_equal(pred, pred_d) and np.array_equal(gini, gini_d)
