@@ -13,6 +13,7 @@
  * Which reference arithmetic each entry point replaces (paths relative to the reference):
  *   tip_deepgini        src/core/deepgini.py:31-35     argmax + 1 - sum(p*p)
  *   tip_kmnc            src/core/neuron_coverage.py:82-94 (+ sum_score :8-22)
+ *   tip_cam_buckets     src/core/prioritizers.py:16-45 (greedy loop of cam) on compact KMNC profiles
  *   tip_pair_prep       (new) operand packing for the tensor-core pass
  *   tip_nn_filter       src/core/surprise.py:638-647   the B x M x D difference/norm/min, as a
  *                       tcgen05 pass that yields a per-query candidate set provably containing
@@ -93,6 +94,24 @@ int tip_deepgini(const void* probs, int dtype, int64_t n, int64_t c, int32_t* pr
 int tip_kmnc(const void* act, int act_dtype, int64_t n, int64_t d, const void* mins,
              const void* jumps, int stat_dtype, int32_t sections, void* bucket, int bucket_dtype,
              int32_t* score, void* stream);
+
+/* ---- Coverage-Additional Method over compact coverage profiles (prioritizers.py:16-59) ----
+ * bucket: n x d section ids as tip_kmnc writes them (TIP_I16 / TIP_I32, -1 = none): the one-hot-per-
+ * neuron profile of neuron_coverage.py:82-94 without its dense n x d x sections form.  Runs up to
+ * `rounds` rounds of the reference's greedy loop — pick = first index of the largest gain (np.argmax),
+ * mark the cells the pick newly covers, subtract from every sample the number of those cells it shares
+ * — and stops for good when the best gain is 0.  Caller-owned state, all on the device:
+ *   gain[n]      in: number of valid cells per sample (= KMNC score); updated in place
+ *   covered      ceil(d*sections/32) words, zero before the first call
+ *   newlist      2*d int32 scratch
+ *   order[n]     out: the picks in order; state[0] = how many (zero before the first call)
+ *   state[4]     {picks, done flag, scratch, scratch}, zero before the first call; call again with the
+ *                same buffers while state[1] == 0 && state[0] < n.
+ * The tail of the reference's generator (not-yet-picked samples by np.argsort(-scores), :47-59) is host
+ * NumPy, so ties fall exactly as in the reference. */
+int tip_cam_buckets(const void* bucket, int bucket_dtype, int64_t n, int64_t d, int32_t sections,
+                    int32_t* gain, uint32_t* covered, int32_t* newlist, int32_t* order, int32_t* state,
+                    int32_t rounds, void* stream);
 
 /* ---- operand packing for the tensor-core pass ----------------------------------------
  * Packed row (bf16), D16 = round_up(d,16), one 16-wide tail block:

@@ -204,12 +204,33 @@ def prioritizer_cases(ref):
     print("prioritizers ok")
 
 
+def cam_kmnc_cases(ref):
+    """CAM over KMNC profiles (handler_coverage.py:122-124: `cam(scores, profiles)` with the dense
+    N x D x k profile of neuron_coverage.py:82-94), stored with the COMPACT bucket ids so that a CAM
+    that never materialises the dense profile can be checked against the reference's order."""
+    out = {}
+    for i, (n, d, k, seed) in enumerate([(40, 24, 5, 61), (120, 64, 16, 62), (300, 96, 50, 63), (64, 32, 2, 64)]):
+        act, mins, maxs = np_oracle.synth_relu(n, d, seed=seed)
+        km = ref.neuron_coverage.KMNC([mins], [maxs], k)
+        score, prof = km([act])
+        order = np.array(list(ref.prioritizers.cam(score, prof.copy())), dtype=np.int64)
+        out[f"camk{i}.bucket"] = np.where(prof.any(axis=2), prof.argmax(axis=2), -1).astype(np.int32)
+        out[f"camk{i}.score"], out[f"camk{i}.sections"], out[f"camk{i}.order"] = score, np.array(k), order
+        assert int(prof.sum(axis=2).max()) <= 1
+    np.savez_compressed(os.path.join(OUT, "cam_kmnc_reference.npz"), **out)
+    print("cam over kmnc ok")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = ref_harness.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "cam_kmnc":      # add this file without touching the others
+        cam_kmnc_cases(ref)
+        sys.exit(0)
     dsa_cases(ref)
     lsa_cases(ref)
     coverage_cases(ref)
     gini_apfd_cases(ref)
     prioritizer_cases(ref)
+    cam_kmnc_cases(ref)
     print("sizes:", {f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))})

@@ -336,6 +336,47 @@ def ctm_order(scores: np.ndarray) -> np.ndarray:
     return np.argsort(-scores)
 
 
+def cam_from_buckets_oracle(scores: np.ndarray, bucket: np.ndarray, sections: int) -> np.ndarray:
+    """Coverage-additional order (prioritizers.py:16-59) for a one-hot-per-neuron profile given by
+    its compact form bucket[n, d] in {-1, 0..sections-1} (KMNC, neuron_coverage.py:82-94), without
+    building the N x D x k array: `num_coverable` (:22) starts as the number of valid cells of a
+    sample; a pick (`np.argmax`, first index on ties, :26) newly covers the cells (d, bucket[pick, d])
+    not covered yet; every sample loses one per newly covered cell it shares (:38-39); the loop ends
+    when the best gain is 0 (:30-31) or everything coverable is covered (:44-45); the rest follows
+    by `np.argsort(-scores)` over the not-yet-yielded samples (:47-59)."""
+    scores = np.asarray(scores).copy()
+    bucket = np.asarray(bucket)
+    n, d = bucket.shape
+    covered = np.zeros((d, sections), dtype=bool)
+    gain = (bucket >= 0).sum(axis=1).astype(np.int64)
+    remaining = d * sections
+    taken = np.zeros(n, dtype=bool)
+    order = []
+    cols = np.arange(d)
+    while True:
+        pick = int(np.argmax(gain))
+        fresh = int(gain[pick])
+        if fresh == 0:
+            break
+        order.append(pick)
+        taken[pick] = True
+        cell = bucket[pick]
+        new = (cell >= 0) & ~covered[cols, np.maximum(cell, 0)]
+        remaining -= fresh
+        nd = cols[new]
+        gain = gain - (bucket[:, nd] == cell[nd][None, :]).sum(axis=1)
+        covered[nd, cell[nd]] = True
+        if remaining == 0:
+            break
+    floor = np.min(scores) - 1
+    scores[taken] = floor - 1
+    for i in np.argsort(-scores):
+        if scores[i] < floor:
+            break
+        order.append(int(i))
+    return np.asarray(order, dtype=np.int64)
+
+
 # --------------------------------------------------------------------------------------
 # Seeded synthetic traces for the BASELINE.json configurations (SURVEY.md 8d)
 # --------------------------------------------------------------------------------------

@@ -443,3 +443,35 @@ def test_device_resident_traces_give_the_same_bits():
     pred, gini = DeepGini.calculate(p)
     pred_d, gini_d = DeepGini.calculate(torch.from_numpy(p).to(dev))
     assert np.array_equal(pred, pred_d) and np.array_equal(gini, gini_d)
+
+
+# ------------------------------------------------------------------------------------------
+# CAM over compact KMNC profiles: same order as the reference's generator
+# ------------------------------------------------------------------------------------------
+def test_cam_from_buckets_matches_reference_order(golden):
+    torch = _torch()
+    from src.core.neuron_coverage import KMNC
+    from src.core.prioritizers import cam_from_buckets
+
+    g = golden("cam_kmnc_reference.npz")
+    for i in range(4):
+        bucket, score, k = g[f"camk{i}.bucket"], g[f"camk{i}.score"], int(g[f"camk{i}.sections"])
+        got = np.array(list(cam_from_buckets(score, bucket, k)), dtype=np.int64)
+        assert np.array_equal(got, g[f"camk{i}.order"]), i                 # order of the unmodified reference
+        got16 = np.array(list(cam_from_buckets(score, bucket.astype(np.int16), k)), dtype=np.int64)
+        assert np.array_equal(got16, got), i
+    # larger case, end to end on the device: KMNC bucket ids never leave HBM
+    act, mins, maxs = np_oracle.synth_relu(1500, 512, seed=21)
+    km = KMNC([mins], [maxs], 100)
+    score_d, bucket_d = km.buckets([torch.from_numpy(act).to("cuda")], device_out=True)
+    score = score_d.cpu().numpy()
+    got = np.array(list(cam_from_buckets(score, bucket_d, 100)), dtype=np.int64)
+    want = np_oracle.cam_from_buckets_oracle(score, bucket_d.cpu().numpy(), 100)
+    assert np.array_equal(got, want)
+    assert sorted(got.tolist()) == list(range(1500))
+    # degenerate inputs: nothing coverable -> pure score order; a single sample
+    none = np.full((7, 5), -1, dtype=np.int32)
+    s = np.array([3, 1, 4, 1, 5, 9, 2])
+    assert np.array_equal(np.array(list(cam_from_buckets(s, none, 3))), np_oracle.cam_from_buckets_oracle(s, none, 3))
+    one = np.array([[0, 2, -1]], dtype=np.int32)
+    assert list(cam_from_buckets(np.array([2]), one, 3)) == [0]

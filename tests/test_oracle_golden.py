@@ -157,3 +157,24 @@ def test_deepgini_known_answer_from_reference_tests():
 def test_apfd_known_answers_from_reference_tests(order, fault, expected):
     """tests/test_apfd.py:7-18."""
     assert np_oracle.apfd_oracle(np.array(fault), order) == expected
+
+
+def test_compact_cam_oracle_matches_reference_cam_on_kmnc_profiles(golden):
+    """prioritizers.py:16-59 run by the reference on dense KMNC profiles vs the compact restatement
+    that only sees the bucket ids (what the GPU path, tip_cam_buckets, is checked against)."""
+    g = golden("cam_kmnc_reference.npz")
+    for i in range(4):
+        bucket, score, k = g[f"camk{i}.bucket"], g[f"camk{i}.score"], int(g[f"camk{i}.sections"])
+        want = g[f"camk{i}.order"]
+        got = np_oracle.cam_from_buckets_oracle(score, bucket, k)
+        assert np.array_equal(got, want), i
+        assert sorted(got.tolist()) == list(range(bucket.shape[0]))      # a permutation of the samples
+    # and the dense host mirror agrees with both on a fresh case
+    from src.core.prioritizers import cam
+
+    rng = np.random.default_rng(5)
+    bucket = rng.integers(-1, 6, size=(50, 30)).astype(np.int32)
+    prof = np.zeros((50, 30, 6), dtype=bool)
+    np.put_along_axis(prof, np.maximum(bucket, 0)[..., None], (bucket >= 0)[..., None], axis=2)
+    score = prof.sum(axis=(1, 2))
+    assert np.array_equal(np.array(list(cam(score, prof.copy()))), np_oracle.cam_from_buckets_oracle(score, bucket, 6))
