@@ -266,3 +266,53 @@ def test_train_shard_protocol_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(msg == "ok" for _, msg in results), results
+
+
+def test_balanced_items_random_histograms_property():
+    """Property check of the resident kernel's planner over random class histograms: whatever the
+    shapes, every (query, train row) pair a stage needs is covered exactly once, items respect the
+    tile height, pool items are short and real, and padding never carries work."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(0, 700), min_size=1, max_size=6), st.lists(st.integers(0, 900), min_size=1, max_size=6),
+           st.sampled_from([1, 7, 148]), st.sampled_from([64, 192, 256]), st.booleans(), st.sampled_from([0.0, 0.2, 0.5]))
+    def check(q_counts, t_counts, n_cta, col_tile, mixed, pool_frac):
+        classes = min(len(q_counts), len(t_counts))
+        q_off = np.concatenate(([0], np.cumsum(q_counts[:classes])))
+        t_off = np.concatenate(([0], np.cumsum(t_counts[:classes])))
+        m, n = int(q_off[-1]), int(t_off[-1])
+        q_class = np.repeat(np.arange(classes), np.diff(q_off))
+        for mode in ("same", "other"):
+            if mixed and mode == "same":
+                continue
+            ranges = [[(t_off[c], t_off[c + 1])] if mode == "same" else [(0, t_off[c]), (t_off[c + 1], t_off[-1])]
+                      for c in range(classes)]
+            tiles = E.query_tiles(q_off, ranges, t_off, 256, mixed)
+            items, n_static = E.build_balanced_items(tiles, col_tile, n_cta, pool_frac=pool_frac, pool_tiles=3)
+            assert items.dtype == np.int32 and items.shape[1] == 6 and 0 <= n_static <= items.shape[0]
+            cover = np.zeros((m, n), dtype=np.int32)
+            for q0, rows, c0, c1, _, flag in items:
+                if c1 <= c0:
+                    assert (q0, rows, c0, c1, flag) == (0, 0, 0, 0, 0)       # padding entry
+                    continue
+                assert 1 <= rows <= 256 and 0 <= c0 < c1 <= n and q0 + rows <= m
+                block = np.ones((rows, c1 - c0), dtype=np.int32)
+                if flag & 1:
+                    for r in range(rows):
+                        c = q_class[q0 + r]
+                        lo, hi = max(t_off[c], c0), min(t_off[c + 1], c1)
+                        if hi > lo:
+                            block[r, lo - c0:hi - c0] = 0
+                cover[q0:q0 + rows, c0:c1] += block
+            want = np.zeros((m, n), dtype=np.int32)
+            for c in range(classes):
+                for lo, hi in ranges[c]:
+                    want[q_off[c]:q_off[c + 1], lo:hi] = 1
+            assert np.array_equal(cover, want)
+            pool = items[n_static:]
+            assert np.all(pool[:, 3] > pool[:, 2]) and np.all(-(-(pool[:, 3] - pool[:, 2]) // col_tile) <= 3)
+
+    check()
