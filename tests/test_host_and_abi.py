@@ -28,6 +28,19 @@ def test_c_abi_exports_every_declared_symbol():
     assert C.sizeof(_lib.WorkItem) == 24
 
 
+def test_ctypes_signatures_have_the_header_arity():
+    """Every prototype of include/b200tip.h and its ctypes binding take the same number of arguments
+    (a mismatch would corrupt the call silently)."""
+    header = open(os.path.join(ROOT, "include", "b200tip.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = dict(re.findall(r"\b(tip_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    assert set(protos) == set(_lib.symbols())
+    for name, params in protos.items():
+        params = params.strip()
+        n_header = 0 if params in ("", "void") else params.count(",") + 1
+        assert n_header == len(_lib._SIGNATURES[name][1]), (name, n_header, len(_lib._SIGNATURES[name][1]))
+
+
 def test_product_package_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "simple_tip_b200")
     for dirpath, _, files in os.walk(pkg):
