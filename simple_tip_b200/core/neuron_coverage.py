@@ -12,7 +12,6 @@ with host NumPy (next rows).
 from __future__ import annotations
 
 import abc
-import ctypes as C
 from typing import List, Tuple
 
 import numpy as np

@@ -11,10 +11,8 @@ stays host NumPy with the reference's expressions.  `fit` / `score` are additive
 from __future__ import annotations
 
 import abc
-import math
 import os
 import warnings
-from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Dict, Iterable, List, Optional, Tuple, Union
 
 import numpy as np

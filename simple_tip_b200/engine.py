@@ -20,7 +20,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch
