@@ -244,6 +244,7 @@ class LSA(SA):
                  max_features: Optional[Union[int, float]] = 300):
         super().__init__()
         activations = _flatten_layers(activations)
+        self._source_width = int(activations.shape[1])
         assert var_threshold is None or max_features is None, (
             "Both var_threshold and max_features cannot be specified at the same time."
             "We recommend using the max_features arg to dynamically keep the features"
@@ -294,6 +295,11 @@ class LSA(SA):
 
         dev = E.device_matrix(activations)            # traces already in HBM stay there
         activations = dev if dev is not None else _flatten_layers(activations)
+        if activations.ndim != 2 or int(activations.shape[1]) != self._source_width:
+            # the reference fails here too (np.delete IndexError / scipy's dimension ValueError); the
+            # kernels index with the fitted columns, so a narrower matrix must never reach them
+            raise ValueError(f"activation traces have {tuple(activations.shape)[1:]} features per sample, "
+                             f"this LSA was fitted on {self._source_width}")
         if self.kde is None:
             return np.zeros(shape=(activations.shape[0],))
         # column removal happens on the GPU (the kde knows which source columns it was fitted on)
@@ -375,6 +381,10 @@ class DSA(SA):
                                     f"({self._compute_dtype}), got {target_ats.dtype}")
         eng = self._engine
         dev = eng.dev
+        if target_ats.ndim != 2 or int(target_ats.shape[1]) != eng.d:
+            # the reference's `from_ats[:, None] - to_ats` raises the same kind of error (surprise.py:638)
+            raise ValueError(f"operands could not be broadcast together: test traces have shape "
+                             f"{tuple(target_ats.shape)}, training traces have {eng.d} features")
         n_total = target_pred.shape[0]
         sharded = self._comm is not None and self._comm.world > 1
         fused = self.use_graphs and not sharded     # one CUDA graph from landing buffer to result

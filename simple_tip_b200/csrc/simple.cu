@@ -831,6 +831,7 @@ extern "C" int tip_whiten(const void* x, int dtype, int64_t m, int64_t d_in, con
                           const double* mu, const float* w, float* out, void* stream) {
   TIP_REQUIRE(x && mu && w && out, "null pointer");
   TIP_REQUIRE(m >= 0 && d_in >= 1 && d_out >= 1 && d_out <= 65535 * 64, "shape");
+  TIP_REQUIRE(cols != nullptr || d_in >= d_out, "without a column list the input must be at least d_out wide");
   if (m == 0) return TIP_OK;
   dim3 grid((unsigned)((d_out + 63) / 64), (unsigned)((m + 63) / 64));
   TIP_REQUIRE((m + 63) / 64 <= 65535, "too many rows for one launch");
