@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TIP_VERSION 100
+#define TIP_VERSION 200
 
 typedef enum tip_status {
   TIP_OK = 0,
@@ -212,6 +212,54 @@ int tip_dsa_pack_out(const void* dist_a, const void* dist_b, int dtype, const in
 /* dst[i,:] = src[pos[i],:]  (rows of `row_bytes` bytes; pos < 0 -> zero row) */
 int tip_gather_rows(const void* src, int64_t row_bytes, const int32_t* pos, int64_t m, void* dst,
                     void* stream);
+
+/* ---- N_train sharded over the GPUs of one NVSwitch box (no counterpart in the
+ * reference — the dependency that forces the exchange is src/core/surprise.py:615-631: stage 2's
+ * queries are the GLOBAL stage-1 winners) -------------------------------------------------------
+ * A tip_comm is a set of symmetric receive buffers, one per rank (one process per GPU), opened
+ * across processes through CUDA IPC.  An exchange is: every rank pushes m 16-byte records into the
+ * slots of all peers with plain NVLink stores and raises a flag (tip_comm_push_*); the consumer
+ * kernel (tip_shard_winner_queries / tip_comm_min / tip_comm_lse) waits for all flags and reduces the
+ * `world` records per query from local memory in its prologue.  Exchanges must be issued in the same
+ * order on every rank; at most `cap_records` records per exchange.  Set-up (host side, once):
+ *   tip_comm_alloc      cudaMalloc + zero the local buffer, return its 64-byte IPC handle
+ *   (all-gather the handles with torch.distributed)
+ *   tip_comm_open       map the peers' buffers; all_handles = world x 64 bytes in rank order
+ *   tip_comm_close      unmap the peers;  tip_comm_free_local frees the local buffer. */
+#define TIP_COMM_MAX_WORLD 16
+#define TIP_COMM_HANDLE_BYTES 64
+typedef struct tip_comm tip_comm;
+int64_t tip_comm_bytes(int32_t world, int64_t cap_records);
+int tip_comm_alloc(int32_t world, int64_t cap_records, void** local_buf, void* ipc_handle);
+int tip_comm_open(int32_t rank, int32_t world, void* local_buf, const void* all_handles,
+                  int64_t cap_records, tip_comm** out);
+int tip_comm_close(tip_comm* comm);
+int tip_comm_free_local(void* local_buf);
+/* record i = (bit pattern of dist[i] (NaN = no row on this shard), gid[i] or 0): the per-shard result
+ * of tip_nn_rerank for query i; dtype TIP_F32 / TIP_F64 */
+int tip_comm_push_nn(tip_comm* comm, const void* dist, int dtype, const int32_t* gid, int64_t m,
+                     void* stream);
+/* record i = this shard's partial KDE sum (running max, sum of exp(. - max)) of tip_kde_combine */
+int tip_comm_push_lse(tip_comm* comm, const float* part_max, const float* part_sum, int64_t m,
+                      void* stream);
+/* out_dist[i] = min over the ranks of the pushed distances (NaN if no shard had a row) */
+int tip_comm_min(tip_comm* comm, int dtype, int64_t m, void* out_dist, void* stream);
+/* merged log-sum-exp partials, in rank order, identical on every rank: out_max = max_r max_r,
+ * out_sum = sum_r sum_r * exp(max_r - out_max) (double) */
+int tip_comm_lse(tip_comm* comm, int64_t m, float* out_max, double* out_sum, void* stream);
+/* Global stage-1 winners -> stage-2 queries.  comm != NULL: waits for the exchange started by the
+ * last tip_comm_push_nn and takes, per query, the lexicographic minimum of (distance, original
+ * index) over the shards; comm == NULL: gdist[m] / ggid[m] hold that minimum already (reduced by
+ * torch.distributed).  train_full: the whole (post-subsample) training set, n_full x d in the trace
+ * dtype, rows in ORIGINAL order, replicated on every rank (C5: 10.5 GB of 180).  Writes the global
+ * dist_a (NaN if the class has no training row anywhere), the winner's original index (-1), a copy
+ * of the winning rows (out_rows, m x d: the exact re-rank's queries) and the packed bf16 queries +
+ * reset filter state of the following tip_nn_filter call (see tip_nn_rerank's next_* outputs). */
+int tip_shard_winner_queries(tip_comm* comm, const void* gdist, const int32_t* ggid, int dtype,
+                             int64_t m, int64_t d, const void* train_full, int64_t n_full,
+                             const float* center, void* out_dist, int32_t* out_gid, void* out_rows,
+                             void* next_pack, float* next_sqnorm, float* next_rounderr,
+                             uint32_t* next_row_min_bits, int32_t* next_cand_cnt, void* stream);
 
 /* ---- LSA: whitening and the fused Gaussian-KDE log-sum-exp ---------------------------
  * out[m x d_out] (fp32) = (x[:, cols] - mu) . w, x: m x d_in (TIP_F32/TIP_F64), cols[d_out] the kept

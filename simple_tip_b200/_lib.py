@@ -45,6 +45,17 @@ _SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tip_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "tip_dsa_pack_out": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "tip_comm_bytes": (_i64, [_i32, _i64]),
+    "tip_comm_alloc": (C.c_int, [_i32, _i64, C.POINTER(C.c_void_p), _vp]),
+    "tip_comm_open": (C.c_int, [_i32, _i32, _vp, _vp, _i64, C.POINTER(C.c_void_p)]),
+    "tip_comm_close": (C.c_int, [_vp]),
+    "tip_comm_free_local": (C.c_int, [_vp]),
+    "tip_comm_push_nn": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _vp]),
+    "tip_comm_push_lse": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "tip_comm_min": (C.c_int, [_vp, C.c_int, _i64, _vp, _vp]),
+    "tip_comm_lse": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
+    "tip_shard_winner_queries": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _vp, _vp, _vp]),
     "tip_whiten": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "tip_kde_lse": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),
     "tip_kde_combine": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),

@@ -26,7 +26,8 @@ import numpy as np
 class StableGaussianKDE:
     MAX_INCREMENT = 1e-5
 
-    def __init__(self, dataset, bw_method=None, weights=None, source_columns: Optional[np.ndarray] = None):
+    def __init__(self, dataset, bw_method=None, weights=None, source_columns: Optional[np.ndarray] = None,
+                 comm=None):
         if bw_method is not None or weights is not None:
             raise NotImplementedError("only the reference's usage (scott bandwidth, uniform weights) is supported")
         self.dataset = np.atleast_2d(np.asarray(dataset)).astype(np.float64)     # stable_kde.py:22
@@ -37,6 +38,7 @@ class StableGaussianKDE:
         self.neff = 1.0 / np.sum(self.weights ** 2)
         self.source_columns = None if source_columns is None else np.asarray(source_columns, dtype=np.int32)
         self._engine = None
+        self._comm = comm          # N_train-sharded evaluation (engine.TrainShardComm); the fit is replicated
         self._compute_covariance()
         if not self.prepare_failed:
             self._upload()
@@ -96,7 +98,7 @@ class StableGaussianKDE:
         # squared distances are translation invariant: centre before whitening so the split-bf16
         # operands carry the spread, not the offset, of the traces
         p = (self.dataset.T - self.mean) @ self.whitening
-        self._engine = E.KdeEngine(p)
+        self._engine = E.KdeEngine(p, self._comm)
         dev = self._engine.dev
         self._w_dev = torch.from_numpy(self.whitening.astype(np.float32)).to(dev)
         self._mu_dev = torch.from_numpy(self.mean).to(dev)

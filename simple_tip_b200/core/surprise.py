@@ -241,8 +241,9 @@ class LSA(SA):
     GPU, then `-np.log(density)` (:494-495; +inf where the float64 density underflows to 0)."""
 
     def __init__(self, activations: Activations, var_threshold: Optional[float] = None,
-                 max_features: Optional[Union[int, float]] = 300):
+                 max_features: Optional[Union[int, float]] = 300, *, comm=None):
         super().__init__()
+        self._comm = comm         # additive: N_train-sharded KDE evaluation (engine.TrainShardComm)
         activations = _flatten_layers(activations)
         self._source_width = int(activations.shape[1])
         assert var_threshold is None or max_features is None, (
@@ -268,7 +269,7 @@ class LSA(SA):
         try:
             kept = np.delete(np.arange(activations.shape[1]), self.removed_neurons) \
                 if len(self.removed_neurons) > 0 else None
-            return StableGaussianKDE(cleaned.transpose(), source_columns=kept)
+            return StableGaussianKDE(cleaned.transpose(), source_columns=kept, comm=self._comm)
         except (np.linalg.LinAlgError, ValueError) as e:
             # surprise.py:456-476: only two message patterns trigger drop-a-neuron-and-retry;
             # NumPy's "Matrix is not positive definite" matches neither, so this re-raises.
@@ -335,6 +336,8 @@ class DSA(SA):
         self.badge_size = badge_size          # kept for API compatibility; tiles replace badges
         self.use_filter = os.environ.get("B200TIP_DSA_EXHAUSTIVE", "0") != "1"
         self.use_graphs = os.environ.get("B200TIP_GRAPHS", "1") != "0"   # CUDA-graph replay of the search
+        self.capture_on_first_call = os.environ.get("B200TIP_CAPTURE_FIRST", "0") == "1"
+        self._seen_shapes = set()
         self._comm = comm
         self._engine = None
         self._build_engine()
@@ -353,11 +356,21 @@ class DSA(SA):
         else:       # device tensor: float64 stays, everything else is scored in float32
             self._compute_dtype = np.dtype(np.float64) if str(train.dtype) == "torch.float64" else np.dtype(np.float32)
         labels = self.train_predictions
-        gids = np.arange(train.shape[0])
         if self._comm is not None and self._comm.world > 1:
+            # N_train sharded: every class is dealt round-robin over the ranks; the raw training set stays
+            # replicated in HBM (original row order) so that global stage-1 winners are gathered by index
+            import torch
+
+            dev = E.require_cuda()
+            full = E.to_device(train, dev)
+            if full.dtype not in (torch.float32, torch.float64):
+                full = full.to(torch.float32)
             keep = E.shard_rows(labels, int(self.num_classes), self._comm.rank, self._comm.world)
-            train, labels, gids = _take_rows(train, keep), labels[keep], gids[keep]
-        self._engine = E.NnEngine.from_host(train, labels, int(self.num_classes), gids)
+            shard = full.index_select(0, torch.from_numpy(keep).to(dev))
+            self._engine = E.NnEngine.from_host(shard, labels[keep], int(self.num_classes), keep)
+            self._engine.t_full = full.contiguous()
+        else:
+            self._engine = E.NnEngine.from_host(train, labels, int(self.num_classes), np.arange(train.shape[0]))
 
     def __call__(self, activations: Activations, predictions: Predictions, num_threads: int = None) -> np.ndarray:
         import torch
@@ -387,17 +400,13 @@ class DSA(SA):
                              f"{tuple(target_ats.shape)}, training traces have {eng.d} features")
         n_total = target_pred.shape[0]
         sharded = self._comm is not None and self._comm.world > 1
-        fused = self.use_graphs and not sharded     # one CUDA graph from landing buffer to result
         # start the (asynchronous, if the caller's buffer is pinned) upload first; the host-side
         # planning below overlaps with it
         x_all = None
         if n_total:
-            if fused:
-                x_all = eng.input_buffer(n_total, torch_dtype)
-                x_all.copy_(target_ats if dev_ats is not None else torch.from_numpy(np.ascontiguousarray(target_ats)),
-                            non_blocking=True)
-            else:
-                x_all = E.to_device(target_ats, dev)
+            x_all = eng.input_buffer(n_total, torch_dtype)
+            x_all.copy_(target_ats if dev_ats is not None else torch.from_numpy(np.ascontiguousarray(target_ats)),
+                        non_blocking=True)
         # class-grouped order; rows labelled >= num_classes are never scored by the reference
         # (its result buffer is np.empty there, surprise.py:576-580) -> NaN here.
         order, q_off = E.class_layout(target_pred, int(self.num_classes))
@@ -411,15 +420,25 @@ class DSA(SA):
             self._last_raw = np.full((3, n_total), np.nan)
             self._last_raw[2] = -1.0
             return np.full(shape=n_total, fill_value=np.nan)
+        # A batch shape (size, class histogram) seen for the first time is launched eagerly — the reference's
+        # pipeline scores most datasets exactly once (handler_surprise.py:84-99) and a capture costs ~3 eager
+        # calls; its CUDA-graph plan is captured on the second sighting and replayed from then on.
+        shape_key = (int(order.size), n_total, q_off.tobytes(), str(torch_dtype))
+        fused = self.use_graphs and (shape_key in self._seen_shapes or self.capture_on_first_call)
+        if self.use_graphs and not fused:
+            if len(self._seen_shapes) > 64:
+                self._seen_shapes.clear()
+            self._seen_shapes.add(shape_key)
         if fused:
             # steady state: upload the permutation, replay, one D2H copy into pinned memory
-            plan = E.dsa_plan(eng, int(order.size), q_off, x_all.dtype, self.use_filter, None, n_total=n_total)
+            plan = E.dsa_plan(eng, int(order.size), q_off, x_all.dtype, self.use_filter,
+                              self._comm if sharded else None, n_total=n_total)
             if plan.x_in.data_ptr() != x_all.data_ptr():
                 # the engine recycled its landing buffer since this plan was captured (many batch sizes)
                 plan.x_in.copy_(x_all)
             np.copyto(plan.idx_host.numpy(), order, casting="unsafe")      # pinned staging: async H2D
             plan.idx.copy_(plan.idx_host, non_blocking=True)
-            plan.graph.replay()
+            plan.run()
             plan.out_host.copy_(plan.out, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             # the division already happened on the device in the trace dtype (surprise.py:595);
@@ -427,16 +446,10 @@ class DSA(SA):
             self._last_raw = plan.out_host.numpy()
             return self._last_raw[3].copy()
         idx = torch.from_numpy(order).to(dev, non_blocking=True)
-        if self.use_graphs:
-            # sharded training sets replay one graph per stage with eager NCCL all-reduces in between
-            plan = E.dsa_plan(eng, int(order.size), q_off, x_all.dtype, self.use_filter, self._comm)
-            torch.index_select(x_all, 0, idx, out=plan.x)
-            packed = plan.run()
-        else:
-            x = x_all.index_select(0, idx)
-            q_class = torch.from_numpy(target_pred[order].astype(np.int32)).to(dev, non_blocking=True)
-            dist_a, dist_b, gid = E.dsa_distances(eng, x, q_class, q_off, self._comm, self.use_filter)
-            packed = torch.stack([dist_a.to(torch.float64), dist_b.to(torch.float64), gid.to(torch.float64)])
+        x = x_all.index_select(0, idx)
+        q_class = torch.from_numpy(target_pred[order].astype(np.int32)).to(dev, non_blocking=True)
+        dist_a, dist_b, gid = E.dsa_distances(eng, x, q_class, q_off, self._comm if sharded else None, self.use_filter)
+        packed = torch.stack([dist_a.to(torch.float64), dist_b.to(torch.float64), gid.to(torch.float64)])
         # back to the caller's order on the device, then a single D2H transfer
         # (float32/float64 -> float64 and int -> float64 are exact)
         full = torch.full((3, n_total), float("nan"), dtype=torch.float64, device=dev)

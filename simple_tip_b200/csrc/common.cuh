@@ -209,4 +209,38 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// One query row -> packed bf16 operand of tip_nn_filter (one segment) + reset filter state, by a full
+// warp: the arithmetic of pair_prep_kernel (query role): centre in fp32, round to bf16, |h|^2 and
+// the dropped part's norm accumulated in double.  src == nullptr packs a zero row.
+template <typename T>
+__device__ __forceinline__ void warp_pack_query(const T* __restrict__ src, int d, const float* __restrict__ center,
+                                                __nv_bfloat16* __restrict__ out, int64_t pitch, float* sqnorm,
+                                                float* rounderr, uint32_t* row_min, int32_t* cand_cnt, int lane) {
+  const int d16 = (d + 15) & ~15;
+  double acc = 0.0, err = 0.0;
+  for (int c = lane; c < d16; c += 32) {
+    float v = 0.f;
+    if (c < d) {
+      const T xv = src ? src[c] : (T)0;
+      const float ctr = center ? center[c] : 0.f;
+      v = sizeof(T) == 8 ? (float)((double)xv - (double)ctr) : __fsub_rn((float)xv, ctr);
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float hf = __bfloat162float(h);
+    const float res = __fsub_rn(v, hf);
+    acc += (double)hf * (double)hf;
+    err += (double)res * (double)res;
+    out[c] = h;
+  }
+  acc = warp_sum(acc);
+  err = warp_sum(err);
+  for (int c = d16 + lane; c < pitch; c += 32) out[c] = __float2bfloat16_rn(c - d16 < 3 ? 1.f : 0.f);
+  if (lane == 0) {
+    *sqnorm = (float)acc;
+    if (rounderr) *rounderr = (float)sqrt(err) * 1.000001f;
+    *row_min = 0x7f800000u;
+    *cand_cnt = 0;
+  }
+}
+
 }  // namespace tip

@@ -93,36 +93,10 @@ __device__ __forceinline__ void write_result(const RerankArgs<T>& a, int64_t row
     T* dst = a.out_rows + row * (int64_t)a.d;
     for (int i = lane; i < a.d; i += nlanes) dst[i] = b.pos >= 0 ? src[i] : (T)0;
   }
-  if (a.next_pack) {
-    // same arithmetic as pair_prep_kernel (query role, one segment): centre in fp32, round to bf16,
-    // |h|^2 and the dropped part's norm accumulated in double; nlanes == 32 here
-    __nv_bfloat16* out = a.next_pack + row * a.next_pitch;
-    const int d16 = (a.d + 15) & ~15;
-    double acc = 0.0, err = 0.0;
-    for (int c = lane; c < d16; c += 32) {
-      float v = 0.f;
-      if (c < a.d) {
-        const T xv = b.pos >= 0 ? src[c] : (T)0;
-        const float ctr = a.next_center ? a.next_center[c] : 0.f;
-        v = sizeof(T) == 8 ? (float)((double)xv - (double)ctr) : __fsub_rn((float)xv, ctr);
-      }
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
-      const float hf = __bfloat162float(h);
-      const float res = __fsub_rn(v, hf);
-      acc += (double)hf * (double)hf;
-      err += (double)res * (double)res;
-      out[c] = h;
-    }
-    acc = warp_sum(acc);
-    err = warp_sum(err);
-    for (int c = d16 + lane; c < a.next_pitch; c += 32) out[c] = __float2bfloat16_rn(c - d16 < 3 ? 1.f : 0.f);
-    if (lane == 0) {
-      a.next_sqnorm[row] = (float)acc;
-      if (a.next_rounderr) a.next_rounderr[row] = (float)sqrt(err) * 1.000001f;
-      a.next_row_min[row] = 0x7f800000u;
-      a.next_cand_cnt[row] = 0;
-    }
-  }
+  if (a.next_pack)   // nlanes == 32 here
+    warp_pack_query<T>(b.pos >= 0 ? src : nullptr, a.d, a.next_center, a.next_pack + row * a.next_pitch, a.next_pitch,
+                       a.next_sqnorm + row, a.next_rounderr ? a.next_rounderr + row : nullptr, a.next_row_min + row,
+                       a.next_cand_cnt + row, lane);
 }
 
 // ---- kernel 1: one warp per query, candidate lists ----------------------------------------------

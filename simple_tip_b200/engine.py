@@ -338,49 +338,188 @@ def count_tile_pairs(q_off: np.ndarray, ranges_per_class, row_tile: int = _lib.R
 # ------------------------------------------------------------------------------------------
 # cross-rank protocol (N_train sharded over the ranks of one NVSwitch box)
 # ------------------------------------------------------------------------------------------
-class TrainShardComm:
-    """All-reduces of per-shard results over a torch.distributed group (NCCL on GPUs, gloo in
-    the CPU tests).  All messages are O(N_test) scalars except the stage-2 query rows."""
+KEY_NONE_HI32 = 0x7F800000           # +inf as float bits: "this shard has no row of that range"
+KEY_NONE_LO = 0x7FFFFFFF
+P2P_MIN_RECORDS = 1 << 18            # receive slots per rank: 2 x world x 4 MiB
 
-    def __init__(self, group=None):
+
+def pack_winner_keys(dist: torch.Tensor, gid: torch.Tensor) -> torch.Tensor:
+    """float32 distances (>= 0, NaN = no row on this shard) and original indices -> int64 keys
+    (float bits << 32 | index).  Non-negative IEEE floats order like their bit patterns and the
+    sign bit is clear, so ONE integer MIN all-reduce yields np.min and np.argmin's first occurrence
+    (surprise.py:645-647) over all shards.  Plain torch ops: runs on CPU (gloo test) and CUDA."""
+    assert dist.dtype == torch.float32
+    none = torch.isnan(dist) | (gid < 0)
+    hi = torch.where(none, torch.full_like(dist, float("inf")), dist).view(torch.int32).to(torch.int64)
+    lo = torch.where(none, torch.full_like(gid, KEY_NONE_LO, dtype=torch.int64), gid.to(torch.int64))
+    return (hi << 32) | lo
+
+
+def unpack_winner_keys(keys: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Inverse of pack_winner_keys: (float32 distance with NaN for 'no row anywhere', int64 index or -1)."""
+    hi = (keys >> 32).to(torch.int32)
+    lo = keys & 0xFFFFFFFF
+    none = (hi >= KEY_NONE_HI32) | (lo >= KEY_NONE_LO)
+    dist = torch.where(none, torch.full((), float("nan"), dtype=torch.float32, device=keys.device), hi.view(torch.float32))
+    return dist, torch.where(none, torch.full_like(lo, -1), lo)
+
+
+class P2PExchange:
+    """Symmetric receive buffers of libb200tip's tip_comm, one per rank, opened across the
+    processes of one box with CUDA IPC; the handles travel through torch.distributed once."""
+
+    def __init__(self, dist, group, dev: torch.device, cap_records: int):
+        self.lib = _lib.load()
+        self.cap = int(cap_records)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.handle = None
+        self.local = C.c_void_p(0)
+        handle = (C.c_ubyte * 64)()
+        rc = self.lib.tip_comm_alloc(self.world, self.cap, C.byref(self.local), handle)
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
+        every = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(every, mine, group=group)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        err = None
+        if int(ok.item()) == 1:
+            blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in every)
+            out = C.c_void_p(0)
+            rc = self.lib.tip_comm_open(self.rank, self.world, self.local, blob, self.cap, C.byref(out))
+            if rc == 0:
+                self.handle = out
+            else:
+                err = self.lib.tip_last_error().decode(errors="replace")
+        else:
+            err = "tip_comm_alloc failed on some rank"
+        ok = torch.tensor([1 if self.handle is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)       # all ranks take the same path
+        if int(ok.item()) != 1:
+            self.close()
+            raise RuntimeError(f"peer-memory exchange unavailable: {err or 'a peer could not map the buffers'}")
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.tip_comm_close(self.handle)
+            self.handle = None
+        if self.local:
+            self.lib.tip_comm_free_local(self.local)
+            self.local = C.c_void_p(0)
+
+    def push_nn(self, dist_t: torch.Tensor, gid: Optional[torch.Tensor]):
+        _lib.check(self.lib.tip_comm_push_nn(self.handle, _p(dist_t), tip_dtype(dist_t.dtype), _p(gid), dist_t.shape[0],
+                                             _stream()), "tip_comm_push_nn")
+
+    def min_into(self, out: torch.Tensor):
+        _lib.check(self.lib.tip_comm_min(self.handle, tip_dtype(out.dtype), out.shape[0], _p(out), _stream()), "tip_comm_min")
+
+    def lse(self, mx: torch.Tensor, sm: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        m = mx.shape[0]
+        _lib.check(self.lib.tip_comm_push_lse(self.handle, _p(mx), _p(sm), m, _stream()), "tip_comm_push_lse")
+        gm = torch.empty(m, dtype=torch.float32, device=mx.device)
+        gs = torch.empty(m, dtype=torch.float64, device=mx.device)
+        _lib.check(self.lib.tip_comm_lse(self.handle, m, _p(gm), _p(gs), _stream()), "tip_comm_lse")
+        return gm, gs
+
+
+class TrainShardComm:
+    """Exchange steps of the N_train-sharded search over a torch.distributed group.
+
+    On GPUs of one NVSwitch box the per-query records travel as peer stores fused into our own
+    kernels (`P2PExchange`, csrc/shard.cu); otherwise — gloo in the CPU tests, B200TIP_EXCHANGE=nccl,
+    or no peer access — as ONE integer MIN all-reduce per stage through torch.distributed.  All
+    messages are O(N_test) scalars; the stage-2 query rows are gathered from the replicated raw
+    training set by original index (or, without a replica, summed from their owners)."""
+
+    def __init__(self, group=None, exchange: Optional[str] = None):
         import torch.distributed as dist
 
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.dist = dist
         self.group = group
+        self.exchange = exchange or os.environ.get("B200TIP_EXCHANGE", "auto")     # auto | p2p | nccl
+        assert self.exchange in ("auto", "p2p", "nccl"), self.exchange
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self.collectives = 0          # torch.distributed all-reduces issued on the data path
+        self._p2p = None
+        self._p2p_failed = None
+
+    # -- peer-memory exchange -----------------------------------------------------------------
+    def p2p(self, dev: torch.device, records: int) -> Optional[P2PExchange]:
+        """The peer-memory exchange sized for `records` queries, or None (collective fallback).
+        Collective: every rank must call it with the same arguments."""
+        if self.exchange == "nccl" or self.world < 2 or dev.type != "cuda" or self.world > 16:
+            return None
+        if self._p2p is not None:
+            # never re-allocated: captured graphs hold its addresses.  Larger batches take the collective path.
+            return self._p2p if self._p2p.cap >= records else None
+        if self._p2p_failed is not None:
+            return None
+        try:
+            self._p2p = P2PExchange(self.dist, self.group, dev, max(int(records), P2P_MIN_RECORDS))
+        except (RuntimeError, _lib.TipError) as e:
+            if self.exchange == "p2p":
+                raise
+            self._p2p_failed = str(e)
+            return None
+        return self._p2p
+
+    def close(self):
+        if self._p2p is not None:
+            self._p2p.close()
+            self._p2p = None
 
     def min_(self, t: torch.Tensor) -> torch.Tensor:
+        self.collectives += 1
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
         return t
 
     def max_(self, t: torch.Tensor) -> torch.Tensor:
+        self.collectives += 1
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return t
 
     def sum_(self, t: torch.Tensor) -> torch.Tensor:
+        self.collectives += 1
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
 
     # -- DSA stage 1: global (distance, lowest original index) and the winning rows -----------
-    def reduce_winners(self, dist_a: torch.Tensor, gid: torch.Tensor, rows: torch.Tensor
-                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """dist_a[m] local minima (NaN = this shard has no row of the class), gid[m] original
-        index of the local winner, rows[m, d] the local winner's trace.  Returns the global
-        minimum distance, the global winner's original index (lowest index among exact ties,
-        i.e. np.argmin's first occurrence) and its trace on every rank."""
+    def reduce_winner_index(self, dist_a: torch.Tensor, gid: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Global minimum distance (NaN where no shard has a row of the class) and the original
+        index of the winner — lowest index among exact ties, i.e. np.argmin's first occurrence.
+        float32: one MIN all-reduce of packed 64-bit keys; float64: MIN of the distances, then MIN
+        of the index among the ranks that hold the minimum."""
+        if dist_a.dtype == torch.float32:
+            return unpack_winner_keys(self.min_(pack_winner_keys(dist_a, gid)))
         big = torch.iinfo(torch.int64).max
         local = torch.where(torch.isnan(dist_a), torch.full_like(dist_a, float("inf")), dist_a)
         gmin = self.min_(local.clone())
-        cand = torch.where(local == gmin, gid.to(torch.int64), torch.full_like(gid, big, dtype=torch.int64))
+        cand = torch.where((local == gmin) & (gid >= 0), gid.to(torch.int64),
+                           torch.full_like(gid, big, dtype=torch.int64))
         ggid = self.min_(cand)
-        mine = (local == gmin) & (gid.to(torch.int64) == ggid) & torch.isfinite(gmin)
-        contrib = torch.where(mine[:, None], rows, torch.zeros_like(rows))
-        self.sum_(contrib)
-        gmin = torch.where(torch.isinf(gmin) & torch.isnan(dist_a), dist_a, gmin)  # nobody had the class
-        return gmin, ggid, contrib
+        none = torch.isinf(gmin) | (ggid == big)
+        return (torch.where(none, torch.full_like(gmin, float("nan")), gmin),
+                torch.where(none, torch.full_like(ggid, -1), ggid))
+
+    def reduce_winners(self, dist_a: torch.Tensor, gid: torch.Tensor, rows: Optional[torch.Tensor] = None,
+                       train_full: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """dist_a[m] local minima (NaN = this shard has no row of the class), gid[m] original
+        index of the local winner.  Returns the global minimum distance, the global winner's original
+        index and its trace on every rank: gathered from `train_full` (the replicated training set in
+        original order) when given, else all-reduced from `rows[m, d]` (owner contributes, others
+        zeros -> exact)."""
+        gmin, ggid = self.reduce_winner_index(dist_a, gid)
+        if train_full is not None:
+            winners = train_full.index_select(0, ggid.clamp(min=0))
+            winners = torch.where((ggid >= 0)[:, None], winners, torch.zeros_like(winners))
+        else:
+            mine = (ggid >= 0) & (gid.to(torch.int64) == ggid)
+            winners = torch.where(mine[:, None], rows, torch.zeros_like(rows))
+            self.sum_(winners)
+        return gmin, ggid, winners
 
     def reduce_min_nan(self, d: torch.Tensor) -> torch.Tensor:
         """min over ranks where NaN means 'empty range on this shard'."""
@@ -428,6 +567,9 @@ class NnEngine:
         self._capture_refs = None     # while a plan is being captured: engine-owned tensors its graph reads
         self.sched_counter = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.last_cand_cnt_by_mode = {}
+        # N_train-sharded engines: the whole (post-subsample) training set in ORIGINAL row order, replicated on
+        # every rank, from which the global stage-1 winners are gathered by index (set by the owner)
+        self.t_full = None
         if self.n > 0:
             self.center = self.t.mean(dim=0, dtype=torch.float64).to(torch.float32).contiguous()
             self.t_pack = torch.empty((self.n, self.pitch), dtype=torch.bfloat16, device=self.dev)
@@ -600,32 +742,107 @@ class NnEngine:
         return out
 
 
+def winner_queries(engine: "NnEngine", p2p: Optional[P2PExchange], gdist: Optional[torch.Tensor],
+                   ggid: Optional[torch.Tensor], m: int, dtype: torch.dtype, state2):
+    """Global stage-1 winners -> (dist_a, original index, winning rows) + the packed stage-2 query
+    state, gathered from the replicated training set (tip_shard_winner_queries).  With `p2p` the
+    per-shard records of the exchange started by the last push are reduced inside the kernel."""
+    dev = engine.dev
+    dist_a = torch.empty(m, dtype=dtype, device=dev)
+    gid = torch.empty(m, dtype=torch.int32, device=dev)
+    rows = torch.empty((m, engine.d), dtype=dtype, device=dev)
+    q_pack, q_sq, q_err, row_min, cand_cnt = state2
+    _lib.check(engine.lib.tip_shard_winner_queries(p2p.handle if p2p is not None else None, _p(gdist), _p(ggid),
+                                                   tip_dtype(dtype), m, engine.d, _p(engine.t_full),
+                                                   engine.t_full.shape[0], _p(engine.center), _p(dist_a), _p(gid), _p(rows),
+                                                   _p(q_pack), _p(q_sq), _p(q_err), _p(row_min), _p(cand_cnt), _stream()),
+               "tip_shard_winner_queries")
+    return dist_a, gid, rows
+
+
 def dsa_distances(engine: NnEngine, x: torch.Tensor, q_class: torch.Tensor, q_off: np.ndarray,
                   comm: Optional[TrainShardComm] = None, use_filter: bool = True
                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """surprise.py:615-631 for class-sorted queries x: (dist_a, dist_b, winner original index)."""
+    """surprise.py:615-631 for class-sorted queries x: (dist_a, dist_b, winner original index).
+    Eager launches (the CUDA-graph plans below replay the same sequence)."""
     sharded = comm is not None and comm.world > 1
-    # single shard: stage 1's re-rank also emits its winners as the packed queries of stage 2
-    fuse = use_filter and not sharded and engine.has_items(q_off, _lib.RANGE_OTHER_CLASSES)
-    state2 = engine.query_state(x.shape[0]) if fuse else None
-    dist_a, _, gid, winners = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter, want_rows=True,
-                                            next_query=state2)
-    if sharded:
-        dist_a, gid, winners = comm.reduce_winners(dist_a, gid, winners)
-    dist_b = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter, prepacked=state2)[0]
-    if comm is not None and comm.world > 1:
-        dist_b = comm.reduce_min_nan(dist_b)
+    m = x.shape[0]
+    if not sharded:
+        # single shard: stage 1's re-rank also emits its winners as the packed queries of stage 2
+        fuse = use_filter and engine.has_items(q_off, _lib.RANGE_OTHER_CLASSES)
+        state2 = engine.query_state(m) if fuse else None
+        dist_a, _, gid, winners = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter, want_rows=True,
+                                                next_query=state2)
+        dist_b = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter, prepacked=state2)[0]
+        return dist_a, dist_b, gid
+    replica = engine.t_full is not None
+    p2p = comm.p2p(engine.dev, m) if replica else None
+    local_a, _, local_gid, local_rows = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter,
+                                                      want_rows=not replica)
+    if replica:
+        state2 = engine.query_state(m)
+        if p2p is not None:
+            p2p.push_nn(local_a, local_gid)
+            dist_a, gid, winners = winner_queries(engine, p2p, None, None, m, x.dtype, state2)
+        else:
+            gmin, ggid = comm.reduce_winner_index(local_a, local_gid)
+            dist_a, gid, winners = winner_queries(engine, None, gmin.contiguous(), ggid.to(torch.int32).contiguous(), m,
+                                                  x.dtype, state2)
+        prepacked = state2 if (use_filter and engine.has_items(q_off, _lib.RANGE_OTHER_CLASSES)) else None
+    else:
+        dist_a, gid, winners = comm.reduce_winners(local_a, local_gid, local_rows)
+        prepacked = None
+    local_b = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter, prepacked=prepacked)[0]
+    if p2p is not None:
+        p2p.push_nn(local_b, None)
+        dist_b = torch.empty_like(local_b)
+        p2p.min_into(dist_b)
+    else:
+        dist_b = comm.reduce_min_nan(local_b)
     return dist_a, dist_b, gid
 
 
+class _Capture:
+    """Context for capturing engine work into a CUDA graph: garbage from earlier engines (old graphs,
+    their private pools) must not be released in the middle of the capture — a cudaFree / graph
+    destroy there invalidates it — and engine-owned tensors whose addresses get baked into the
+    graph are kept alive by the plan."""
+
+    def __init__(self, engine: "NnEngine", keep: list):
+        self.engine, self.keep = engine, keep
+
+    def __enter__(self):
+        import gc
+
+        gc.collect()
+        self.was_enabled = gc.isenabled()
+        gc.disable()
+        self.engine._capture_refs = []
+        return self
+
+    def __exit__(self, *exc):
+        import gc
+
+        self.keep.extend(self.engine._capture_refs)
+        self.engine._capture_refs = None
+        if self.was_enabled:
+            gc.enable()
+        return False
+
+
 class DsaPlan:
-    """The whole scoring call for one (batch size, class histogram) captured as ONE CUDA graph:
+    """The whole scoring call for one (batch size, class histogram) captured as CUDA graph(s):
     gather into class-sorted order -> pack -> filter -> re-rank(+winner rows) -> pack -> filter ->
     re-rank -> scatter of (dist_a, dist_b, winner index) back to the caller's row order.
     Inputs: `x_in` [n_total, d] (the engine's landing buffer for host uploads) and `idx` [m]
     (original row of every class-sorted query).  Output: `out` [4, n_total] float64 in the
     caller's order — dist_a, dist_b, winner index, dist_a / dist_b (divided in the trace dtype) —
-    where rows the reference never scores keep NaN / -1."""
+    where rows the reference never scores keep NaN / -1.
+
+    N_train sharded (comm.world > 1): with the peer-memory exchange the two exchange steps are
+    kernels of ours and the call is still ONE graph; with the torch.distributed fallback the call is
+    three graph segments with one eager MIN all-reduce between consecutive segments (two for float64
+    traces in the first exchange)."""
 
     def __init__(self, engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool,
                  comm: Optional[TrainShardComm] = None, n_total: Optional[int] = None):
@@ -645,40 +862,104 @@ class DsaPlan:
         q_class = np.repeat(np.arange(engine.num_classes, dtype=np.int32), np.diff(self.q_off))
         self.q_class = torch.from_numpy(q_class).to(dev)
         row_bytes = engine.d * self.x.element_size()
+        self.comm = comm if (comm is not None and comm.world > 1) else None
+        sharded = self.comm is not None
+        if sharded and engine.t_full is None:
+            raise RuntimeError("the sharded plan needs the replicated training set (NnEngine.t_full)")
+        self.p2p = self.comm.p2p(dev, self.m) if sharded else None
+        self._keep_alive = []
+        S = self.state = {}
 
-        def body():
+        def gather():
             _lib.check(lib.tip_gather_rows(_p(self.x_in), row_bytes, _p(self.idx), self.m, _p(self.x), _stream()),
                        "tip_gather_rows")
-            a, b, gid = dsa_distances(engine, self.x, self.q_class, self.q_off, comm, use_filter)
+
+        def scatter(a, b, gid):
             if self.n_total != self.m:         # which rows are unscored can change between calls
                 self.out.fill_(float("nan"))
                 self.out[2].fill_(-1.0)
             _lib.check(lib.tip_dsa_pack_out(_p(a), _p(b), tip_dtype(a.dtype), _p(gid), _p(self.idx), self.m,
                                             self.n_total, _p(self.out), _stream()), "tip_dsa_pack_out")
-            return a, b, gid
+            self.dist_a, self.dist_b, self.gid = a, b, gid
 
+        if not sharded or self.p2p is not None:
+            def whole():
+                gather()
+                scatter(*dsa_distances(engine, self.x, self.q_class, self.q_off, self.comm, use_filter))
+
+            segments = [(whole, True)]
+        else:
+            # torch.distributed fallback: static exchange buffers written by one graph segment,
+            # all-reduced in place (eager), read by the next segment
+            f32 = dtype == torch.float32
+            S["keys"] = torch.zeros(self.m, dtype=torch.int64 if f32 else dtype, device=dev)
+            S["cand"] = torch.zeros(self.m, dtype=torch.int64, device=dev)
+            S["bmin"] = torch.zeros(self.m, dtype=dtype, device=dev)
+            big = torch.iinfo(torch.int64).max
+
+            def seg_a():
+                gather()
+                la, _, lg, _ = engine.search(self.x, self.q_class, self.q_off, _lib.RANGE_SAME_CLASS, use_filter)
+                S["la"], S["lg"] = la, lg
+                if f32:
+                    S["keys"].copy_(pack_winner_keys(la, lg))
+                else:
+                    S["keys"].copy_(torch.where(torch.isnan(la), torch.full_like(la, float("inf")), la))
+
+            def exch_1():
+                self.comm.min_(S["keys"])
+                if not f32:
+                    la = torch.where(torch.isnan(S["la"]), torch.full_like(S["la"], float("inf")), S["la"])
+                    S["cand"].copy_(torch.where((la == S["keys"]) & (S["lg"] >= 0), S["lg"].to(torch.int64),
+                                                torch.full_like(S["cand"], big)))
+                    self.comm.min_(S["cand"])
+
+            def seg_b():
+                if f32:
+                    gmin, ggid = unpack_winner_keys(S["keys"])
+                else:
+                    none = torch.isinf(S["keys"]) | (S["cand"] == big)
+                    gmin = torch.where(none, torch.full_like(S["keys"], float("nan")), S["keys"])
+                    ggid = torch.where(none, torch.full_like(S["cand"], -1), S["cand"])
+                state2 = engine.query_state(self.m)
+                a, gid, winners = winner_queries(engine, None, gmin.contiguous(), ggid.to(torch.int32).contiguous(),
+                                                 self.m, dtype, state2)
+                S["a"], S["gid"] = a, gid
+                pre = state2 if (use_filter and engine.has_items(self.q_off, _lib.RANGE_OTHER_CLASSES)) else None
+                lb = engine.search(winners, self.q_class, self.q_off, _lib.RANGE_OTHER_CLASSES, use_filter, prepacked=pre)[0]
+                S["bmin"].copy_(torch.where(torch.isnan(lb), torch.full_like(lb, float("inf")), lb))
+
+            def exch_2():
+                self.comm.min_(S["bmin"])
+
+            def seg_c():
+                b = torch.where(torch.isinf(S["bmin"]), torch.full_like(S["bmin"], float("nan")), S["bmin"])
+                scatter(S["a"], b, S["gid"])
+
+            segments = [(seg_a, True), (exch_1, False), (seg_b, True), (exch_2, False), (seg_c, True)]
+
+        # eager warm-up on a side stream: fills caches, sets kernel attributes, runs the collectives once
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):          # eager warm-up: fills caches, sets kernel attributes
-            body()
+        with torch.cuda.stream(side):
+            for fn, _ in segments:
+                fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        # Garbage from earlier engines (old graphs, their private pools) must not be released in the
-        # middle of the capture: a cudaFree / graph destroy there invalidates it.
-        import gc
-
-        gc.collect()
-        was_enabled = gc.isenabled()
-        gc.disable()
-        engine._capture_refs = []
-        try:
-            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-                self.dist_a, self.dist_b, self.gid = body()
-        finally:
-            self._keep_alive, engine._capture_refs = engine._capture_refs, None
-            if was_enabled:
-                gc.enable()
+        self.steps = []
+        for fn, capturable in segments:
+            if capturable:
+                g = torch.cuda.CUDAGraph()
+                with _Capture(engine, self._keep_alive):
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        fn()
+                self.steps.append(g.replay)
+            else:
+                fn()                      # keeps the ranks' collective sequences aligned during set-up
+                self.steps.append(fn)
+        self.graph = None
+        if len(segments) == 1:
+            self.graph = g
 
     def load_sorted(self, x_sorted: torch.Tensor):
         """Device-resident input already in class-sorted order (benchmarks, tools)."""
@@ -687,64 +968,9 @@ class DsaPlan:
         self.idx.copy_(torch.arange(self.m, dtype=torch.int32, device=self.idx.device))
 
     def run(self):
-        self.graph.replay()
+        for step in self.steps:
+            step()
         return self.out
-
-
-class StagePlan:
-    """One stage of the search (pack -> filter -> re-rank) for a fixed batch shape as a CUDA graph;
-    inputs are copied into `q`, outputs are `dist`, `gid`, `rows`."""
-
-    def __init__(self, engine: "NnEngine", m: int, q_off: np.ndarray, q_class: torch.Tensor, dtype: torch.dtype,
-                 mode: int, use_filter: bool, want_rows: bool):
-        import gc
-
-        self.q = torch.zeros((m, engine.d), dtype=dtype, device=engine.dev)
-        side = torch.cuda.Stream(device=engine.dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            engine.search(self.q, q_class, q_off, mode, use_filter, want_rows)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        gc.collect()
-        was_enabled = gc.isenabled()
-        gc.disable()
-        engine._capture_refs = []
-        try:
-            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-                self.dist, _, self.gid, self.rows = engine.search(self.q, q_class, q_off, mode, use_filter, want_rows)
-        finally:
-            self._keep_alive, engine._capture_refs = engine._capture_refs, None
-            if was_enabled:
-                gc.enable()
-
-
-class ShardedDsaPlan:
-    """N_train-sharded search: the two local stages are CUDA graphs, the all-reduces between them
-    are ordinary (eager) NCCL calls — no collective is captured."""
-
-    def __init__(self, engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool,
-                 comm: TrainShardComm):
-        self.comm = comm
-        self.q_off = np.asarray(q_off, dtype=np.int64).copy()
-        q_class = np.repeat(np.arange(engine.num_classes, dtype=np.int32), np.diff(self.q_off))
-        self.q_class = torch.from_numpy(q_class).to(engine.dev)
-        self.stage1 = StagePlan(engine, m, self.q_off, self.q_class, dtype, _lib.RANGE_SAME_CLASS, use_filter, True)
-        self.stage2 = StagePlan(engine, m, self.q_off, self.q_class, dtype, _lib.RANGE_OTHER_CLASSES, use_filter, False)
-        self.x = self.stage1.q
-
-    def load_sorted(self, x_sorted: torch.Tensor):
-        self.x.copy_(x_sorted)
-
-    def run(self) -> torch.Tensor:
-        self.stage1.graph.replay()
-        dist_a, gid, winners = self.comm.reduce_winners(self.stage1.dist, self.stage1.gid, self.stage1.rows)
-        self.stage2.q.copy_(winners)
-        self.stage2.graph.replay()
-        dist_b = self.comm.reduce_min_nan(self.stage2.dist)
-        self.dist_a, self.dist_b, self.gid = dist_a, dist_b, gid
-        return torch.stack([dist_a.to(torch.float64), dist_b.to(torch.float64), gid.to(torch.float64)])
 
 
 def dsa_plan(engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool,
@@ -755,10 +981,7 @@ def dsa_plan(engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, 
     if plan is None:
         if len(engine._plans) >= 8:
             engine._plans.pop(next(iter(engine._plans)))
-        if comm is not None and comm.world > 1:
-            plan = ShardedDsaPlan(engine, m, q_off, dtype, use_filter, comm)
-        else:
-            plan = DsaPlan(engine, m, q_off, dtype, use_filter, n_total=n_total)
+        plan = DsaPlan(engine, m, q_off, dtype, use_filter, comm, n_total=n_total)
         engine._plans[key] = plan
     return plan
 
@@ -767,11 +990,17 @@ def dsa_plan(engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, 
 # Gaussian-KDE engine (LSA)
 # ------------------------------------------------------------------------------------------
 class KdeEngine:
-    def __init__(self, p_whitened: np.ndarray):
-        """p_whitened: [n, d] float64 whitened, centred training traces (host)."""
+    def __init__(self, p_whitened: np.ndarray, comm: Optional[TrainShardComm] = None):
+        """p_whitened: [n, d] float64 whitened, centred training traces (host).  With a communicator
+        of more than one rank the engine keeps rows rank::world (N_train sharded) and merges the
+        per-shard partial sums in log_kernel_sum (north_star: one exchange of partial KDE sums)."""
         self.dev = require_cuda()
         self.lib = _lib.load()
+        self.comm = comm if (comm is not None and comm.world > 1) else None
+        if self.comm is not None:
+            p_whitened = np.ascontiguousarray(p_whitened[self.comm.rank::self.comm.world])
         self.n, self.d = p_whitened.shape
+        self.precision = "split-bf16 x3 (h.h + h.l + l.h, ~2^-17 relative)"
         self.pitch = int(self.lib.tip_pair_pitch(self.d, 3))
         sms = C.c_int(0)
         _lib.check(self.lib.tip_device_info(C.byref(sms), None, None), "tip_device_info")
@@ -804,6 +1033,9 @@ class KdeEngine:
         sm = torch.empty(m, dtype=torch.float32, device=self.dev)
         _lib.check(lib.tip_kde_combine(_p(part_max), _p(part_sum), m, slots, _p(mx), _p(sm), _stream()),
                    "tip_kde_combine")
+        if self.comm is not None:
+            p2p = self.comm.p2p(self.dev, m)
+            mx, sm = p2p.lse(mx, sm) if p2p is not None else self.comm.reduce_lse(mx, sm)
         return mx, sm, q_sq
 
 

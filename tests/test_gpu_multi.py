@@ -1,5 +1,8 @@
-"""N_train-sharded DSA / LSA over NCCL (needs >= 2 GPUs; skipped otherwise).  Every rank must
-reproduce the single-GPU (= oracle) result bit for bit for DSA, and within the LSA tolerance."""
+"""N_train-sharded DSA / LSA on >= 2 GPUs (skipped otherwise; the driver's GPU-test box has one
+GPU, so bench.py repeats the DSA check at every --gpus N > 1 and prints `parity_ok`).  Every rank
+must reproduce the oracle bit for bit for DSA and within the LSA tolerance for the KDE, with both
+exchange implementations: peer-memory stores fused into our kernels (csrc/shard.cu) and the
+torch.distributed (NCCL) MIN all-reduce of packed keys."""
 import os
 
 import numpy as np
@@ -10,7 +13,7 @@ from oracle import np_oracle
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, exchange, q):
     import torch
     import torch.distributed as dist
 
@@ -19,9 +22,9 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from simple_tip_b200 import engine as E
-        from simple_tip_b200.core.surprise import DSA
+        from simple_tip_b200.core.surprise import DSA, LSA
 
-        comm = E.TrainShardComm()
+        comm = E.TrainShardComm(exchange=exchange)
         for n_train, n_test, d, classes, dt, seed in [(6000, 700, 128, 10, np.float32, 2), (2500, 300, 200, 4, np.float32, 3),
                                                       (1500, 200, 24, 3, np.float64, 4)]:
             xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(n_train, n_test, d, classes, seed=seed, dtype=dt)
@@ -30,11 +33,28 @@ def _worker(rank, world, port, q):
             xte[:10], pte[:10] = xtr[0:10], ytr[0:10]
             want = np_oracle.dsa_oracle(xtr, ytr, xte, pte)
             sa = DSA(xtr, ytr, comm=comm)
-            assert sa._engine.n < n_train
-            got = sa(xte, pte)
-            assert np.array_equal(got, want["dsa"], equal_nan=True), (rank, "dsa")
-            assert np.array_equal(sa.last_winner_index, want["idx_a"]), (rank, "winner")
-            assert np.array_equal(sa.last_dist_b, want["dist_b"]), (rank, "dist_b")
+            assert sa._engine.n < n_train and sa._engine.t_full.shape[0] == n_train
+            for graphs in (True, False):
+                sa.use_graphs = graphs
+                for rep in range(2):            # second call replays the captured plan
+                    got = sa(xte, pte)
+                    assert np.array_equal(got, want["dsa"], equal_nan=True), (rank, "dsa", graphs, rep)
+                    assert np.array_equal(sa.last_winner_index, want["idx_a"]), (rank, "winner", graphs, rep)
+                    assert np.array_equal(sa.last_dist_a, want["dist_a"]), (rank, "dist_a", graphs, rep)
+                    assert np.array_equal(sa.last_dist_b, want["dist_b"]), (rank, "dist_b", graphs, rep)
+            # a test class held by one shard only / a different batch (new plan, same communicator)
+            got = sa(xte[5:77], pte[5:77])
+            assert np.array_equal(got, want["dsa"][5:77], equal_nan=True), (rank, "sub-batch")
+        if exchange != "nccl":
+            assert comm._p2p is not None, comm._p2p_failed
+            assert comm.collectives == 0, "peer-memory exchange must not fall back to torch.distributed collectives"
+        # LSA: per-shard partial KDE sums merged across the ranks
+        xs, _, xt, _, _ = np_oracle.synth_clusters(3000, 257, 48, 4, seed=9)
+        ref = np_oracle.lsa_oracle(xs, xt)
+        lsa = LSA(xs, comm=comm)
+        assert lsa.kde._engine.n < 3000
+        got = lsa(xt)
+        assert np.allclose(got, ref, rtol=1e-4, atol=2e-4), (rank, float(np.max(np.abs(got - ref))))
         q.put((rank, "ok"))
     except Exception:
         import traceback
@@ -44,7 +64,8 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_sharded_dsa_nccl():
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_sharded_dsa_lsa(exchange):
     import torch
     import torch.multiprocessing as mp
 
@@ -53,8 +74,8 @@ def test_sharded_dsa_nccl():
         pytest.skip("needs >= 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29600 + (os.getpid() % 2000) + (7 if exchange == "nccl" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, exchange, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in procs]

@@ -17,12 +17,12 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 def test_c_abi_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "b200tip.h")).read()
     declared = set(re.findall(r"\b(tip_[a-z0-9_]+)\s*\(", header))
-    declared -= {"tip_status", "tip_dtype", "tip_work_item"}
+    declared -= {"tip_status", "tip_dtype", "tip_work_item", "tip_comm"}
     assert declared == set(_lib.symbols()), declared ^ set(_lib.symbols())
     lib = _lib.load()                      # static cudart: loads without a GPU
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.tip_version() == 100
+    assert lib.tip_version() == 200
     assert lib.tip_pair_pitch(128, 1) == 192 and lib.tip_pair_pitch(256, 3) == 832
     assert lib.tip_pair_pitch(5, 1) == 64 and lib.tip_pair_pitch(0, 1) == -1
     assert C.sizeof(_lib.WorkItem) == 24
@@ -237,6 +237,23 @@ def _worker(rank, world, port, q):
         assert np.array_equal(g_da.numpy(), full["dist_a"])
         assert np.array_equal(g_gid.numpy(), full["idx_a"])
         assert np.array_equal(g_rows.numpy(), xtr[full["idx_a"]])
+        # float32 distances travel as ONE MIN all-reduce of packed (float bits << 32 | index) keys
+        before = comm.collectives
+        k_da, k_gid = comm.reduce_winner_index(torch.from_numpy(da), torch.from_numpy(gid))
+        assert comm.collectives == before + 1
+        assert np.array_equal(k_da.numpy(), full["dist_a"]) and np.array_equal(k_gid.numpy(), full["idx_a"])
+        # ... and the winners come from the replicated training set by index: no row exchange at all
+        before = comm.collectives
+        r_da, r_gid, r_rows = comm.reduce_winners(torch.from_numpy(da), torch.from_numpy(gid), None, torch.from_numpy(xtr))
+        assert comm.collectives == before + 1 and np.array_equal(r_rows.numpy(), xtr[full["idx_a"]])
+        # float64: MIN of the distances, then MIN of the index among the holders of the minimum
+        d_da, d_gid = comm.reduce_winner_index(torch.from_numpy(da.astype(np.float64)), torch.from_numpy(gid))
+        assert np.array_equal(d_da.numpy(), full["dist_a"].astype(np.float64)) and np.array_equal(d_gid.numpy(), full["idx_a"])
+        # a class nobody holds: NaN / -1 on every rank, both dtypes
+        for dt in (torch.float32, torch.float64):
+            e_d, e_g = comm.reduce_winner_index(torch.tensor([float("nan"), 2.0 + rank], dtype=dt),
+                                                torch.tensor([-1, 7 + rank]))
+            assert np.isnan(e_d[0].item()) and e_g[0].item() == -1 and e_d[1].item() == 2.0 and e_g[1].item() == 7
         # stage 2 on the shard: distance from the winning TRAIN rows to other-class rows
         db = np.full(60, np.nan, dtype=np.float32)
         for i in range(60):
@@ -329,3 +346,25 @@ def test_balanced_items_random_histograms_property():
             assert np.all(pool[:, 3] > pool[:, 2]) and np.all(-(-(pool[:, 3] - pool[:, 2]) // col_tile) <= 3)
 
     check()
+
+
+def test_winner_keys_order_like_numpy_argmin():
+    """Packed (float bits << 32 | index) keys: integer order == (distance, first occurrence)."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    d = np.abs(rng.normal(size=4096)).astype(np.float32)
+    d[::7] = d[0]                                 # exact ties
+    d[5] = 0.0
+    d[9] = np.float32(1e-45)                      # subnormal
+    gid = rng.permutation(4096).astype(np.int64)
+    keys = E.pack_winner_keys(torch.from_numpy(d), torch.from_numpy(gid))
+    assert (keys >= 0).all()
+    order = np.lexsort((gid, d))
+    assert np.array_equal(np.argsort(keys.numpy(), kind="stable"), order)
+    back_d, back_g = E.unpack_winner_keys(keys)
+    assert np.array_equal(back_d.numpy(), d) and np.array_equal(back_g.numpy(), gid)
+    none = E.pack_winner_keys(torch.tensor([float("nan"), 1.0]), torch.tensor([3, -1]))
+    assert (none > keys.max()).all()
+    nd, ng = E.unpack_winner_keys(none)
+    assert np.isnan(nd.numpy()).all() and (ng.numpy() == -1).all()
