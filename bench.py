@@ -502,8 +502,11 @@ def run_ours(args):
 
     # ---- north_star layout on the C5-shaped slice (all ranks) ---------------------------------------------
     c5 = None
+    launch_mode = "CUDA-graph replay of the search" if plan is not None else "eager launches"
+    if parity is not None and rank == 0:
+        print("[bench] parity:", json.dumps(parity), file=sys.stderr, flush=True)
     if not args.no_c5:
-        del plan
+        plan = None
         sa._engine._plans.clear()
         torch.cuda.empty_cache()
         try:
@@ -512,6 +515,8 @@ def run_ours(args):
             import traceback
 
             c5 = {"error": f"{type(e).__name__}: {e}", "traceback": traceback.format_exc()[-1500:]}
+        if rank == 0:
+            print("[bench] n_train_sharded:", json.dumps(c5), file=sys.stderr, flush=True)
 
     others = None
     if rank == 0 and world == 1 and not args.no_others:
@@ -559,7 +564,7 @@ def run_ours(args):
                                            "measured in n_train_sharded" if world > 1 else "1 GPU"),
                            "filter": "bf16 tcgen05 candidate filter + exact fp32 re-rank (bit-identical to NumPy)",
                            "l2": "flushed between steps (256 MiB write)", "timing": "per-step CUDA events, summed",
-                           "launch": "CUDA-graph replay of the search" if plan is not None or sa.use_graphs else "eager launches",
+                           "launch": launch_mode,
                            "cpu_affinity": affinity},
                 "e2e": {"value": e2e, "unit": "inputs/s", "ms_per_step": tot_e2e_ms / args.steps,
                         "source": "pinned host memory (caller-pinned NumPy array)",
@@ -655,8 +660,11 @@ def secondary(wl, args, tm: Timer, dev, steps: int, with_cpu: bool = True):
         fault = pte != yte
         want_pc = np_oracle.pc_lsa_oracle(xtr, ytr, xte[sub], pte[sub])
         got_pc = pc(xte, pte)
-        rel_pc = np.abs(got_pc[sub] - want_pc) / np.abs(want_pc)
-        extra["pc_lsa"]["max_rel_err_256_rows"] = float(rel_pc.max())
+        fin = np.isfinite(want_pc)
+        rel_pc = np.abs(got_pc[sub][fin] - want_pc[fin]) / np.abs(want_pc[fin])
+        extra["pc_lsa"]["max_rel_err_256_rows"] = float(rel_pc.max()) if fin.any() else None
+        extra["pc_lsa"]["inf_pattern_equal"] = bool(np.array_equal(np.isinf(got_pc[sub]), np.isinf(want_pc)))
+        extra["pc_lsa"]["inf_rows"] = int((~fin).sum())
         extra["apfd_lsa_order"] = float(apfd_from_order(fault, np.argsort(-got_all)))
 
         def cpu():

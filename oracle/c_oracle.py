@@ -22,7 +22,7 @@ _lib = None
 
 def build(force: bool = False) -> str:
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
-        cmd = ["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+        cmd = ["gcc", "-O3", "-mavx2", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
                _SRC, "-o", _SO, "-lm"]
         subprocess.run(cmd, check=True)
     return _SO
@@ -68,7 +68,12 @@ def dsa(train, train_pred, test, test_pred, threads: int = 0):
     da = np.empty(m, dtype=train.dtype)
     db = np.empty(m, dtype=train.dtype)
     ia = np.empty(m, dtype=np.int64)
-    f = lib().oracle_dsa_f32 if train.dtype == np.float32 else lib().oracle_dsa_f64
+    nthreads = threads or max_threads()
+    by_rows = m * 4 < nthreads and n >= 4096          # few inputs, many train rows: parallel over train rows
+    if by_rows:
+        f = lib().oracle_dsa_rows_f32 if train.dtype == np.float32 else lib().oracle_dsa_rows_f64
+    else:
+        f = lib().oracle_dsa_f32 if train.dtype == np.float32 else lib().oracle_dsa_f64
     f(_p(train), _p(tp), C.c_int64(n), C.c_int64(d), _p(test), _p(sp), C.c_int64(m),
       _p(da), _p(db), _p(ia), C.c_int(threads or max_threads()))
     with np.errstate(divide="ignore", invalid="ignore"):

@@ -131,7 +131,7 @@ def shard_rows(labels: np.ndarray, num_classes: int, rank: int, world: int) -> n
     return np.sort(np.concatenate(keep)) if keep else np.zeros(0, dtype=np.int64)
 
 
-def span_tiles_for(total_tile_pairs: int, sms: int, per_sm: int = 6, lo: int = 2, hi: int = 32) -> int:
+def span_tiles_for(total_tile_pairs: int, sms: int, per_sm: int = 6, lo: int = 2, hi: int = 16) -> int:
     """Column tiles per work item: aim for ~per_sm items per SM so the static round-robin balances."""
     return int(min(hi, max(lo, round(total_tile_pairs / max(1, sms * per_sm)))))
 
@@ -321,6 +321,17 @@ def build_balanced_items(tiles, col_tile: int, n_cta: int, item_cost: float = 0.
     n_static = len(out)
     out.extend(pool)
     return np.asarray(out, dtype=np.int32).reshape(-1, 6), n_static
+
+
+def span_major(items: np.ndarray) -> np.ndarray:
+    """Order the streaming kernel's work list by (train span, query tile).  CTA b runs items b, b + G, ...,
+    so the CTAs that run at the same time then scan the SAME train rows for different query tiles: a train
+    tile comes out of HBM once and is shared through L2.  Query-tile-major order re-reads the whole packed
+    training set from HBM for every 128-row query tile — at C5's size (2.7 GB per rank) that made the
+    tensor-core pass HBM-bound at 128 flop/B (measured: 42 ms instead of 26 for 10k x 640k x 2048)."""
+    if items.shape[0] < 2:
+        return items
+    return np.ascontiguousarray(items[np.lexsort((items[:, 0], items[:, 2]))])
 
 
 def count_tile_pairs(q_off: np.ndarray, ranges_per_class, row_tile: int = _lib.ROW_TILE,
@@ -681,6 +692,7 @@ class NnEngine:
                     else:
                         pairs = count_tile_pairs(q_off, ranges, self.row_tile, self.col_tile)
                         items, _ = build_items(q_off, ranges, span_of(pairs), self.row_tile, self.col_tile)
+                    items = span_major(items)
                 flops = 2.0 * self.d * sum(int(q_off[c + 1] - q_off[c]) * sum(int(hi) - int(lo) for lo, hi in ranges[c])
                                            for c in range(self.num_classes))
                 flagged = bool(items.shape[0] and (items[:, 5] & 1).any())
@@ -1023,6 +1035,7 @@ class KdeEngine:
         q_off = np.array([0, m], dtype=np.int64)
         ranges = [[(0, self.n)]]
         items, slots = build_items(q_off, ranges, span_tiles_for(count_tile_pairs(q_off, ranges), self.sms))
+        items = span_major(items)
         items_dev = torch.from_numpy(items).to(self.dev, non_blocking=True)
         slots *= 2      # the kernel writes one partial per 128-column half of every span
         part_max = torch.full((slots, m), float("-inf"), dtype=torch.float32, device=self.dev)

@@ -102,7 +102,11 @@ def test_work_items_cover_every_pair_exactly_once():
         assert np.array_equal(cover, want)
         assert E.count_tile_pairs(q_off, ranges) >= items.shape[0]
     assert E.build_items(np.array([0, 0]), [[(0, 10)]], 2)[0].shape == (0, 6)
-    assert 2 <= E.span_tiles_for(10, 148) <= 32 and E.span_tiles_for(10 ** 7, 148) == 32
+    assert 2 <= E.span_tiles_for(10, 148) <= 16 and E.span_tiles_for(10 ** 7, 148) == 16
+    # span-major order: the same items, sorted by (train span, query tile)
+    sm = E.span_major(items)
+    assert sorted(map(tuple, sm.tolist())) == sorted(map(tuple, items.tolist()))
+    assert np.all(np.diff(sm[:, 2]) >= 0)
 
 
 def test_other_class_items_cover_every_pair_exactly_once():
