@@ -113,6 +113,55 @@ int tip_cam_buckets(const void* bucket, int bucket_dtype, int64_t n, int64_t d, 
                     int32_t* gain, uint32_t* covered, int32_t* newlist, int32_t* order, int32_t* state,
                     int32_t rounds, void* stream);
 
+/* ---- sibling coverage criteria and their fit step (neuron_coverage.py:52-62,97-173;
+ * aggregate_statistics.py:37-67 + welford==0.2.5) ------------------------------------------
+ * tip_cover_threshold: act n x d (TIP_F32/TIP_F64); mode
+ *   TIP_COVER_NAC   profile[n,d]   = act >  threshold                      (lo = hi = NULL)
+ *   TIP_COVER_SNAC  profile[n,d]   = act >= hi[d]
+ *   TIP_COVER_NBC   profile[n,d,2] = (act <= lo[d], act >= hi[d])
+ * lo / hi: d boundaries of stat_dtype, computed by the caller with the reference's NumPy expressions
+ * (min - s*std, max + s*std); comparisons run in NumPy's promoted dtype of (act, boundary), so the
+ * profile is bit-identical.  profile_u8 (one byte per entry: the reference's dense bool array) and
+ * bits (the same profile bit-packed for tip_cam_bits, tip_cover_packed_words(d) words per row and
+ * plane, NBC: 2 planes; layout in csrc/coverage.cu) are both optional; score[n] = number of set
+ * entries per sample (== sum_score, neuron_coverage.py:8-22). */
+#define TIP_COVER_NAC 0
+#define TIP_COVER_SNAC 1
+#define TIP_COVER_NBC 2
+int64_t tip_cover_packed_words(int64_t d);
+int tip_cover_threshold(const void* act, int act_dtype, int64_t n, int64_t d, const void* lo,
+                        const void* hi, int stat_dtype, double threshold, int mode, void* profile_u8,
+                        uint32_t* bits, int32_t* score, void* stream);
+/* Top-k neuron coverage of ONE layer (neuron_coverage.py:160-168): for every sample the k largest of its
+ * d_layer activations are marked in profile_u8[r * row_stride + col_off + i] (all entries of the layer's
+ * columns are written) and/or OR-ed into the packed words of neuron col_off + i (bits must be zero-filled
+ * by the caller; bit_words = words per row).  Equal values: the higher index wins (NumPy's unstable
+ * argsort leaves that case implementation-defined). */
+int tip_tknc(const void* act, int dtype, int64_t n, int64_t d_layer, int32_t k, void* profile_u8,
+             int64_t row_stride, int64_t col_off, uint32_t* bits, int64_t bit_words, void* stream);
+/* Streaming per-neuron statistics over a batch of n samples x d neurons: mins/maxs and welford==0.2.5's
+ * `add` applied sample by sample in the activation dtype (mean, m2 = sum of squared deviations; the caller
+ * keeps the integer count: count_before = samples folded in so far).  State arrays hold d values of
+ * `dtype`; initial state: mean = m2 = 0, mins = +inf, maxs = -inf. */
+int tip_stats_update(const void* act, int dtype, int64_t n, int64_t d, int64_t count_before, void* mean,
+                     void* m2, void* mins, void* maxs, void* stream);
+
+/* ---- Coverage-Additional Method over dense boolean profiles, bit-packed (prioritizers.py:16-45) ----
+ * tip_pack_bool: byte profile n x f (non-zero = covered) -> ceil(f/32) words per row.
+ * tip_cam_bits: bits n x words (any packing, the order of the picks does not depend on it).  One
+ * persistent cooperative kernel runs up to max_rounds greedy rounds: pick = first index of the largest
+ * gain, new = profile[pick] & ~covered, gain[i] -= popcount(profile[i] & new); it stops for good when
+ * the best gain is 0.  Caller-owned device state: gain[n] (init_gain != 0: initialised here to the row
+ * popcounts), covered2[2*words] zero-filled, cand_scratch[4*TIP_CAM_MAX_BLOCKS] int32, order[n],
+ * state[4] = {picks, done, -, -} zero-filled before the first call; call again with the same buffers
+ * (init_gain = 0) while state[1] == 0 && state[0] < n.  max_rounds must be even when more calls follow
+ * (the covered set is double-buffered by round parity). */
+#define TIP_CAM_MAX_BLOCKS 1024
+int tip_pack_bool(const void* profile_u8, int64_t n, int64_t f, uint32_t* bits, void* stream);
+int tip_cam_bits(const uint32_t* bits, int64_t n, int64_t words, int32_t* gain, uint32_t* covered2,
+                 int32_t* cand_scratch, int32_t* order, int32_t* state, int32_t max_rounds,
+                 int32_t init_gain, void* stream);
+
 /* ---- operand packing for the tensor-core pass ----------------------------------------
  * Packed row (bf16), D16 = round_up(d,16), one 16-wide tail block:
  *   segments == 1:  [ s*h(v) | tail ]                 v = fl32(x - center)
@@ -266,6 +315,12 @@ int tip_shard_winner_queries(tip_comm* comm, const void* gdist, const int32_t* g
  * columns (NULL = all), mu: d_out doubles, w: d_out x d_out fp32 row-major. */
 int tip_whiten(const void* x, int dtype, int64_t m, int64_t d_in, const int32_t* cols,
                int64_t d_out, const double* mu, const float* w, float* out, void* stream);
+
+/* out[m] (double) = sum_k y[row,k]^2 of a whitened matrix y (m x d fp32, from tip_whiten): the squared
+ * Mahalanobis distance to one centre (MDSA, surprise.py:374-393: sklearn EmpiricalCovariance.mahalanobis) or
+ * the quadratic form of one mixture component (MLSA, surprise.py:498-520: sklearn
+ * _estimate_log_gaussian_prob, y = (x - mu_k) . precisions_cholesky_k). */
+int tip_row_sqnorm(const float* y, int64_t m, int64_t d, double* out, void* stream);
 
 /* q_pack / t_pack from tip_pair_prep(segments=3, scale=1, norm_coef=-0.5 on the train side).
  * For every work item writes the partial (max_i a_ij, sum_i exp(a_ij - max)) of

@@ -221,11 +221,103 @@ def cam_kmnc_cases(ref):
     print("cam over kmnc ok")
 
 
+def sibling_cases(ref):
+    """NAC / NBC / SNAC / TKNC (neuron_coverage.py:52-62,97-173) with the configurations of
+    handler_coverage.py:49-101, fitted on statistics from the reference's own AggregateStatisticsCollector
+    (welford==0.2.5 restated, see ref_harness), plus `cam` on each profile (handler_coverage.py:122-124) and the
+    surprise-coverage CAM of handler_surprise.py:101-115."""
+    agg = ref_harness.load_aggregate_statistics()
+    nc = ref.neuron_coverage
+    out = {}
+    rng = np.random.default_rng(71)
+    shapes = [(6, 5, 4), (37,), (3, 11)]                       # conv-like, dense, 2-D layers
+    n_train, n_test = 230, 90
+
+    def draw(n, scale):
+        return [np.maximum(rng.normal(size=(n,) + sh) * scale + 0.2, 0).astype(np.float32) for sh in shapes]
+
+    train = draw(n_train, 1.0)
+    col = agg.AggregateStatisticsCollector()
+    cuts = [0, 64, 128, 131, 230]                              # ragged badges, like the last batch of a dataset walk
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        col.track([l[a:b] for l in train])
+    mins, maxs, stds = col.get()
+    test = draw(n_test, 1.4)
+    test[1][0, 3] = maxs[1][3]                                 # exactly on a boundary (>= / <= matter)
+    test[1][1, 4] = mins[1][4]
+    for i, l in enumerate(train):
+        out[f"sib.train{i}"] = l
+    for i, l in enumerate(test):
+        out[f"sib.test{i}"] = l
+    out["sib.cuts"] = np.array(cuts)
+    for i in range(len(shapes)):
+        out[f"sib.min{i}"], out[f"sib.max{i}"], out[f"sib.std{i}"] = mins[i], maxs[i], stds[i]
+    metrics = {"NAC_0": nc.NAC(0.0), "NAC_0.75": nc.NAC(0.75),
+               "NBC_0": nc.NBC(mins, maxs, stds, 0), "NBC_0.5": nc.NBC(mins, maxs, stds, 0.5), "NBC_1": nc.NBC(mins, maxs, stds, 1),
+               "SNAC_0": nc.SNAC(maxs, stds, 0), "SNAC_0.5": nc.SNAC(maxs, stds, 0.5), "SNAC_1": nc.SNAC(maxs, stds, 1),
+               "TKNC_1": nc.TKNC(1), "TKNC_2": nc.TKNC(2), "TKNC_3": nc.TKNC(3)}
+    for name, m in metrics.items():
+        score, prof = m([l.copy() for l in test])
+        out[f"sib.{name}.score"], out[f"sib.{name}.profile"] = score, prof
+        out[f"sib.{name}.cam"] = np.array(list(ref.prioritizers.cam(score, prof.copy())), dtype=np.int64)
+    # float64 activations / statistics
+    tr64 = [l.astype(np.float64) for l in train[:2]]
+    col = agg.AggregateStatisticsCollector()
+    col.track(tr64)
+    mn, mx, sd = col.get()
+    te64 = [l.astype(np.float64) for l in test[:2]]
+    for i in range(2):
+        out[f"sib64.min{i}"], out[f"sib64.max{i}"], out[f"sib64.std{i}"] = mn[i], mx[i], sd[i]
+    s, p = nc.NBC(mn, mx, sd, 0.5)(te64)
+    out["sib64.NBC_0.5.score"], out["sib64.NBC_0.5.profile"] = s, p
+    # surprise-coverage CAM: 1000 buckets up to the largest observed value (handler_surprise.py:101-115, NUM_SC_BUCKETS)
+    sa = np.abs(rng.normal(size=400)) * 3
+    sa[17] = sa.max()                                          # the maximum itself falls outside the half-open last bucket
+    mapper = ref.surprise.SurpriseCoverageMapper(1000, np.max(sa))
+    prof = mapper.get_coverage_profile(sa)
+    out["sc.values"], out["sc.profile"] = sa, prof
+    out["sc.cam"] = np.array(list(ref.prioritizers.cam(sa, prof.copy())), dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "siblings_reference.npz"), **out)
+    print("siblings ok", {k: int(out[f"sib.{k}.score"].sum()) for k in metrics})
+
+
+def mdsa_mlsa_cases(ref):
+    """MDSA / MLSA (surprise.py:374-393,498-520) and their per-class forms (handler_surprise.py:28-33) run by the
+    reference's own classes on top of this container's scikit-learn.  GaussianMixture's fit draws from NumPy's
+    global RNG, so the fitted parameters are stored next to the outputs."""
+    out = {}
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(3000, 400, 48, 4, seed=91, spread=1.5)
+    xtr, xte = xtr.astype(np.float64), xte.astype(np.float64)
+    out["x.xtr"], out["x.ytr"], out["x.xte"], out["x.pte"] = xtr, ytr, xte, pte
+    m = quiet(ref.surprise.MDSA, xtr)
+    out["mdsa.out"] = m(xte)
+    out["mdsa.location"], out["mdsa.precision"] = m.covariance_matrix.location_, m.covariance_matrix.get_precision()
+    pc = quiet(ref.surprise.MultiModalSA.build_by_class, xtr, ytr, lambda x, y: ref.surprise.MDSA(x))
+    out["pcmdsa.out"] = pc(xte, pte)
+    np.random.seed(1234)
+    g = quiet(ref.surprise.MLSA, xtr, 3)
+    out["mlsa.out"] = g(xte)
+    out["mlsa.means"], out["mlsa.prec_chol"], out["mlsa.weights"] = g.gmm.means_, g.gmm.precisions_cholesky_, g.gmm.weights_
+    # a rank-deficient covariance (duplicated column): sklearn's pinvh precision is singular
+    xs = np.concatenate([xtr[:, :10], xtr[:, :1]], axis=1)
+    ms = quiet(ref.surprise.MDSA, xs)
+    out["sing.xtr"], out["sing.xte"] = xs, np.concatenate([xte[:, :10], xte[:, :1]], axis=1)
+    out["sing.out"] = ms(out["sing.xte"])
+    np.savez_compressed(os.path.join(OUT, "mdsa_mlsa_reference.npz"), **out)
+    print("mdsa/mlsa ok", float(out["mdsa.out"].mean()), float(out["mlsa.out"].mean()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = ref_harness.load()
     if len(sys.argv) > 1 and sys.argv[1] == "cam_kmnc":      # add this file without touching the others
         cam_kmnc_cases(ref)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "mdsa_mlsa":
+        mdsa_mlsa_cases(ref)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "siblings":
+        sibling_cases(ref)
         sys.exit(0)
     dsa_cases(ref)
     lsa_cases(ref)
@@ -233,4 +325,6 @@ if __name__ == "__main__":
     gini_apfd_cases(ref)
     prioritizer_cases(ref)
     cam_kmnc_cases(ref)
+    sibling_cases(ref)
+    mdsa_mlsa_cases(ref)
     print("sizes:", {f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))})

@@ -321,6 +321,113 @@ def kmnc_buckets_oracle(mins, maxs, sections: int, activations) -> Tuple[np.ndar
 
 
 # --------------------------------------------------------------------------------------
+# NAC / NBC / SNAC / TKNC (neuron_coverage.py:52-62, 97-173) and their fit
+# (src/dnn_test_prio/aggregate_statistics.py:12-67 on welford==0.2.5)
+# --------------------------------------------------------------------------------------
+def _sum_score(prof: np.ndarray) -> np.ndarray:
+    total = int(np.prod(prof[0].shape))
+    dt = np.int16 if total <= np.iinfo(np.int16).max else (np.int32 if total <= np.iinfo(np.int32).max else np.int64)
+    return np.sum(prof.reshape(prof.shape[0], -1), axis=1, dtype=dt)                  # :8-22
+
+
+def _cat(layers):
+    return np.concatenate([np.asarray(l).flatten() for l in layers])
+
+
+def nac_oracle(threshold, activations):
+    prof = flatten_rows(list(activations)) > threshold                                # :60-61
+    return _sum_score(prof), prof
+
+
+def nbc_oracle(mins, maxs, stds, scaler, activations):
+    lo = _cat(mins) - scaler * _cat(stds)                                             # :113-114
+    hi = _cat(maxs) + scaler * _cat(stds)
+    act = flatten_rows(list(activations))
+    prof = np.zeros((act.shape[0], act.shape[1], 2), dtype=bool)
+    prof[..., 0] = act <= lo                                                          # :129-130
+    prof[..., 1] = act >= hi
+    return _sum_score(prof), prof
+
+
+def snac_oracle(maxs, stds, scaler, activations):
+    hi = _cat(maxs) + scaler * _cat(stds)                                             # :142
+    prof = flatten_rows(list(activations)) >= hi                                      # :146-147
+    return _sum_score(prof), prof
+
+
+def tknc_oracle(top_neurons: int, activations):
+    """neuron_coverage.py:159-173.  np.argsort is unstable: for exactly tied activations at the k-th rank the
+    marked neuron is implementation-defined (use tie-free inputs when comparing)."""
+    per_layer = []
+    for layer in activations:
+        flat = layer.reshape((layer.shape[0], -1))
+        top = np.argsort(flat, axis=1)[..., -top_neurons:]
+        mark = np.zeros_like(flat, dtype=bool)
+        np.put_along_axis(mark, top, True, axis=1)
+        per_layer.append(mark)
+    prof = np.concatenate(per_layer, axis=1)
+    return _sum_score(prof), prof
+
+
+def stats_oracle(badges):
+    """AggregateStatisticsCollector.track per badge, then get() (aggregate_statistics.py:37-67): running
+    np.minimum / np.maximum and, per layer, welford==0.2.5's `Welford`: initialised with the first sample
+    (mean = x, s = 0), then `add` per sample — count += 1; delta = x - m; m += delta / count;
+    s += delta * (x - m) — in the dtype NumPy gives the state (float32 for float32 activations);
+    std = sqrt(s / (count - 1)).  badges: list of badges, each a list of layer arrays [n_b, ...]."""
+    mins = maxs = ms = ss = None
+    count = 0
+    for badge in badges:
+        badge = [np.asarray(l) for l in badge]
+        if mins is None:
+            mins = [l[0] for l in badge]
+            maxs = [l[0] for l in badge]
+            ms = [np.mean(np.expand_dims(l[0], 0), axis=0) for l in badge]
+            ss = [np.var(np.expand_dims(l[0], 0), axis=0, ddof=0) * 1 for l in badge]
+            count = 1
+            badge = [l[1:] for l in badge]
+        mins = [np.minimum(mins[i], np.min(badge[i], axis=0)) for i in range(len(badge))] if badge[0].shape[0] else mins
+        maxs = [np.maximum(maxs[i], np.max(badge[i], axis=0)) for i in range(len(badge))] if badge[0].shape[0] else maxs
+        for r in range(badge[0].shape[0]):
+            count += 1
+            for i, l in enumerate(badge):
+                delta = l[r] - ms[i]
+                ms[i] += delta / count
+                ss[i] += delta * (l[r] - ms[i])
+    stds = [np.sqrt(s / (count - 1)) if count > 1 else np.sqrt(np.full(s.shape, np.nan)) for s in ss]
+    return mins, maxs, stds
+
+
+def cam_oracle(scores: np.ndarray, profiles: np.ndarray) -> np.ndarray:
+    """Coverage-additional order on a dense boolean profile, restated from prioritizers.py:16-59."""
+    scores = np.asarray(scores).copy()
+    prof = np.asarray(profiles).reshape((profiles.shape[0], -1)).copy()
+    gain = np.sum(prof, axis=1).flatten()                                             # :22
+    remaining = prof.shape[1]
+    yielded = np.zeros(scores.shape[0], dtype=bool)
+    order = []
+    while remaining > 0 and prof.shape[0] > 0:
+        nxt = int(np.argmax(gain))                                                    # :26 (first index on ties)
+        fresh = gain[nxt]
+        if fresh == 0:                                                                # :30-31
+            break
+        order.append(nxt)
+        yielded[nxt] = True
+        cols = prof[nxt].nonzero()[0]
+        remaining -= fresh
+        gain = gain - np.sum(prof[:, cols], axis=1)                                   # :38-39
+        prof[:, cols] = 0
+    if scores.shape[0]:
+        floor = np.min(scores) - 1                                                    # :48-52
+        scores[yielded] = floor - 1
+        for x in np.argsort(-scores):
+            if scores[x] < floor:
+                break
+            order.append(int(x))
+    return np.array(order, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------------------
 # APFD / CTM (apfd.py:8-19, prioritizers.py:7-13, eval_apfd_table.py:86,101)
 # --------------------------------------------------------------------------------------
 def apfd_oracle(is_fault: np.ndarray, order) -> float:

@@ -19,6 +19,11 @@ the container's newer stack:
                              `StableGaussianKDE`, `LSA` and `MultiModalSA` run unmodified.
                              Its evaluate() is the literal loop nest of
                              `_stats.gaussian_kernel_estimate` (C port: tip_oracle.c).
+  4. `welford`             — welford==0.2.5 (requirements.txt:6) is not installable offline; a stub
+                             module restates its `Welford` class (init / add / add_all / var_s) so that
+                             the reference's own `AggregateStatisticsCollector`
+                             (src/dnn_test_prio/aggregate_statistics.py) runs unmodified
+                             (`load_aggregate_statistics`).
 """
 from __future__ import annotations
 
@@ -124,6 +129,96 @@ def _uwiz_stub() -> types.ModuleType:
     q.Quantifier, q.MaxSoftmax = Quantifier, MaxSoftmax
     uw.quantifiers, uw.ProblemType = q, ProblemType
     return uw
+
+
+class Welford025:
+    """welford==0.2.5 `welford.Welford`, the subset aggregate_statistics.py touches: constructed from a
+    (1, ...) array (`init`), `add_all` = sequential `add` per sample, `var_s` = s / (count - 1).  Mean and
+    the sum of squared deviations keep the dtype NumPy gives them (float32 for float32 activations)."""
+
+    def __init__(self, elements=None):
+        self._shape = None
+        self._count, self._m, self._s = 0, None, None
+        if elements is not None:
+            self.init(elements)
+
+    def init(self, elements):
+        self._shape = elements[0].shape
+        self._count = elements.shape[0]
+        self._m = np.mean(elements, axis=0)
+        self._s = np.var(elements, axis=0, ddof=0) * elements.shape[0]
+
+    def add(self, element, backup_flg=True):
+        if self._shape is None:
+            self._shape = element.shape
+            self._m, self._s = np.zeros(element.shape), np.zeros(element.shape)
+        self._count += 1
+        delta = element - self._m
+        self._m += delta / self._count
+        self._s += delta * (element - self._m)
+
+    def add_all(self, elements, backup_flg=True):
+        for elem in elements:
+            self.add(elem, backup_flg=False)
+
+    @property
+    def count(self):
+        return self._count
+
+    @property
+    def mean(self):
+        return self._m
+
+    @property
+    def var_s(self):
+        if self._count <= 0:
+            return None
+        if self._count <= 1:
+            return np.full(self._shape, np.nan)
+        return self._s / (self._count - 1)
+
+    @property
+    def var_p(self):
+        if self._count <= 0:
+            return None
+        return self._s / self._count
+
+
+def _welford_stub() -> types.ModuleType:
+    w = types.ModuleType("welford")
+    w.Welford = Welford025
+    return w
+
+
+def load_aggregate_statistics():
+    """The reference's `src.dnn_test_prio.aggregate_statistics` module (unmodified) on top of the welford stub."""
+    if not available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    sys.modules.setdefault("welford", _welford_stub())  # shim 4
+    saved_path = list(sys.path)
+    saved_src = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
+    for k in saved_src:
+        del sys.modules[k]
+    try:
+        here = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+        sys.path[:] = [REFERENCE_ROOT] + [p for p in saved_path if os.path.abspath(p or ".") != here]
+        import importlib.util as _ilu
+
+        importlib.invalidate_caches()
+
+        # the package __init__ of src.dnn_test_prio is empty, but import the one file only: its siblings need TensorFlow
+        timer = importlib.import_module("src.core.timer")
+        assert os.path.abspath(timer.__file__).startswith(os.path.abspath(REFERENCE_ROOT))
+        spec = _ilu.spec_from_file_location(
+            "tip_ref_aggregate_statistics", os.path.join(REFERENCE_ROOT, "src", "dnn_test_prio", "aggregate_statistics.py"))
+        mod = _ilu.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    finally:
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+            del sys.modules[k]
+        sys.modules.update(saved_src)
 
 
 _loaded = {}

@@ -14,6 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200tip.so")
 
 TIP_F32, TIP_F64, TIP_BF16, TIP_I16, TIP_I32 = 0, 1, 2, 3, 4
+COVER_NAC, COVER_SNAC, COVER_NBC = 0, 1, 2
+CAM_MAX_BLOCKS = 1024
 ROLE_QUERY, ROLE_TRAIN = 0, 1
 RANGE_SAME_CLASS, RANGE_OTHER_CLASSES = 0, 1
 ROW_TILE, COL_TILE = 128, 256
@@ -35,6 +37,12 @@ _SIGNATURES = {
     "tip_deepgini": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, _vp]),
     "tip_kmnc": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, C.c_int, _i32, _vp, C.c_int, _vp, _vp]),
     "tip_cam_buckets": (C.c_int, [_vp, C.c_int, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "tip_cover_packed_words": (_i64, [_i64]),
+    "tip_cover_threshold": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, C.c_int, C.c_double, C.c_int, _vp, _vp, _vp, _vp]),
+    "tip_tknc": (C.c_int, [_vp, C.c_int, _i64, _i64, _i32, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "tip_stats_update": (C.c_int, [_vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "tip_pack_bool": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    "tip_cam_bits": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "tip_pair_pitch": (_i64, [_i64, C.c_int]),
     "tip_pair_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, C.c_int, C.c_int, _f32, _f32, _vp, _vp, _vp, _vp]),
     "tip_nn_filter": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _f32, _vp, _vp,
@@ -57,6 +65,7 @@ _SIGNATURES = {
     "tip_shard_winner_queries": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _vp, _vp]),
     "tip_whiten": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "tip_row_sqnorm": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "tip_kde_lse": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),
     "tip_kde_combine": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "tip_nn_filter_tile": (C.c_int, [_i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -6,8 +6,10 @@ pass computes, per (sample, neuron), the section index i with
 rounding) and the per-sample count, i.e. the compact form of the reference's dense
 N x D x sections boolean profile.  `KMNC.__call__` expands it to the dense profile only because
 the reference API returns one (consumers: `cam`, handler_coverage.py:122-124); `buckets()` is the
-compact entry point for large `sections`.  NAC / NBC / SNAC / TKNC keep the reference's contract
-with host NumPy (next rows).
+compact entry point for large `sections`.  NAC / NBC / SNAC / TKNC (neuron_coverage.py:52-62,97-173)
+run on the GPU as well (csrc/coverage.cu): the boundaries are the reference's NumPy expressions, the
+comparisons happen in NumPy's promoted dtype, so scores and profiles are bit-identical; every class
+also offers `packed(...)`, the same profile bit-packed in HBM for `prioritizers.cam_from_bits`.
 """
 from __future__ import annotations
 
@@ -45,16 +47,103 @@ class CoverageMethod(abc.ABC):
         ...
 
 
-class NAC(CoverageMethod):
-    """Neuron activation coverage: a > threshold."""
+def _device_activations(activations):
+    """Activations (NumPy array / list of layers / torch CUDA tensors) as one contiguous [N, D] matrix in
+    HBM plus its NumPy dtype; float32 / float64 are kept, everything else is scored in float32... after
+    NumPy's promotion with the boundaries (done by the caller)."""
+    import torch
+
+    from .. import engine as E
+
+    dev = E.require_cuda()
+    dev_act = E.device_matrix(activations)
+    if dev_act is not None:
+        act = dev_act if dev_act.dtype in (torch.float32, torch.float64) else dev_act.to(torch.float32)
+        return act.contiguous(), E.NP_DTYPE[act.dtype]
+    if isinstance(activations, np.ndarray):
+        act = activations.reshape((activations.shape[0], -1))
+    elif len(activations) == 1:
+        act = np.reshape(activations[0], (activations[0].shape[0], -1))
+    else:
+        act = flatten_layers(activations)
+    if act.dtype not in (np.float32, np.float64):
+        act = act.astype(np.result_type(act.dtype, np.float32))
+        if act.dtype not in (np.float32, np.float64):
+            raise TypeError(f"unsupported activation dtype {act.dtype}")
+    return E.to_device(act, dev), act.dtype
+
+
+class _ThresholdCoverage(CoverageMethod):
+    """Shared launch path of NAC / SNAC / NBC (tip_cover_threshold)."""
+
+    _mode = None
+    _planes = 1
+
+    def _bounds(self):
+        """(lo, hi, scalar threshold): NumPy arrays / None as the criterion defines them"""
+        raise NotImplementedError
+
+    def _run(self, activations, want_profile: bool, want_bits: bool):
+        import torch
+
+        from .. import _lib
+        from .. import engine as E
+
+        lib = _lib.load()
+        act, act_dt = _device_activations(activations)
+        dev = act.device
+        n, d = act.shape
+        lo, hi, thr = self._bounds()
+        if hi is not None:
+            assert d == hi.shape[0], "activation width does not match the boundary statistics"
+            stat_dt = np.result_type(hi.dtype, np.float32) if hi.dtype.kind != "f" else hi.dtype
+            if stat_dt not in (np.float32, np.float64):
+                stat_dt = np.dtype(np.float64)
+            key = ("bounds", str(stat_dt), str(dev))
+            if getattr(self, "_dev_key", None) != key:
+                self._dev_hi = E.to_device(np.ascontiguousarray(hi, dtype=stat_dt), dev)
+                self._dev_lo = None if lo is None else E.to_device(np.ascontiguousarray(lo, dtype=stat_dt), dev)
+                self._dev_key = key
+            lo_dev, hi_dev = self._dev_lo, self._dev_hi
+            thr_val = 0.0
+        else:
+            # NAC: `activations > threshold` with a Python / NumPy scalar: NumPy compares in the promoted dtype
+            stat_dt = np.result_type(act_dt, thr)
+            if stat_dt not in (np.float32, np.float64):
+                stat_dt = np.dtype(np.float64)
+            lo_dev = hi_dev = None
+            thr_val = float(np.asarray(thr).astype(stat_dt))
+        profile = torch.empty((n, d) if self._planes == 1 else (n, d, 2), dtype=torch.bool, device=dev) if want_profile else None
+        words = int(lib.tip_cover_packed_words(d))
+        bits = torch.empty((n, self._planes * words), dtype=torch.int32, device=dev) if want_bits else None
+        score = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.check(lib.tip_cover_threshold(E._p(act), E.tip_dtype(act_dt), n, d, E._p(lo_dev), E._p(hi_dev),
+                                           E.tip_dtype(stat_dt), thr_val, self._mode, E._p(profile), E._p(bits),
+                                           E._p(score), E._stream()), "tip_cover_threshold")
+        return score, profile, bits, d
+
+    def __call__(self, activations: List[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+        score, profile, _, d = self._run(activations, True, False)
+        return score.cpu().numpy().astype(_score_dtype(d * self._planes)), profile.cpu().numpy()
+
+    def packed(self, activations):
+        """(scores int32 [N], profile bit-packed [N, words] int32) as CUDA tensors — nothing leaves HBM; feed
+        to `prioritizers.cam_from_bits`."""
+        score, _, bits, _ = self._run(activations, False, True)
+        return score, bits
+
+
+class NAC(_ThresholdCoverage):
+    """Neuron activation coverage: a > threshold (neuron_coverage.py:52-62)."""
+
+    _mode = 0
 
     def __init__(self, cov_threshold: float):
         super().__init__()
         self.cov_threshold = cov_threshold
 
-    def __call__(self, activations):
-        prof = flatten_layers(activations) > self.cov_threshold
-        return sum_score(prof), prof
+    def _bounds(self):
+        return None, None, self.cov_threshold
 
 
 class KMNC(CoverageMethod):
@@ -137,24 +226,29 @@ class KMNC(CoverageMethod):
         return score.astype(_score_dtype(d * self.sections)), profiles
 
 
-class NBC(CoverageMethod):
-    """Neuron boundary coverage: below min - s*std or above max + s*std."""
+class NBC(_ThresholdCoverage):
+    """Neuron boundary coverage: at or below min - s*std, at or above max + s*std (neuron_coverage.py:97-132);
+    profile [N, D, 2]."""
+
+    _mode = 2
+    _planes = 2
 
     def __init__(self, mins, maxs, stds, scaler: float):
         super().__init__()
         lo = np.concatenate([np.asarray(l).flatten() for l in mins])
         hi = np.concatenate([np.asarray(l).flatten() for l in maxs])
         sd = np.concatenate([np.asarray(l).flatten() for l in stds])
-        self.min_boundaries, self.max_boundaries = lo - scaler * sd, hi + scaler * sd
+        self.min_boundaries, self.max_boundaries = lo - scaler * sd, hi + scaler * sd     # :113-114, same NumPy expressions
 
-    def __call__(self, activations):
-        act = flatten_layers(activations)
-        prof = np.stack([act <= self.min_boundaries, act >= self.max_boundaries], axis=-1)
-        return sum_score(prof), prof
+    def _bounds(self):
+        dt = np.result_type(self.min_boundaries.dtype, self.max_boundaries.dtype)
+        return self.min_boundaries.astype(dt), self.max_boundaries.astype(dt), None
 
 
-class SNAC(CoverageMethod):
-    """Strong neuron activation coverage: at or above max + s*std."""
+class SNAC(_ThresholdCoverage):
+    """Strong neuron activation coverage: at or above max + s*std (neuron_coverage.py:135-148)."""
+
+    _mode = 1
 
     def __init__(self, maxs, stds, scaler: float):
         super().__init__()
@@ -162,25 +256,57 @@ class SNAC(CoverageMethod):
         sd = np.concatenate([np.asarray(l).flatten() for l in stds])
         self.max_boundaries = hi + scaler * sd
 
-    def __call__(self, activations):
-        prof = flatten_layers(activations) >= self.max_boundaries
-        return sum_score(prof), prof
+    def _bounds(self):
+        return None, self.max_boundaries, None
 
 
 class TKNC(CoverageMethod):
-    """Top-k neuron coverage, per layer."""
+    """Top-k neuron coverage, per layer (neuron_coverage.py:151-173).  Equal activations at the k-th rank:
+    the higher index is marked (NumPy's unstable argsort leaves that case open; the reference's own test
+    accepts either outcome)."""
 
     def __init__(self, top_neurons: int):
         super().__init__()
         self.top_neurons = top_neurons
 
-    def __call__(self, activations):
-        per_layer = []
+    def _run(self, activations, want_profile: bool, want_bits: bool):
+        import torch
+
+        from .. import _lib
+        from .. import engine as E
+
+        lib = _lib.load()
+        dev = E.require_cuda()
+        layers = []
         for layer in activations:
-            flat = layer.reshape((layer.shape[0], -1))
-            top = np.argsort(flat, axis=1)[..., -self.top_neurons:]
-            mark = np.zeros_like(flat, dtype=bool)
-            np.put_along_axis(mark, top, True, axis=1)
-            per_layer.append(mark)
-        prof = flatten_layers(per_layer)
-        return sum_score(prof), prof
+            if isinstance(layer, torch.Tensor):
+                flat = layer.reshape(layer.shape[0], -1)
+                flat = flat if flat.dtype in (torch.float32, torch.float64) else flat.to(torch.float32)
+                layers.append(flat.to(dev).contiguous())
+            else:
+                flat = np.reshape(layer, (layer.shape[0], -1))
+                if flat.dtype not in (np.float32, np.float64):
+                    flat = flat.astype(np.result_type(flat.dtype, np.float32))
+                layers.append(E.to_device(flat, dev))
+        n = layers[0].shape[0]
+        total = sum(int(l.shape[1]) for l in layers)
+        profile = torch.empty((n, total), dtype=torch.bool, device=dev) if want_profile else None
+        words = int(lib.tip_cover_packed_words(total))
+        bits = torch.zeros((n, words), dtype=torch.int32, device=dev) if want_bits else None
+        off = 0
+        for l in layers:
+            _lib.check(lib.tip_tknc(E._p(l), E.tip_dtype(l.dtype), n, l.shape[1], int(self.top_neurons), E._p(profile),
+                                    total, off, E._p(bits), words, E._stream()), "tip_tknc")
+            off += int(l.shape[1])
+        score = sum(min(int(self.top_neurons), int(l.shape[1])) for l in layers)
+        return score, profile, bits, n, total
+
+    def __call__(self, activations):
+        score, profile, _, n, total = self._run(activations, True, False)
+        return np.full(n, score, dtype=_score_dtype(total)), profile.cpu().numpy()
+
+    def packed(self, activations):
+        import torch
+
+        score, _, bits, n, _ = self._run(activations, False, True)
+        return torch.full((n,), score, dtype=torch.int32, device=bits.device), bits

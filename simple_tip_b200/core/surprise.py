@@ -202,32 +202,121 @@ class MultiModalSA(SA):
         return res
 
 
+def _psd_factor(precision: np.ndarray) -> np.ndarray:
+    """W with W . W^T = precision for a symmetric positive SEMI-definite matrix (float64, host): eigenvectors
+    scaled by the square roots of the (clipped) eigenvalues, so |(x - mu) . W|^2 = (x - mu)^T P (x - mu) also when
+    sklearn's pinvh produced a singular precision."""
+    vals, vecs = np.linalg.eigh((precision + precision.T) / 2.0)
+    return vecs * np.sqrt(np.clip(vals, 0.0, None))[None, :]
+
+
+def _device_rows(activations):
+    """[N, D] device matrix (float32 / float64) from NumPy arrays, lists of layers or torch CUDA tensors."""
+    import torch
+
+    from .. import engine as E
+
+    dev = E.require_cuda()
+    x = E.device_matrix(activations)
+    if x is None:
+        a = _flatten_layers(activations)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        x = E.to_device(a, dev)
+    elif x.dtype not in (torch.float32, torch.float64):
+        x = x.to(torch.float32)
+    return x.contiguous()
+
+
 class MDSA(SA):
-    """Mahalanobis distance (surprise.py:374-393): sklearn call, host."""
+    """Mahalanobis-distance surprise adequacy (surprise.py:374-393): squared Mahalanobis distance to the mean of
+    the training traces.  Fit = sklearn's `EmpiricalCovariance` on the host exactly as in the reference (one
+    D x D covariance, its pseudo-inverse); score = whitening by a factor of the precision + squared row norm on
+    the GPU (tip_whiten + tip_row_sqnorm), float64 out like `EmpiricalCovariance.mahalanobis`."""
 
     def __init__(self, activations: Activations):
         super().__init__()
         from sklearn.covariance import EmpiricalCovariance
 
+        from .. import engine as E
+
+        host = E.device_matrix(activations)
+        acts = host.cpu().numpy() if host is not None else _flatten_layers(activations)
         self.covariance_matrix = EmpiricalCovariance()
-        self.covariance_matrix.fit(_flatten_layers(activations))
+        self.covariance_matrix.fit(acts)
+        self._width = int(acts.shape[1])
+        self._centres = None
+
+    def _upload(self):
+        import torch
+
+        from .. import engine as E
+
+        dev = E.require_cuda()
+        w = _psd_factor(np.asarray(self.covariance_matrix.get_precision(), dtype=np.float64))
+        mu = np.asarray(self.covariance_matrix.location_, dtype=np.float64)
+        self._centres = [(torch.from_numpy(mu).to(dev), torch.from_numpy(np.ascontiguousarray(w.astype(np.float32))).to(dev))]
 
     def __call__(self, activations, predictions=None, num_threads=None) -> np.ndarray:
-        return self.covariance_matrix.mahalanobis(_flatten_layers(activations))
+        from .. import engine as E
+
+        x = _device_rows(activations)
+        if x.ndim != 2 or int(x.shape[1]) != self._width:
+            raise ValueError(f"X has {tuple(x.shape)[1:]} features, but MDSA was fitted with {self._width} features")
+        if self._centres is None:
+            self._upload()
+        return E.quadratic_forms(x, self._centres)[0].cpu().numpy()
 
 
 class MLSA(SA):
-    """GMM negative log-likelihood (surprise.py:498-520): sklearn call, host."""
+    """Multimodal likelihood surprise adequacy (surprise.py:498-520): negative log-likelihood under a Gaussian
+    mixture.  Fit = sklearn's `GaussianMixture` on the host as in the reference; score: per component
+    y = (x - mu_k) . precisions_cholesky_k on the GPU (sklearn `_estimate_log_gaussian_prob`), squared row norms,
+    then `-logsumexp_k(log w_k - (D log 2pi + |y|^2) / 2 + log det chol_k)` in float64 on the host — the tail of
+    `GaussianMixture.score_samples`."""
 
     def __init__(self, activations: Activations, num_components: int = 2):
         super().__init__()
         from sklearn.mixture import GaussianMixture
 
+        from .. import engine as E
+
+        host = E.device_matrix(activations)
+        acts = host.cpu().numpy() if host is not None else _flatten_layers(activations)
         self.gmm = GaussianMixture(n_components=num_components)
-        self.gmm.fit(_flatten_layers(activations))
+        self.gmm.fit(acts)
+        self._width = int(acts.shape[1])
+        self._centres = None
+
+    def _upload(self):
+        import torch
+
+        from .. import engine as E
+
+        dev = E.require_cuda()
+        if self.gmm.covariance_type != "full":
+            raise NotImplementedError("only sklearn's default covariance_type='full' (what the reference uses)")
+        chol = np.asarray(self.gmm.precisions_cholesky_, dtype=np.float64)
+        self._centres = [(torch.from_numpy(np.ascontiguousarray(self.gmm.means_[k], dtype=np.float64)).to(dev),
+                          torch.from_numpy(np.ascontiguousarray(chol[k].astype(np.float32))).to(dev))
+                         for k in range(chol.shape[0])]
+        # log det of the precision Cholesky factors (sklearn _compute_log_det_cholesky, 'full')
+        self._log_det = np.array([np.sum(np.log(np.diag(chol[k]))) for k in range(chol.shape[0])])
+        self._log_w = np.log(np.asarray(self.gmm.weights_, dtype=np.float64))
 
     def __call__(self, activations, predictions=None, num_threads=0) -> np.ndarray:
-        return -self.gmm.score_samples(_flatten_layers(activations))
+        from scipy.special import logsumexp
+
+        from .. import engine as E
+
+        x = _device_rows(activations)
+        if x.ndim != 2 or int(x.shape[1]) != self._width:
+            raise ValueError(f"X has {tuple(x.shape)[1:]} features, but MLSA was fitted with {self._width} features")
+        if self._centres is None:
+            self._upload()
+        q = E.quadratic_forms(x, self._centres).cpu().numpy()            # [K, m]
+        log_prob = -0.5 * (self._width * np.log(2 * np.pi) + q) + self._log_det[:, None]
+        return -logsumexp(log_prob + self._log_w[:, None], axis=0)
 
 
 # ------------------------------------------------------------------------------------------

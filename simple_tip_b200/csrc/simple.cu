@@ -645,6 +645,20 @@ __global__ void __launch_bounds__(256) kde_combine_kernel(const float* __restric
   os[row] = sum;
 }
 
+// out[row] = sum_k y[row, k]^2 accumulated in double (one warp per row): the squared Mahalanobis distance /
+// the Gaussian quadratic form of a whitened row (MDSA, MLSA)
+__global__ void __launch_bounds__(256) row_sqnorm_kernel(const float* __restrict__ y, int64_t m, int64_t d,
+                                                         double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= m) return;
+  const float* r = y + row * d;
+  double acc = 0.0;
+  for (int64_t k = lane; k < d; k += 32) acc += (double)r[k] * (double)r[k];
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+
 }  // namespace tip
 
 // =============================================================================================
@@ -842,6 +856,15 @@ extern "C" int tip_whiten(const void* x, int dtype, int64_t m, int64_t d_in, con
     whiten_kernel<double><<<grid, 256, 0, st>>>((const double*)x, m, d_in, cols, (int)d_out, mu, w, out);
   else
     TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
+}
+
+extern "C" int tip_row_sqnorm(const float* y, int64_t m, int64_t d, double* out, void* stream) {
+  TIP_REQUIRE(y && out, "null pointer");
+  TIP_REQUIRE(m >= 0 && d >= 1, "shape");
+  if (m == 0) return TIP_OK;
+  row_sqnorm_kernel<<<(unsigned)((m + 7) / 8), 256, 0, (cudaStream_t)stream>>>(y, m, d, out);
   TIP_LAUNCH_CHECK();
   return TIP_OK;
 }

@@ -1061,3 +1061,17 @@ def whiten(x: torch.Tensor, cols: Optional[torch.Tensor], mu: torch.Tensor, w: t
     _lib.check(lib.tip_whiten(_p(x), tip_dtype(x.dtype), m, d_in, _p(cols), d_out, _p(mu), _p(w), _p(out), _stream()),
                "tip_whiten")
     return out
+
+
+def quadratic_forms(x, centres: Sequence[Tuple[torch.Tensor, torch.Tensor]], cols: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q[k, j] = |(x_j - mu_k) . W_k|^2 for every (mu_k [d] float64, W_k [d, d] float32) pair: whitening on the
+    GPU (tip_whiten, centred first) + a double-accumulated row norm (tip_row_sqnorm).  x: [m, d_in] device
+    matrix (float32 / float64).  Returns float64 [len(centres), m] on the device."""
+    lib = _lib.load()
+    m = x.shape[0]
+    out = torch.empty((len(centres), m), dtype=torch.float64, device=x.device)
+    for k, (mu, w) in enumerate(centres):
+        y = whiten(x, cols, mu, w)
+        if m:
+            _lib.check(lib.tip_row_sqnorm(_p(y), m, y.shape[1], _p(out[k]), _stream()), "tip_row_sqnorm")
+    return out

@@ -604,3 +604,164 @@ def test_lsa_orders_give_the_oracles_apfd(golden):
     rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
     print(f"LSA max relative error without an absolute floor: {rel.max():.3e}; elements needing the 2e-4 floor: "
           f"{int((rel > 1e-4).sum())} of {rel.size}")
+
+
+# ------------------------------------------------------------------------------------------
+# NAC / NBC / SNAC / TKNC and the streaming statistics on the GPU, bit for bit against the
+# outputs of the reference's own classes; §8 f1: CAM over dense boolean / bit-packed profiles
+# ------------------------------------------------------------------------------------------
+def _sibling_metrics(nc, mins, maxs, stds):
+    m = {"NAC_0": nc.NAC(0.0), "NAC_0.75": nc.NAC(0.75), "TKNC_1": nc.TKNC(1), "TKNC_2": nc.TKNC(2), "TKNC_3": nc.TKNC(3)}
+    for sc in (0, 0.5, 1):
+        m[f"NBC_{sc}"] = nc.NBC(mins, maxs, stds, sc)
+        m[f"SNAC_{sc}"] = nc.SNAC(maxs, stds, sc)
+    return m
+
+
+def test_sibling_coverage_and_statistics_golden(golden):
+    torch = _torch()
+    import src.core.neuron_coverage as nc
+    from src.core.prioritizers import cam, cam_from_bits
+    from src.dnn_test_prio.aggregate_statistics import AggregateStatisticsCollector
+
+    s = golden("siblings_reference.npz")
+    train = [s[f"sib.train{i}"] for i in range(3)]
+    test = [s[f"sib.test{i}"] for i in range(3)]
+    cuts = s["sib.cuts"]
+    col = AggregateStatisticsCollector()
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        col.track([l[a:b] for l in train])
+    mins, maxs, stds = col.get()
+    for i in range(3):
+        for got, key in ((mins[i], "min"), (maxs[i], "max"), (stds[i], "std")):
+            want = s[f"sib.{key}{i}"]
+            assert got.shape == want.shape and got.dtype == want.dtype and np.array_equal(got, want), (key, i)
+    # badges straight from HBM (forward-hook tensors) give the same statistics
+    col_d = AggregateStatisticsCollector()
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        col_d.track([torch.from_numpy(l[a:b]).cuda() for l in train])
+    for got, want in zip(col_d.get()[2], stds):
+        assert np.array_equal(got, want)
+    for name, metric in _sibling_metrics(nc, mins, maxs, stds).items():
+        score, prof = metric([l.copy() for l in test])
+        want_s, want_p = s[f"sib.{name}.score"], s[f"sib.{name}.profile"]
+        assert score.dtype == want_s.dtype and np.array_equal(score, want_s), name
+        assert prof.dtype == bool and prof.shape == want_p.shape and np.array_equal(prof, want_p), name
+        # CAM: dense signature of the reference, and the bit-packed profile that never left HBM
+        assert np.array_equal(np.array(list(cam(score, prof))), s[f"sib.{name}.cam"]), name
+        sc_d, bits = metric.packed([torch.from_numpy(l).cuda() for l in test])
+        assert np.array_equal(sc_d.cpu().numpy(), want_s.astype(np.int32)), name
+        assert np.array_equal(np.array(list(cam_from_bits(score, bits))), s[f"sib.{name}.cam"]), name
+    # float64 statistics and activations
+    tr64 = [l.astype(np.float64) for l in train[:2]]
+    col = AggregateStatisticsCollector()
+    col.track(tr64)
+    mn, mx, sd = col.get()
+    for i in range(2):
+        assert np.array_equal(mn[i], s[f"sib64.min{i}"]) and np.array_equal(mx[i], s[f"sib64.max{i}"])
+        assert sd[i].dtype == np.float64 and np.array_equal(sd[i], s[f"sib64.std{i}"])
+    sc64, p64 = nc.NBC(mn, mx, sd, 0.5)([l.astype(np.float64) for l in test[:2]])
+    assert np.array_equal(sc64, s["sib64.NBC_0.5.score"]) and np.array_equal(p64, s["sib64.NBC_0.5.profile"])
+    # surprise-coverage CAM (handler_surprise.py:101-115): 1000 buckets up to the largest value
+    from src.core.surprise import SurpriseCoverageMapper
+
+    prof = SurpriseCoverageMapper(1000, np.max(s["sc.values"])).get_coverage_profile(s["sc.values"])
+    assert np.array_equal(prof, s["sc.profile"])
+    assert np.array_equal(np.array(list(cam(s["sc.values"], prof))), s["sc.cam"])
+
+
+def test_sibling_coverage_study_shapes_vs_oracle():
+    """The study's layer widths (MNIST: 36 384 neurons over 4 layers, case_study_mnist.py:50-62): scores and profiles of
+    every criterion equal the NumPy oracle's; reference known answers (tests/test_coverage_metrics.py)."""
+    torch = _torch()
+    import src.core.neuron_coverage as nc
+    from src.core.prioritizers import cam
+    from src.dnn_test_prio.aggregate_statistics import AggregateStatisticsCollector
+
+    rng = np.random.default_rng(81)
+    shapes = [(26, 26, 32), (13, 13, 32), (11, 11, 64), (5, 5, 64)]            # 21632 + 5408 + 7744 + 1600 = 36384
+    def draw(n, scale):
+        return [np.maximum(rng.normal(size=(n,) + sh).astype(np.float32) * scale + 0.1, 0) for sh in shapes]
+    train, test = draw(96, 1.0), draw(64, 1.3)
+    col = AggregateStatisticsCollector()
+    col.track([l[:50] for l in train])
+    col.track([l[50:] for l in train])
+    mins, maxs, stds = col.get()
+    o_min, o_max, o_std = np_oracle.stats_oracle([[l[:50] for l in train], [l[50:] for l in train]])
+    for i in range(4):
+        assert np.array_equal(mins[i], o_min[i]) and np.array_equal(maxs[i], o_max[i]) and np.array_equal(stds[i], o_std[i]), i
+    want = {"NAC_0.75": np_oracle.nac_oracle(0.75, test), "NBC_0.5": np_oracle.nbc_oracle(mins, maxs, stds, 0.5, test),
+            "SNAC_0": np_oracle.snac_oracle(maxs, stds, 0, test)}
+    got = _sibling_metrics(nc, mins, maxs, stds)
+    for name, (ws, wp) in want.items():
+        gs, gp = got[name](test)
+        assert gs.dtype == ws.dtype and np.array_equal(gs, ws) and np.array_equal(gp, wp), name
+    # TKNC on tie-free layers (positive part only has ties at 0, never among the top 3 of these layers)
+    dense = [rng.normal(size=(64, 500)).astype(np.float32), rng.normal(size=(64, 7, 9)).astype(np.float32)]
+    for k in (1, 2, 3, 10):
+        ws, wp = np_oracle.tknc_oracle(k, dense)
+        gs, gp = nc.TKNC(k)(dense)
+        assert np.array_equal(gs, ws) and np.array_equal(gp, wp), k
+    # reference known answers: tests/test_coverage_metrics.py:67-168
+    acts = [np.array([[0.1, 0.4, 0.9, 0.4], [0.1, 0.9, 0.9, 0.4]]), np.array([[0.3, 0.2, 0.1, 0.6, 0.8], [0.3, 0.9, 0.1, 0.6, 0.8]]),
+            np.array([[0.2, 0.3, 0.4, 0.4], [0.2, 0.9, 0.4, 0.4]])]
+    mn = [np.array([0] * 4), np.array([0] * 5), np.array([0.1] * 4)]
+    mx = [np.array([1] * 4), np.array([1] * 5), np.array([0.95] * 4)]
+    zero = [np.array([0] * 4), np.array([0] * 5), np.array([0] * 4)]
+    pt2 = [np.array([0.2] * 4), np.array([0.2] * 5), np.array([0.2] * 4)]
+    out = [a.copy() for a in acts]
+    out[0][0][0], out[1][0][0] = -0.1, 1.5
+    assert np.all(nc.NBC(mn, mx, zero, scaler=1)(acts)[0] == [0, 0])
+    assert np.all(nc.NBC(mn, mx, zero, scaler=1)(out)[0] == [2, 0])
+    assert np.all(nc.NBC(mn, mx, pt2, scaler=1)(out)[0] == [1, 0])
+    assert np.all(nc.NBC(mn, mx, pt2, scaler=6)(out)[0] == [0, 0])
+    assert np.all(nc.SNAC(mx, zero, scaler=1)(out)[0] == [1, 0]) and np.all(nc.SNAC(mx, pt2, scaler=6)(out)[0] == [0, 0])
+    score, profile = nc.TKNC(2)(acts)
+    assert np.all(score == [6, 6])
+    assert np.all(profile[0][4:9] == [False, False, False, True, True]) and np.all(profile[0][9:] == [False, False, True, True])
+    assert np.all(profile[0][:4] == [False, True, True, False]) or np.all(profile[0][:4] == [False, False, True, True])
+    nac_score, nac_prof = nc.NAC(0.5)(acts)
+    assert np.array_equal(nac_prof, np.concatenate(acts, axis=1) > 0.5) and np.all(nac_score == nac_prof.sum(axis=1))
+    # dense CAM at a realistic size against the restated reference loop
+    prof = rng.random((700, 3000)) < 0.02
+    sc = prof.sum(axis=1)
+    assert np.array_equal(np.array(list(cam(sc, prof))), np_oracle.cam_oracle(sc, prof))
+    sc2 = rng.random(700)                                  # float scores: the tail is by score, the greedy part by coverage
+    assert np.array_equal(np.array(list(cam(sc2, prof[:, :40]))), np_oracle.cam_oracle(sc2, prof[:, :40]))
+
+
+# ------------------------------------------------------------------------------------------
+# SURVEY.md §8 f3: MDSA / MLSA scored on the GPU (fits = the reference's sklearn calls)
+# ------------------------------------------------------------------------------------------
+def test_mdsa_mlsa_golden_and_live_sklearn(golden):
+    from src.core.surprise import MDSA, MLSA, MultiModalSA
+
+    g = golden("mdsa_mlsa_reference.npz")
+    xtr, ytr, xte, pte = g["x.xtr"], g["x.ytr"], g["x.xte"], g["x.pte"]
+    m = MDSA(xtr)
+    np.testing.assert_allclose(m(xte), g["mdsa.out"], rtol=1e-4)
+    np.testing.assert_allclose(m(xte), m.covariance_matrix.mahalanobis(xte), rtol=1e-4)      # the live third-party arithmetic
+    pc = MultiModalSA.build_by_class(xtr, ytr, lambda x, y: MDSA(x))
+    np.testing.assert_allclose(pc(xte, pte), g["pcmdsa.out"], rtol=1e-4)
+    # float32 traces in, float64 distances out (sklearn validates to float and scipy's cdist returns float64)
+    out32 = MDSA(xtr.astype(np.float32))(xte.astype(np.float32))
+    assert out32.dtype == np.float64
+    np.testing.assert_allclose(out32, g["mdsa.out"], rtol=2e-4)
+    # singular covariance: sklearn's pinvh precision, eigen-factor whitening
+    np.testing.assert_allclose(MDSA(g["sing.xtr"])(g["sing.xte"]), g["sing.out"], rtol=1e-4, atol=1e-6)
+    # MLSA: the reference's fitted mixture (GaussianMixture's fit draws from NumPy's global RNG) ...
+    np.random.seed(1234)
+    ml = MLSA(xtr, num_components=3)
+    ml.gmm.means_, ml.gmm.precisions_cholesky_, ml.gmm.weights_ = g["mlsa.means"], g["mlsa.prec_chol"], g["mlsa.weights"]
+    ml._centres = None
+    np.testing.assert_allclose(ml(xte), g["mlsa.out"], rtol=1e-4)
+    # ... and a fresh fit against sklearn's own score_samples on this machine
+    fresh = MLSA(xtr, num_components=3)
+    np.testing.assert_allclose(fresh(xte), -fresh.gmm.score_samples(xte), rtol=1e-4)
+    pcm = MultiModalSA.build_by_class(xtr, ytr, lambda x, y: MLSA(x, num_components=3))
+    want = np.full(pte.shape, -np.inf)
+    for c, sa in pcm.modal_sa.items():
+        want[pte == c] = -sa.gmm.score_samples(xte[pte == c])
+    np.testing.assert_allclose(pcm(xte, pte), want, rtol=1e-4)
+    with pytest.raises(ValueError):
+        m(xte[:, :5])

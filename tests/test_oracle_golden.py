@@ -169,12 +169,53 @@ def test_compact_cam_oracle_matches_reference_cam_on_kmnc_profiles(golden):
         got = np_oracle.cam_from_buckets_oracle(score, bucket, k)
         assert np.array_equal(got, want), i
         assert sorted(got.tolist()) == list(range(bucket.shape[0]))      # a permutation of the samples
-    # and the dense host mirror agrees with both on a fresh case
-    from src.core.prioritizers import cam
-
+    # and the dense restatement agrees with both on a fresh case
     rng = np.random.default_rng(5)
     bucket = rng.integers(-1, 6, size=(50, 30)).astype(np.int32)
     prof = np.zeros((50, 30, 6), dtype=bool)
     np.put_along_axis(prof, np.maximum(bucket, 0)[..., None], (bucket >= 0)[..., None], axis=2)
     score = prof.sum(axis=(1, 2))
-    assert np.array_equal(np.array(list(cam(score, prof.copy()))), np_oracle.cam_from_buckets_oracle(score, bucket, 6))
+    assert np.array_equal(np_oracle.cam_oracle(score, prof), np_oracle.cam_from_buckets_oracle(score, bucket, 6))
+
+
+def test_dense_cam_oracle_matches_reference(golden):
+    """prioritizers.py:16-59 as run by the unmodified reference (tests/golden/prioritizers_reference.npz and the
+    CAM orders over NAC/NBC/SNAC/TKNC and surprise-coverage profiles in siblings_reference.npz)."""
+    g = golden("prioritizers_reference.npz")
+    for i in range(4):
+        assert np.array_equal(np_oracle.cam_oracle(g[f"cam{i}.scores"], g[f"cam{i}.profiles"]), g[f"cam{i}.order"]), i
+    s = golden("siblings_reference.npz")
+    for name in sorted({k.split(".")[1] for k in s.files if k.startswith("sib.") and k.endswith(".cam")}):
+        assert np.array_equal(np_oracle.cam_oracle(s[f"sib.{name}.score"], s[f"sib.{name}.profile"]), s[f"sib.{name}.cam"]), name
+    assert np.array_equal(np_oracle.cam_oracle(s["sc.values"], s["sc.profile"]), s["sc.cam"])
+
+
+def test_sibling_coverage_oracles_match_reference(golden):
+    """NAC / NBC / SNAC / TKNC and the streaming statistics (welford==0.2.5 restated) against the outputs of
+    the reference's own classes (oracle/make_golden.py: sibling_cases)."""
+    s = golden("siblings_reference.npz")
+    train = [s[f"sib.train{i}"] for i in range(3)]
+    test = [s[f"sib.test{i}"] for i in range(3)]
+    cuts = s["sib.cuts"]
+    mins, maxs, stds = np_oracle.stats_oracle([[l[a:b] for l in train] for a, b in zip(cuts[:-1], cuts[1:])])
+    for i in range(3):
+        for got, key in ((mins[i], "min"), (maxs[i], "max"), (stds[i], "std")):
+            want = s[f"sib.{key}{i}"]
+            assert got.dtype == want.dtype and np.array_equal(got, want), (key, i)
+    checks = {"NAC_0": lambda: np_oracle.nac_oracle(0.0, test), "NAC_0.75": lambda: np_oracle.nac_oracle(0.75, test),
+              "TKNC_1": lambda: np_oracle.tknc_oracle(1, test), "TKNC_3": lambda: np_oracle.tknc_oracle(3, test)}
+    for sc in (0, 0.5, 1):
+        checks[f"NBC_{sc}"] = lambda sc=sc: np_oracle.nbc_oracle(mins, maxs, stds, sc, test)
+        checks[f"SNAC_{sc}"] = lambda sc=sc: np_oracle.snac_oracle(maxs, stds, sc, test)
+    for name, fn in checks.items():
+        score, prof = fn()
+        assert score.dtype == s[f"sib.{name}.score"].dtype and np.array_equal(score, s[f"sib.{name}.score"]), name
+        assert np.array_equal(prof, s[f"sib.{name}.profile"]), name
+    # float64 statistics
+    tr64 = [l.astype(np.float64) for l in train[:2]]
+    mn, mx, sd = np_oracle.stats_oracle([tr64])
+    for i in range(2):
+        assert np.array_equal(mn[i], s[f"sib64.min{i}"]) and np.array_equal(mx[i], s[f"sib64.max{i}"])
+        assert np.array_equal(sd[i], s[f"sib64.std{i}"])
+    sc64, p64 = np_oracle.nbc_oracle(mn, mx, sd, 0.5, [l.astype(np.float64) for l in test[:2]])
+    assert np.array_equal(sc64, s["sib64.NBC_0.5.score"]) and np.array_equal(p64, s["sib64.NBC_0.5.profile"])

@@ -49,11 +49,18 @@ def test_surprise_coverage_mapper(buckets, limit, overflow, sa, expected):
     assert profile.shape == (3, 3) and profile.dtype == bool and np.all(profile == np.array(expected))
 
 
-def test_surprise_coverage_mapper_and_prioritizers_golden(golden):
+def test_surprise_coverage_mapper_golden(golden):
     g = golden("prioritizers_reference.npz")
     assert np.array_equal(SurpriseCoverageMapper(10, 2.5).get_coverage_profile(g["scm.values"]), g["scm.profile"])
     assert np.array_equal(SurpriseCoverageMapper(10, 2.5, overflow_bucket=True).get_coverage_profile(g["scm.values"]),
                           g["scm.profile_overflow"])
+    for i in range(4):
+        assert np.array_equal(np.array(list(ctm(g[f"cam{i}.scores"]))), g[f"cam{i}.ctm"]), i
+
+
+@pytest.mark.gpu
+def test_prioritizers_golden(golden):
+    g = golden("prioritizers_reference.npz")
     for i in range(4):
         scores, prof = g[f"cam{i}.scores"], g[f"cam{i}.profiles"]
         assert np.array_equal(np.array(list(cam(scores, prof.copy()))), g[f"cam{i}.order"]), i
@@ -61,6 +68,7 @@ def test_surprise_coverage_mapper_and_prioritizers_golden(golden):
 
 
 # ---- reference tests/test_prioritizers.py:27-64 (DeepGini-paper example) ---------------------
+@pytest.mark.gpu
 def test_cam_ctm_paper_example():
     profiles = np.array([[1, 1, 0, 0, 0, 0, 0, 0], [1, 1, 1, 1, 0, 0, 0, 0], [0, 0, 0, 0, 1, 1, 1, 0],
                          [0, 0, 0, 0, 0, 0, 1, 1]], dtype=bool)
@@ -154,8 +162,9 @@ def test_sa_plausibility(creator, strictly_positive):
     assert np.all(sa(big, big_labels).reshape((100, -1)) == first)
 
 
-# ---- reference tests/test_surprise.py:122-130, 174-229 (host sklearn paths) ----------------------
-def test_mdsa_mlsa_kmeans_host_paths():
+# ---- reference tests/test_surprise.py:122-130, 174-229 (sklearn fits on the host, scoring on the GPU) -------------
+@pytest.mark.gpu
+def test_mdsa_mlsa_kmeans_paths():
     rng = np.random.RandomState(42)
     acts = rng.random((20000, 10))
     np.testing.assert_allclose(MDSA(acts).covariance_matrix.covariance_, np.cov(acts.T), 0.1)
