@@ -65,3 +65,35 @@ def test_badges_on_disk_use_the_reference_layout(tmp_path):
     from simple_tip_b200.core.surprise import _flatten_layers
 
     assert _flatten_layers(acts).shape == (250, 3 * 6 * 6 + 5)
+
+
+def test_result_files_use_the_reference_names_and_reload_as_apfd(tmp_path):
+    """eval_prioritization.py:22-58 writes, eval_apfd_table.py:43-108 reads: scores are ranked by np.argsort(-scores),
+    CAM orders are taken as stored, names carry metric / parameter / model id."""
+    from simple_tip_b200.core import results as R
+    from simple_tip_b200.core.apfd import apfd_from_order
+
+    out = str(tmp_path)
+    rng = np.random.default_rng(3)
+    n = 50
+    mis = rng.random(n) < 0.3
+    mis[0] = True
+    R.persist(out, "mnist", "nominal", "is_misclassified", 0, mis)
+    dsa = rng.random(n)
+    cam_order = rng.permutation(n)
+    R.persist_tip(out, "mnist", "nominal", 0, "dsa", dsa, cam_order, times=[1.0, 2.0, 3.0, 4.0])
+    nac = rng.integers(0, 40, size=n)
+    R.persist_tip(out, "mnist", "nominal", 0, "NAC_0.75", nac, cam_order[::-1].copy())
+    R.persist_tip(out, "mnist", "nominal", 0, "pc-lsa", -dsa)
+    R.persist(out, "mnist", "nominal", "uncertainty_deep_gini", 0, dsa * 2)
+    R.persist_tip(out, "mnist", "ood", 0, "dsa", dsa)                       # another dataset: must not be picked up
+    assert sorted(os.listdir(os.path.join(out, "priorities")))[:3] == [
+        "mnist_nominal_0_NAC_0.75_cam_order.npy", "mnist_nominal_0_NAC_0.75_scores.npy", "mnist_nominal_0_dsa_cam_order.npy"]
+    assert np.array_equal(R.load(out, "mnist", "nominal", "dsa_scores", 0), dsa)
+    assert R.load_times(out, "mnist", "nominal", 0, "dsa") == [1.0, 2.0, 3.0, 4.0]
+    apfd = R.load_apfd_values(out, "mnist", "nominal")
+    assert set(apfd) == {"dsa", "dsa-cam", "NAC_0.75", "NAC_0.75-cam", "pc-lsa", "deep_gini"}
+    assert apfd["dsa"][0] == apfd_from_order(mis, np.argsort(-dsa))
+    assert apfd["dsa-cam"][0] == apfd_from_order(mis, cam_order)
+    assert apfd["NAC_0.75-cam"][0] == apfd_from_order(mis, cam_order[::-1])
+    assert apfd["deep_gini"][0] == apfd["dsa"][0]

@@ -765,3 +765,69 @@ def test_mdsa_mlsa_golden_and_live_sklearn(golden):
     np.testing.assert_allclose(pcm(xte, pte), want, rtol=1e-4)
     with pytest.raises(ValueError):
         m(xte[:, :5])
+
+
+# ------------------------------------------------------------------------------------------
+# traces straight from forward hooks (never leaving HBM) through every scorer, results written in
+# the reference's file layout and re-read as APFD
+# ------------------------------------------------------------------------------------------
+def test_forward_hook_traces_to_scores_to_result_files(tmp_path):
+    torch = _torch()
+    from simple_tip_b200.core import activations as A
+    from simple_tip_b200.core import results as R
+    from src.core.apfd import apfd_from_order
+    from src.core.deepgini import DeepGini
+    from src.core.neuron_coverage import KMNC, NAC
+    from src.core.prioritizers import cam_from_bits, cam_from_buckets
+    from src.core.surprise import DSA, LSA
+    from src.dnn_test_prio.aggregate_statistics import AggregateStatisticsCollector
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    model = torch.nn.Sequential(torch.nn.Conv2d(1, 4, 3), torch.nn.ReLU(), torch.nn.MaxPool2d(2), torch.nn.Flatten(),
+                                torch.nn.Linear(4 * 5 * 5, 24), torch.nn.ReLU(), torch.nn.Linear(24, 6),
+                                torch.nn.Softmax(dim=1)).to(dev)
+    tm = A.TransparentModel(model, activation_layers=[1, 5], include_last_layer=True)      # conv ReLU, dense ReLU, softmax
+    rng = np.random.default_rng(0)
+    xtr = torch.from_numpy(rng.normal(size=(1200, 1, 12, 12)).astype(np.float32)).to(dev)
+    xte = torch.from_numpy((rng.normal(size=(300, 1, 12, 12)) * 1.3).astype(np.float32)).to(dev)
+    tr = tm.collect(xtr, batch_size=100)
+    te = tm.collect(xte, batch_size=100)
+    assert all(t.is_cuda for t in tr + te)
+    ytr = tr[-1].argmax(dim=1).cpu().numpy()
+    pred_d, gini = DeepGini.calculate(te[-1])
+    labels = rng.integers(0, 6, size=300)
+    mis = pred_d != labels
+    # device tensors in == host copies in, for every scorer
+    sa_layer_tr, sa_layer_te = tr[1], te[1]
+    dsa = DSA(sa_layer_tr, ytr)(sa_layer_te, pred_d)
+    want = np_oracle.dsa_oracle(sa_layer_tr.cpu().numpy(), ytr, sa_layer_te.cpu().numpy(), pred_d)
+    assert np.array_equal(dsa, want["dsa"], equal_nan=True)
+    lsa = LSA(sa_layer_tr.cpu().numpy())(sa_layer_te)
+    _close(lsa, np_oracle.lsa_oracle(sa_layer_tr.cpu().numpy(), sa_layer_te.cpu().numpy()))
+    col = AggregateStatisticsCollector()
+    for badge in tm.walk_activations(xtr[i:i + 100] for i in range(0, 1200, 100)):
+        col.track(badge[:2])
+    mins, maxs, stds = col.get()
+    o_min, o_max, o_std = np_oracle.stats_oracle([[a[i:i + 100].cpu().numpy() for a in tr[:2]] for i in range(0, 1200, 100)])
+    assert all(np.array_equal(a, b) for a, b in zip(mins + maxs + stds, o_min + o_max + o_std))
+    km = KMNC(mins, maxs, 2)
+    k_score, k_bucket = km.buckets(te[:2], device_out=True)
+    ws, _ = np_oracle.kmnc_oracle(mins, maxs, 2, [a.cpu().numpy() for a in te[:2]])
+    assert np.array_equal(k_score.cpu().numpy(), ws)
+    n_score, n_bits = NAC(0.75).packed(te[:2])
+    os_, op = np_oracle.nac_oracle(0.75, [a.cpu().numpy() for a in te[:2]])
+    assert np.array_equal(n_score.cpu().numpy(), os_)
+    out = str(tmp_path)
+    R.persist(out, "toy", "nominal", "is_misclassified", 0, mis)
+    R.persist(out, "toy", "nominal", "uncertainty_deep_gini", 0, gini)
+    R.persist_tip(out, "toy", "nominal", 0, "dsa", dsa)
+    R.persist_tip(out, "toy", "nominal", 0, "KMNC_2", k_score.cpu().numpy(),
+                  list(cam_from_buckets(k_score.cpu().numpy(), k_bucket, 2)))
+    R.persist_tip(out, "toy", "nominal", 0, "NAC_0.75", os_, list(cam_from_bits(os_, n_bits)))
+    apfd = R.load_apfd_values(out, "toy", "nominal")
+    assert apfd["dsa"][0] == apfd_from_order(mis, np.argsort(-want["dsa"]))
+    assert apfd["deep_gini"][0] == apfd_from_order(mis, np.argsort(-np_oracle.deepgini_oracle(te[-1].cpu().numpy())[1]))
+    assert apfd["NAC_0.75-cam"][0] == apfd_from_order(mis, np_oracle.cam_oracle(os_, op))
+    kprof = np_oracle.kmnc_oracle(mins, maxs, 2, [a.cpu().numpy() for a in te[:2]])[1]
+    assert apfd["KMNC_2-cam"][0] == apfd_from_order(mis, np_oracle.cam_oracle(ws, kprof))
