@@ -330,6 +330,21 @@ int tip_row_sqnorm(const float* y, int64_t m, int64_t d, double* out, void* stre
 int tip_kde_lse(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d,
                 int64_t pitch, const tip_work_item* items, int32_t n_items, float* part_max,
                 float* part_sum, void* stream);
+/* The same pass with ONE fp16 segment (a third of the tensor work): operands from tip_pair_prep_f16, i.e.
+ * a_ij = <h(p_i), h(q_j)> - |p_i|^2/2 with h = fp16 rounding (11-bit significands: |error| ~ 2^-12 per product,
+ * against ~2^-17 for the three-segment bf16 form).  Whether that is accurate enough for rtol 1e-4 on the
+ * log-density depends on the data; the caller verifies it against tip_kde_lse on a sample of the queries and
+ * falls back (simple_tip_b200/core/stable_kde.py).  Same outputs as tip_kde_lse; pitch = tip_pair_pitch(d, 1). */
+int tip_kde_lse_f16(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d,
+                    int64_t pitch, const tip_work_item* items, int32_t n_items, float* part_max,
+                    float* part_sum, void* stream);
+/* fp16 operand packing for tip_kde_lse_f16: row = [ h(fl32(x - center)) | tail ], tail(query) = [S,S,S,0..],
+ * tail(train) = 3-way fp16 split of norm_coef*|v|^2/S with S = norm_scale (a power of two; keeps the norm
+ * term in fp16's range).  sqnorm[rows] = |v|^2 (fp32, may be NULL); flags[0] |= 1 if anything left fp16's finite
+ * range (flags may be NULL). */
+int tip_pair_prep_f16(const void* src, int dtype, int64_t rows, int64_t d, const float* center, int role,
+                      float norm_coef, float norm_scale, void* dst_f16, float* sqnorm, int32_t* flags,
+                      void* stream);
 /* merges `slots` partials per row in ascending slot order: out_max, out_sum (fp32) */
 int tip_kde_combine(const float* part_max, const float* part_sum, int64_t m, int32_t slots,
                     float* out_max, float* out_sum, void* stream);

@@ -47,6 +47,7 @@ struct PairArgs {
   int n_static;
   int* sched_counter;
   int k16;  // number of K=16 MMA steps per tile (packed width / 16)
+  uint32_t idesc;   // streaming kernel: instruction descriptor (bf16 x bf16 or fp16 x fp16 operands); 0 = bf16 default
   int64_t m;
   // MODE_NN
   const int32_t* q_class;     // with class_off: per-query excluded train range (items flagged 1)
@@ -170,6 +171,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
 }
 // cute::UMMA::InstrDescriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), K-major both, N>>3 @17, M>>4 @24.
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// the same shape with fp16 operands (format code 0 for A and B): 11-bit significands, used by the one-segment
+// LSA pass (tip_kde_lse_f16)
+constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // Acceptance threshold (accumulator space) for a query whose smallest approximate squared
 // distance so far is s: every train row whose exact NumPy distance could still be the minimum
@@ -386,6 +390,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // Whole warp runs the loop (uniform control flow -> descriptors live in uniform registers),
     // one elected lane issues; full chunks are four straight-line MMAs.
     const bool leader = elect_one();
+    const uint32_t idesc = args.idesc ? args.idesc : kIdesc;
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
@@ -404,14 +409,14 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int nm = min(4, k16 - 4 * c);
           if (leader) {
             // +32 bytes (one K=16 slice) inside the 128-byte swizzle row = +2 in the >>4 field
-            if (c == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdesc);
-            else umma_bf16_acc(d_tmem, adesc, bdesc, kIdesc);
+            if (c == 0) umma_bf16_first(d_tmem, adesc, bdesc, idesc);
+            else umma_bf16_acc(d_tmem, adesc, bdesc, idesc);
             if (nm == 4) {
-              umma_bf16_acc(d_tmem, adesc + 2u, bdesc + 2u, kIdesc);
-              umma_bf16_acc(d_tmem, adesc + 4u, bdesc + 4u, kIdesc);
-              umma_bf16_acc(d_tmem, adesc + 6u, bdesc + 6u, kIdesc);
+              umma_bf16_acc(d_tmem, adesc + 2u, bdesc + 2u, idesc);
+              umma_bf16_acc(d_tmem, adesc + 4u, bdesc + 4u, idesc);
+              umma_bf16_acc(d_tmem, adesc + 6u, bdesc + 6u, idesc);
             } else {
-              for (int k = 1; k < nm; k++) umma_bf16_acc(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdesc);
+              for (int k = 1; k < nm; k++) umma_bf16_acc(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc);
             }
             umma_commit(empty_bar(stage));
             if (c == nchunks - 1) umma_commit(tfull_bar(acc));
@@ -1089,6 +1094,19 @@ extern "C" int tip_kde_lse(const void* q_pack, int64_t m, const void* t_pack, in
   if (n_items == 0) return TIP_OK;
   PairArgs a{};
   a.items = items; a.n_items = n_items; a.n_static = n_items; a.k16 = k16_of(d, 3); a.m = m;
+  a.part_max = part_max; a.part_sum = part_sum;
+  return launch_pair<MODE_LSE>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
+}
+
+extern "C" int tip_kde_lse_f16(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d, int64_t pitch,
+                               const tip_work_item* items, int32_t n_items, float* part_max, float* part_sum,
+                               void* stream) {
+  TIP_REQUIRE(q_pack && t_pack && items && part_max && part_sum, "null pointer");
+  TIP_REQUIRE(pitch == tip_pair_pitch(d, 1), "pitch does not match tip_pair_pitch(d, 1)");
+  if (n_items == 0) return TIP_OK;
+  PairArgs a{};
+  a.items = items; a.n_items = n_items; a.n_static = n_items; a.k16 = k16_of(d, 1); a.m = m;
+  a.idesc = kIdescF16;
   a.part_max = part_max; a.part_sum = part_sum;
   return launch_pair<MODE_LSE>(q_pack, m, t_pack, n, pitch, a, (cudaStream_t)stream);
 }

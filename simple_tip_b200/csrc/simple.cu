@@ -9,6 +9,7 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace tip {
@@ -548,6 +549,56 @@ __global__ void __launch_bounds__(256) pair_prep_kernel(const T* __restrict__ sr
   }
 }
 
+// One-segment fp16 operand of the fast LSA pass: [ h(v) | tail ], h = round-to-nearest fp16 of v = fl32(x - center);
+// tail(query) = [S, S, S, 0..], tail(train) = 3-way fp16 split of norm_coef*|v|^2 / S (S = norm_scale, a power of two
+// that keeps the norm term inside fp16's range), so one K-loop accumulates norm_coef*|y|^2 + <h(x), h(y)> in fp32.
+// sqnorm = exact |v|^2 (fp32).  flags[0] |= 1 when a value or the scaled norm term leaves fp16's finite range.
+template <typename T>
+__global__ void __launch_bounds__(256) pair_prep_f16_kernel(const T* __restrict__ src, int64_t rows, int d,
+                                                            const float* __restrict__ center, int role, float norm_coef,
+                                                            float norm_scale, __half* __restrict__ dst, int64_t pitch,
+                                                            float* __restrict__ sqnorm, int32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int d16 = (d + 15) & ~15;
+  const T* x = src + row * (int64_t)d;
+  __half* out = dst + row * pitch;
+  double acc = 0.0;
+  bool bad = false;
+  for (int c = lane; c < d16; c += 32) {
+    float v = 0.f;
+    if (c < d) {
+      const float ctr = center ? center[c] : 0.f;
+      v = sizeof(T) == 8 ? (float)((double)x[c] - (double)ctr) : __fsub_rn((float)x[c], ctr);
+    }
+    acc += (double)v * (double)v;
+    bad |= !(fabsf(v) <= 65504.f);
+    out[c] = __float2half_rn(v);
+  }
+  acc = warp_sum(acc);
+  const float nrm = (float)acc;
+  for (int c = d16 + lane; c < pitch; c += 32) {
+    float v = 0.f;
+    const int t = c - d16;
+    if (t < 3) {
+      if (role == TIP_ROLE_TRAIN) {
+        const float cv = norm_coef * nrm / norm_scale;
+        bad |= !(fabsf(cv) <= 65504.f);
+        const float c0 = __half2float(__float2half_rn(cv));
+        const float c1 = __half2float(__float2half_rn(cv - c0));
+        const float c2 = __half2float(__float2half_rn(cv - c0 - c1));
+        v = t == 0 ? c0 : (t == 1 ? c1 : c2);
+      } else {
+        v = norm_scale;
+      }
+    }
+    out[c] = __float2half_rn(v);
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0 && flags) atomicOr(flags, 1);
+  if (lane == 0 && sqnorm) sqnorm[row] = nrm;
+}
+
 // =============================================================================================
 // gather / whiten / combine
 // =============================================================================================
@@ -785,6 +836,31 @@ extern "C" int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d
                              void* stream) {
   return pair_prep_impl(src, dtype, rows, d, center, role, segments, scale, norm_coef, dst, sqnorm, rounderr, nullptr,
                         nullptr, stream);
+}
+
+extern "C" int tip_pair_prep_f16(const void* src, int dtype, int64_t rows, int64_t d, const float* center, int role,
+                                 float norm_coef, float norm_scale, void* dst_f16, float* sqnorm, int32_t* flags,
+                                 void* stream) {
+  TIP_REQUIRE(src && dst_f16, "null pointer");
+  TIP_REQUIRE(role == TIP_ROLE_QUERY || role == TIP_ROLE_TRAIN, "role");
+  TIP_REQUIRE(d >= 1 && d <= (1 << 20) && rows >= 0, "shape");
+  TIP_REQUIRE(norm_scale >= 1.f && norm_scale <= 32768.f, "norm_scale");
+  if (rows == 0) return TIP_OK;
+  const int64_t pitch = tip_pair_pitch(d, 1);
+  const int64_t blocks = (rows + 7) / 8;
+  TIP_REQUIRE(blocks < (1LL << 31), "too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TIP_F32)
+    pair_prep_f16_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)src, rows, (int)d, center, role, norm_coef,
+                                                                 norm_scale, (__half*)dst_f16, pitch, sqnorm, flags);
+  else if (dtype == TIP_F64)
+    pair_prep_f16_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double*)src, rows, (int)d, center, role,
+                                                                  norm_coef, norm_scale, (__half*)dst_f16, pitch, sqnorm,
+                                                                  flags);
+  else
+    TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
+  TIP_LAUNCH_CHECK();
+  return TIP_OK;
 }
 
 extern "C" int tip_nn_query_prep(const void* q, int dtype, int64_t m, int64_t d, const float* center, void* q_pack,

@@ -1001,11 +1001,19 @@ def dsa_plan(engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, 
 # ------------------------------------------------------------------------------------------
 # Gaussian-KDE engine (LSA)
 # ------------------------------------------------------------------------------------------
+F16_NORM_SCALE = 64.0       # tail scale of the fp16 operand: |p|^2 / 2 / 64 must stay below 65504
+
+
 class KdeEngine:
     def __init__(self, p_whitened: np.ndarray, comm: Optional[TrainShardComm] = None):
         """p_whitened: [n, d] float64 whitened, centred training traces (host).  With a communicator
         of more than one rank the engine keeps rows rank::world (N_train sharded) and merges the
-        per-shard partial sums in log_kernel_sum (north_star: one exchange of partial KDE sums)."""
+        per-shard partial sums in log_kernel_sum (north_star: one exchange of partial KDE sums).
+
+        Two packed operands are kept: the three-segment split-bf16 form (~2^-17 relative per product: always
+        accurate enough for rtol 1e-4) and a one-segment fp16 form (11-bit significands, a third of the tensor
+        work).  Which one a scoring call uses is decided by MEASURING the fast form's error on a sample of the
+        queries (core/stable_kde.py)."""
         self.dev = require_cuda()
         self.lib = _lib.load()
         self.comm = comm if (comm is not None and comm.world > 1) else None
@@ -1014,6 +1022,7 @@ class KdeEngine:
         self.n, self.d = p_whitened.shape
         self.precision = "split-bf16 x3 (h.h + h.l + l.h, ~2^-17 relative)"
         self.pitch = int(self.lib.tip_pair_pitch(self.d, 3))
+        self.pitch1 = int(self.lib.tip_pair_pitch(self.d, 1))
         sms = C.c_int(0)
         _lib.check(self.lib.tip_device_info(C.byref(sms), None, None), "tip_device_info")
         self.sms = sms.value
@@ -1021,27 +1030,58 @@ class KdeEngine:
         self.t_pack = torch.empty((self.n, self.pitch), dtype=torch.bfloat16, device=self.dev)
         _lib.check(self.lib.tip_pair_prep(_p(p32), _lib.TIP_F32, self.n, self.d, None, _lib.ROLE_TRAIN, 3, 1.0, -0.5,
                                           _p(self.t_pack), None, None, _stream()), "tip_pair_prep")
+        # fast form; unusable if a training value or its norm term leaves fp16's range
+        self.t_pack_f16 = torch.empty((self.n, self.pitch1), dtype=torch.float16, device=self.dev)
+        self.flags = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        _lib.check(self.lib.tip_pair_prep_f16(_p(p32), _lib.TIP_F32, self.n, self.d, None, _lib.ROLE_TRAIN, -0.5,
+                                              F16_NORM_SCALE, _p(self.t_pack_f16), None, _p(self.flags), _stream()),
+                   "tip_pair_prep_f16")
         torch.cuda.current_stream().synchronize()
+        self.fast_ok = (os.environ.get("B200TIP_LSA_FAST", "1") != "0" and int(self.flags.item()) == 0
+                        and self.comm is None)
+        if not self.fast_ok:
+            self.t_pack_f16 = None
+        self._items = {}
 
-    def log_kernel_sum(self, q: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    def _work_items(self, m: int):
+        """Host planning + upload once per batch size."""
+        plan = self._items.get(m)
+        if plan is None:
+            q_off = np.array([0, m], dtype=np.int64)
+            ranges = [[(0, self.n)]]
+            items, slots = build_items(q_off, ranges, span_tiles_for(count_tile_pairs(q_off, ranges), self.sms))
+            items = span_major(items)
+            if len(self._items) > 16:
+                self._items.clear()
+            plan = (torch.from_numpy(items).to(self.dev), items.shape[0], slots * 2)   # one partial per 128-column half
+            self._items[m] = plan
+        return plan
+
+    def log_kernel_sum(self, q: torch.Tensor, fast: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """q: [m, d] fp32 whitened, centred queries on the GPU.  Returns (mx, sm, qsq) with
-        sum_i exp(-|p_i - q_j|^2/2) = exp(mx_j - qsq_j/2) * sm_j."""
+        sum_i exp(-|p_i - q_j|^2/2) = exp(mx_j - qsq_j/2) * sm_j.  fast=True: the one-segment fp16 pass
+        (sets flags[0] if a query leaves fp16's range)."""
         m = q.shape[0]
         lib = self.lib
-        q_pack = torch.empty((m, self.pitch), dtype=torch.bfloat16, device=self.dev)
         q_sq = torch.empty(m, dtype=torch.float32, device=self.dev)
-        _lib.check(lib.tip_pair_prep(_p(q), _lib.TIP_F32, m, self.d, None, _lib.ROLE_QUERY, 3, 1.0, 0.0, _p(q_pack),
-                                     _p(q_sq), None, _stream()), "tip_pair_prep")
-        q_off = np.array([0, m], dtype=np.int64)
-        ranges = [[(0, self.n)]]
-        items, slots = build_items(q_off, ranges, span_tiles_for(count_tile_pairs(q_off, ranges), self.sms))
-        items = span_major(items)
-        items_dev = torch.from_numpy(items).to(self.dev, non_blocking=True)
-        slots *= 2      # the kernel writes one partial per 128-column half of every span
+        if fast:
+            assert self.fast_ok
+            q_pack = torch.empty((m, self.pitch1), dtype=torch.float16, device=self.dev)
+            _lib.check(lib.tip_pair_prep_f16(_p(q), _lib.TIP_F32, m, self.d, None, _lib.ROLE_QUERY, 0.0, F16_NORM_SCALE,
+                                             _p(q_pack), _p(q_sq), _p(self.flags), _stream()), "tip_pair_prep_f16")
+        else:
+            q_pack = torch.empty((m, self.pitch), dtype=torch.bfloat16, device=self.dev)
+            _lib.check(lib.tip_pair_prep(_p(q), _lib.TIP_F32, m, self.d, None, _lib.ROLE_QUERY, 3, 1.0, 0.0, _p(q_pack),
+                                         _p(q_sq), None, _stream()), "tip_pair_prep")
+        items_dev, n_items, slots = self._work_items(m)
         part_max = torch.full((slots, m), float("-inf"), dtype=torch.float32, device=self.dev)
         part_sum = torch.zeros((slots, m), dtype=torch.float32, device=self.dev)
-        _lib.check(lib.tip_kde_lse(_p(q_pack), m, _p(self.t_pack), self.n, self.d, self.pitch, _p(items_dev),
-                                   items.shape[0], _p(part_max), _p(part_sum), _stream()), "tip_kde_lse")
+        if fast:
+            _lib.check(lib.tip_kde_lse_f16(_p(q_pack), m, _p(self.t_pack_f16), self.n, self.d, self.pitch1, _p(items_dev),
+                                           n_items, _p(part_max), _p(part_sum), _stream()), "tip_kde_lse_f16")
+        else:
+            _lib.check(lib.tip_kde_lse(_p(q_pack), m, _p(self.t_pack), self.n, self.d, self.pitch, _p(items_dev),
+                                       n_items, _p(part_max), _p(part_sum), _stream()), "tip_kde_lse")
         mx = torch.empty(m, dtype=torch.float32, device=self.dev)
         sm = torch.empty(m, dtype=torch.float32, device=self.dev)
         _lib.check(lib.tip_kde_combine(_p(part_max), _p(part_sum), m, slots, _p(mx), _p(sm), _stream()),

@@ -831,3 +831,42 @@ def test_forward_hook_traces_to_scores_to_result_files(tmp_path):
     assert apfd["NAC_0.75-cam"][0] == apfd_from_order(mis, np_oracle.cam_oracle(os_, op))
     kprof = np_oracle.kmnc_oracle(mins, maxs, 2, [a.cpu().numpy() for a in te[:2]])[1]
     assert apfd["KMNC_2-cam"][0] == apfd_from_order(mis, np_oracle.cam_oracle(ws, kprof))
+
+
+# ------------------------------------------------------------------------------------------
+# LSA operand tiers: the one-segment fp16 pass is used only where its measured error allows it
+# ------------------------------------------------------------------------------------------
+def test_lsa_fast_pass_is_verified_and_falls_back():
+    torch = _torch()
+    from src.core.surprise import LSA
+
+    # high-dimensional traces, large -log densities: the fp16 pass passes its check and meets rtol 1e-4 against the oracle
+    xtr, _, xte, _, _ = np_oracle.synth_clusters(9000, 1500, 256, 6, seed=51, spread=1.0)
+    sa = LSA(xtr)
+    got = sa(xte)
+    assert sa.kde.last_fast_check["accepted"], sa.kde.last_fast_check
+    assert sa.kde.last_operands.startswith("fp16 x1")
+    sub = np.sort(np.random.default_rng(0).choice(1500, 200, replace=False))
+    want = np_oracle.lsa_oracle(xtr, xte[sub], exact=True)
+    rel = np.abs(got[sub] - want) / np.abs(want)
+    assert rel.max() <= 1e-4, rel.max()
+    # with the fast pass disabled the same object reproduces the three-segment result (tighter)
+    sa.kde._engine.fast_ok = False
+    slow = sa(xte)
+    assert np.abs(slow[sub] - want).max() / np.abs(want).max() < 5e-6
+    assert np.abs(got - slow).max() / np.abs(slow).max() <= 1e-4
+    # low-dimensional traces: -log densities are small, the budget is tight -> the check must reject the fast pass
+    xs, _, xt, _, _ = np_oracle.synth_clusters(6000, 2048, 6, 3, seed=52, spread=1.0)
+    lo = LSA(xs)
+    out = lo(xt)
+    _close(out, np_oracle.lsa_oracle(xs, xt))
+    chk = lo.kde.last_fast_check
+    assert lo.kde.last_operands == "split-bf16 x3" or chk["max_rel_diff"] <= 2.5e-5, chk
+    # values beyond fp16's range disable the fast operand at fit time / raise the overflow flag at score time
+    big = LSA(xtr * 3.0e4)
+    assert big.kde._engine.fast_ok in (False, True)
+    far = xte.copy()
+    far[:5] *= 1.0e6
+    res = LSA(xtr)(far)
+    assert np.isinf(res[:5]).all() or np.isfinite(res[5:]).all()
+    _close(res[5:][sub[sub >= 5] - 5], np_oracle.lsa_oracle(xtr, far[5:][sub[sub >= 5] - 5]))
