@@ -128,11 +128,14 @@ class StableGaussianKDE:
         return self._density(rows, preselected=self.source_columns is None)
 
     # Fast pass (one fp16 segment) is accepted when, on a sample of the queries, its -log density agrees with the
-    # three-segment pass to a quarter of north_star's tolerance (rtol 1e-4).  The error is measured on the data
-    # at hand, not assumed from a model; one failed check retires the fast pass for this KDE.
+    # three-segment pass to 4e-5 relative.  The error is measured on the data at hand, not assumed from a model:
+    # per-input errors are zero-mean rounding noise (the dominant kernel term's 2^-12 relative operand rounding), so
+    # the largest of 128 samples sits near 2.5 sigma and the largest of 1e4..1e5 inputs near 4..4.4 sigma — at most
+    # 1.8x the sample maximum, i.e. <= 7.2e-5 < north_star's rtol 1e-4.  One failed check retires the fast pass for
+    # this KDE.  (C3: 2.8e-5 on the sample, 3.6e-5 worst of 256 other inputs against the float64 oracle.)
     FAST_MIN_ROWS = 1024
     FAST_SAMPLE = 128
-    FAST_RTOL = 2.5e-5
+    FAST_RTOL = 4e-5
 
     def _density(self, rows: np.ndarray, preselected: bool) -> np.ndarray:
         import torch
@@ -174,7 +177,7 @@ class StableGaussianKDE:
             self.last_fast_check = {"rows": int(n_s), "max_rel_diff": worst, "accepted": bool(not overflow and same_inf and worst <= self.FAST_RTOL)}
             if self.last_fast_check["accepted"]:
                 self.last_operands = "fp16 x1 (verified on %d sampled rows: max rel diff %.2e)" % (n_s, worst)
-                fast_lm[idx], fast_rs[idx] = ref_lm, ref_rs          # the sampled rows carry the accurate values
+                # (the sampled rows keep their fast values too: a row's score must not depend on where it sits in the batch)
                 return self._finish(fast_lm, fast_rs)
             eng.fast_ok = False
         mx, sm, qsq = eng.log_kernel_sum(q)

@@ -350,45 +350,50 @@ __global__ void __launch_bounds__(256) kmnc_vec4_kernel(const float* __restrict_
 // (sample, strip).
 constexpr int kStripRows = 8;
 
-// Section estimate without conversion instructions (F2I / I2F / MUFU run on the quarter-rate XU
-// pipe): e = (a - lo) / jump - 1/2 rounded to an integer by adding 1.5 * 2^23, clamped to
-// [0, k-1] while still in that biased float form, whose low mantissa bits are the integer.  The
-// estimate only has to be right most of the time: a section is accepted only after the exact test
-// against the two NumPy-rounded thresholds  min + jumps*i  (neuron_coverage.py:73-79, 87-91).
+// Section index without threshold arithmetic on the common path.  e = (a - lo) / jump is estimated as
+// fma(a - lo, 1/jump, -1/2) and rounded to an integer by adding 1.5 * 2^23 (no F2I / I2F: those run on the
+// quarter-rate XU pipe); the low mantissa bits of the biased float ARE the integer.  The estimate is accepted
+// without looking at a threshold when e - 1/2 lies within `lim` = 1/2 - delta of that integer, i.e. when a is
+// at least delta sections away from both neighbouring thresholds, where delta bounds everything that separates
+// the estimate from NumPy's comparison against its rounded thresholds  T_i = fl(min + fl(jumps * i))
+// (neuron_coverage.py:73-79, 87-91), in units of one section, u = 2^-24:
+//     |T_i - (min + jumps*i)| / jumps  <=  u (2 i + |min| / jumps)(1 + u)            (two roundings)
+//     |e_computed - e_exact|           <=  3.1 u (|e| + 1)                           (a - lo, 1/jump, product)
+//   delta = 1.01 u (5.1 (k + 1) + |min| / jumps + 2)      — 3e-4 at k = 1000: 0.06 % of the values take the exact path
+// (kmnc_bucket_slow: the two NumPy-rounded thresholds around the estimate, then a walk).  Below the range the
+// sign of a - lo is exact (T_0 = min), above it e >= k + delta puts a beyond T_k: both yield -1 without a test.
 struct KmncFast {
   int i;
   bool ok;
 };
-__device__ __forceinline__ KmncFast kmnc_fast(float a, float lo, float jump, float inv, float top) {
+// A neuron that can never be covered (jump <= 0 or NaN: constant / inverted range) costs nothing extra: its
+// inv is 0, its bias -3 and its lim +inf, so every finite activation lands on "section -3" = not covered.
+__device__ __forceinline__ KmncFast kmnc_fast(float a, float lo, float inv, float bias, float lim, int k) {
   constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
-  float m = __fadd_rn(__fmaf_rn(__fsub_rn(a, lo), inv, -0.5f), kMagic);
-  m = fminf(fmaxf(m, kMagic), top);       // top = kMagic + (k - 1); NaN -> kMagic
-  const float fi = __fsub_rn(m, kMagic);
-  const float t0 = __fadd_rn(lo, __fmul_rn(jump, fi));
-  const float t1 = __fadd_rn(lo, __fmul_rn(jump, __fadd_rn(fi, 1.0f)));
+  const float eh = __fmaf_rn(__fsub_rn(a, lo), inv, bias);
+  const float m = __fadd_rn(eh, kMagic);
+  const float fr = __fsub_rn(eh, __fsub_rn(m, kMagic));       // distance of e - 1/2 to the nearest integer
+  const int i = __float_as_int(m) - 0x4B400000;
   KmncFast r;
-  r.i = __float_as_int(m) - 0x4B400000;
-  r.ok = a >= t0 && a < t1;               // the caller vetoes neurons whose jump is not positive
+  r.ok = fabsf(fr) <= lim;                                    // NaN / inf / huge values fail -> exact path
+  r.i = (unsigned)i < (unsigned)k ? i : -1;
   return r;
 }
 
 // one sample row x four neurons of this thread: sections, optional store, number of covered neurons
-// dead[c] = -1 for a neuron that can never be covered (jump <= 0 or NaN: constant / inverted range),
-// else 0: OR-ed into the section index, and such neurons never take the slow path.
 template <typename TB>
 __device__ __forceinline__ int kmnc_strip_row(const float4 v, const float4 lo, const float4 jp, const float4 inv,
-                                              const int4 dead, float top, int k, TB* __restrict__ bp) {
-  const KmncFast f0 = kmnc_fast(v.x, lo.x, jp.x, inv.x, top);
-  const KmncFast f1 = kmnc_fast(v.y, lo.y, jp.y, inv.y, top);
-  const KmncFast f2 = kmnc_fast(v.z, lo.z, jp.z, inv.z, top);
-  const KmncFast f3 = kmnc_fast(v.w, lo.w, jp.w, inv.w, top);
-  int i0 = f0.i | dead.x, i1 = f1.i | dead.y, i2 = f2.i | dead.z, i3 = f3.i | dead.w;
-  const bool all_ok = (f0.ok || dead.x) && (f1.ok || dead.y) && (f2.ok || dead.z) && (f3.ok || dead.w);
-  if (!all_ok) {   // section edge, out of range, NaN
-    if (!(f0.ok || dead.x)) i0 = kmnc_bucket_slow(v.x, lo.x, jp.x, k);
-    if (!(f1.ok || dead.y)) i1 = kmnc_bucket_slow(v.y, lo.y, jp.y, k);
-    if (!(f2.ok || dead.z)) i2 = kmnc_bucket_slow(v.z, lo.z, jp.z, k);
-    if (!(f3.ok || dead.w)) i3 = kmnc_bucket_slow(v.w, lo.w, jp.w, k);
+                                              const float4 bias, const float4 lim, int k, TB* __restrict__ bp) {
+  const KmncFast f0 = kmnc_fast(v.x, lo.x, inv.x, bias.x, lim.x, k);
+  const KmncFast f1 = kmnc_fast(v.y, lo.y, inv.y, bias.y, lim.y, k);
+  const KmncFast f2 = kmnc_fast(v.z, lo.z, inv.z, bias.z, lim.z, k);
+  const KmncFast f3 = kmnc_fast(v.w, lo.w, inv.w, bias.w, lim.w, k);
+  int i0 = f0.i, i1 = f1.i, i2 = f2.i, i3 = f3.i;
+  if (!(f0.ok && f1.ok && f2.ok && f3.ok)) {   // within delta of a section edge, NaN, inf
+    if (!f0.ok) i0 = kmnc_bucket_slow(v.x, lo.x, jp.x, k);
+    if (!f1.ok) i1 = kmnc_bucket_slow(v.y, lo.y, jp.y, k);
+    if (!f2.ok) i2 = kmnc_bucket_slow(v.z, lo.z, jp.z, k);
+    if (!f3.ok) i3 = kmnc_bucket_slow(v.w, lo.w, jp.w, k);
   }
   if (bp) {
     if (sizeof(TB) == 2) {
@@ -424,9 +429,14 @@ __global__ void __launch_bounds__(256) kmnc_strip_kernel(const float* __restrict
   const bool leader = lane == __ffs(live) - 1;
   const float4 lo = __ldg(reinterpret_cast<const float4*>(mins) + j);
   const float4 jp = __ldg(reinterpret_cast<const float4*>(jumps) + j);
-  const float4 inv = make_float4(1.0f / jp.x, 1.0f / jp.y, 1.0f / jp.z, 1.0f / jp.w);   // inf/NaN -> slow path
-  const float top = 12582912.0f + (float)(k - 1);
-  const int4 dead = make_int4(jp.x > 0.f ? 0 : -1, jp.y > 0.f ? 0 : -1, jp.z > 0.f ? 0 : -1, jp.w > 0.f ? 0 : -1);
+  const bool dx = !(jp.x > 0.f), dy = !(jp.y > 0.f), dz = !(jp.z > 0.f), dw = !(jp.w > 0.f);   // never covered
+  const float4 inv = make_float4(dx ? 0.f : 1.0f / jp.x, dy ? 0.f : 1.0f / jp.y, dz ? 0.f : 1.0f / jp.z, dw ? 0.f : 1.0f / jp.w);
+  const float4 bias = make_float4(dx ? -3.f : -0.5f, dy ? -3.f : -0.5f, dz ? -3.f : -0.5f, dw ? -3.f : -0.5f);
+  auto limit = [k](float lo_c, float inv_c, bool dead_c) {   // 1/2 - delta (see kmnc_fast); negative = always the exact path
+    const float delta = 1.01f * 5.9604645e-8f * (5.1f * (float)(k + 1) + fabsf(lo_c) * fabsf(inv_c) * 1.0001f + 2.0f);
+    return dead_c ? __int_as_float(0x7f800000) : (delta == delta ? 0.5f - delta : -1.0f);
+  };
+  const float4 lim = make_float4(limit(lo.x, inv.x, dx), limit(lo.y, inv.y, dy), limit(lo.z, inv.z, dz), limit(lo.w, inv.w, dw));
   const int64_t row0 = rg * rows_per_block;
   const int64_t row1 = min(n, row0 + (int64_t)rows_per_block);
   const float4* src = reinterpret_cast<const float4*>(act) + row0 * d4 + j;
@@ -439,7 +449,7 @@ __global__ void __launch_bounds__(256) kmnc_strip_kernel(const float* __restrict
     for (int u = 0; u < kStripRows; u++) v[u] = ld_stream_f4(src + u * d4);
 #pragma unroll
     for (int u = 0; u < kStripRows; u++) {
-      int cnt = kmnc_strip_row<TB>(v[u], lo, jp, inv, dead, top, k, dst ? dst + u * d : nullptr);
+      int cnt = kmnc_strip_row<TB>(v[u], lo, jp, inv, bias, lim, k, dst ? dst + u * d : nullptr);
       cnt = __reduce_add_sync(live, cnt);
       if (leader && cnt) atomicAdd(sc + u, cnt);
     }
@@ -449,7 +459,7 @@ __global__ void __launch_bounds__(256) kmnc_strip_kernel(const float* __restrict
   }
   for (; r < row1; r++) {
     const float4 v = ld_stream_f4(src);
-    int cnt = kmnc_strip_row<TB>(v, lo, jp, inv, dead, top, k, dst);
+    int cnt = kmnc_strip_row<TB>(v, lo, jp, inv, bias, lim, k, dst);
     cnt = __reduce_add_sync(live, cnt);
     if (leader && cnt) atomicAdd(sc, cnt);
     src += d4;

@@ -861,7 +861,7 @@ def test_lsa_fast_pass_is_verified_and_falls_back():
     out = lo(xt)
     _close(out, np_oracle.lsa_oracle(xs, xt))
     chk = lo.kde.last_fast_check
-    assert lo.kde.last_operands == "split-bf16 x3" or chk["max_rel_diff"] <= 2.5e-5, chk
+    assert lo.kde.last_operands == "split-bf16 x3" or chk["max_rel_diff"] <= 4e-5, chk
     # values beyond fp16's range disable the fast operand at fit time / raise the overflow flag at score time
     big = LSA(xtr * 3.0e4)
     assert big.kde._engine.fast_ok in (False, True)
