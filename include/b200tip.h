@@ -239,7 +239,13 @@ int tip_nn_filter_tile(int64_t d, int32_t* q_rows, int32_t* t_rows);
  * next_*: optional (all NULL, or pack + sqnorm + row_min_bits + cand_cnt given): the winning rows are
  * also emitted as the packed queries and reset filter state of a following tip_nn_filter call —
  * exactly what tip_nn_query_prep(out_rows, center = next_center) would write — so DSA's second
- * stage (whose queries are stage 1's winners, surprise.py:627-629) needs no pack launch. */
+ * stage (whose queries are stage 1's winners, surprise.py:627-629) needs no pack launch.
+ * next_seed_ub (optional, with next_rounderr): n floats, for every train row an upper bound on its exact
+ * distance to SOME row the next search will scan for it (e.g. its nearest other-class row inside a fixed sample
+ * of the training set, computed once at fit time; +inf = none).  The winner's bound, widened by the filter's own
+ * error terms (next_t_rmax / next_t_errmax = the t_rmax / t_errmax of the next tip_nn_filter call), becomes the
+ * initial next_row_min_bits instead of +inf: the next filter collects no far-away candidates while its running
+ * minima warm up.  A seed never narrows the proven window below the final one. */
 int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype);
 int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n, int64_t d,
                   const int32_t* cand_idx, const int32_t* cand_cnt, int32_t cap,
@@ -247,7 +253,8 @@ int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n,
                   const int32_t* t_gid, void* out_dist, int32_t* out_pos, int32_t* out_gid,
                   void* out_rows, int32_t* work, int64_t* stats, const float* next_center,
                   void* next_pack, float* next_sqnorm, float* next_rounderr,
-                  uint32_t* next_row_min_bits, int32_t* next_cand_cnt, void* stream);
+                  uint32_t* next_row_min_bits, int32_t* next_cand_cnt, const float* next_seed_ub,
+                  float next_t_rmax, float next_t_errmax, void* stream);
 
 /* DSA result packing (surprise.py:576-611 scatter by index): for i < m,
  *   out[0*n_total + j] = dist_a[i], out[1*n_total + j] = dist_b[i], out[2*n_total + j] = gid[i],

@@ -132,7 +132,7 @@ class StableGaussianKDE:
     # per-input errors are zero-mean rounding noise (the dominant kernel term's 2^-12 relative operand rounding), so
     # the largest of 128 samples sits near 2.5 sigma and the largest of 1e4..1e5 inputs near 4..4.4 sigma — at most
     # 1.8x the sample maximum, i.e. <= 7.2e-5 < north_star's rtol 1e-4.  One failed check retires the fast pass for
-    # this KDE.  (C3: 2.8e-5 on the sample, 3.6e-5 worst of 256 other inputs against the float64 oracle.)
+    # this KDE.  (C3: 2.8e-5 on the sample, 3.2e-5 worst of 256 other inputs against the float64 restatement of scipy.)
     FAST_MIN_ROWS = 1024
     FAST_SAMPLE = 128
     FAST_RTOL = 4e-5

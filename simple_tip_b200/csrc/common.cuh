@@ -209,13 +209,34 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Seed of a query's running minimum in tip_nn_filter's "approximate squared distance" space from an upper
+// bound `ub` on the exact distance to SOME row of the range it is about to scan: that row's
+// accumulator value s satisfies s <= (d + e)^2 + g with e the summed input-rounding norms and g the accumulation
+// slack, so every threshold derived from the seed is at least as wide as the one the scan would reach on its
+// own — the candidate set still contains NumPy's argmin, it just stops collecting far-away rows from tile one.
+struct SeedParams {
+  const float* ub;     // per train row (by position), +inf = no bound; nullptr = no seeding
+  float t_rmax, t_err, gamma;
+};
+
+__device__ __forceinline__ uint32_t seed_row_min_bits(float ub, float nx, float q_err, const SeedParams& sp) {
+  if (!(ub < __int_as_float(0x7f800000))) return 0x7f800000u;
+  const float r = sqrtf(nx) + sp.t_rmax;
+  const float e = (q_err + sp.t_err + 1.2e-7f * r) * 1.00001f;
+  const float g = sp.gamma * r * r;
+  const float d = ub * 1.000004f + e;
+  const float s = (d * d + g) * 1.000002f;
+  return s < __int_as_float(0x7f800000) ? __float_as_uint(s) : 0x7f800000u;
+}
+
 // One query row -> packed bf16 operand of tip_nn_filter (one segment) + reset filter state, by a full
 // warp: the arithmetic of pair_prep_kernel (query role): centre in fp32, round to bf16, |h|^2 and
 // the dropped part's norm accumulated in double.  src == nullptr packs a zero row.
 template <typename T>
 __device__ __forceinline__ void warp_pack_query(const T* __restrict__ src, int d, const float* __restrict__ center,
                                                 __nv_bfloat16* __restrict__ out, int64_t pitch, float* sqnorm,
-                                                float* rounderr, uint32_t* row_min, int32_t* cand_cnt, int lane) {
+                                                float* rounderr, uint32_t* row_min, int32_t* cand_cnt, int lane,
+                                                float seed_ub = 3.4e38f, const SeedParams* sp = nullptr) {
   const int d16 = (d + 15) & ~15;
   double acc = 0.0, err = 0.0;
   for (int c = lane; c < d16; c += 32) {
@@ -236,9 +257,12 @@ __device__ __forceinline__ void warp_pack_query(const T* __restrict__ src, int d
   err = warp_sum(err);
   for (int c = d16 + lane; c < pitch; c += 32) out[c] = __float2bfloat16_rn(c - d16 < 3 ? 1.f : 0.f);
   if (lane == 0) {
-    *sqnorm = (float)acc;
-    if (rounderr) *rounderr = (float)sqrt(err) * 1.000001f;
-    *row_min = 0x7f800000u;
+    const float nx = (float)acc;
+    const float qe = (float)sqrt(err) * 1.000001f;
+    *sqnorm = nx;
+    if (rounderr) *rounderr = qe;
+    // the seed needs the measured rounding norm; without it (a-priori window) no seeding
+    *row_min = (sp && sp->ub && rounderr) ? seed_row_min_bits(seed_ub, nx, qe, *sp) : 0x7f800000u;
     *cand_cnt = 0;
   }
 }

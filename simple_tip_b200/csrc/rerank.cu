@@ -78,6 +78,7 @@ struct RerankArgs {
   float* next_rounderr;
   uint32_t* next_row_min;
   int32_t* next_cand_cnt;
+  SeedParams seed;    // optional: per-train-row upper bounds that seed the next stage's running minima
 };
 
 template <typename T>
@@ -96,7 +97,8 @@ __device__ __forceinline__ void write_result(const RerankArgs<T>& a, int64_t row
   if (a.next_pack)   // nlanes == 32 here
     warp_pack_query<T>(b.pos >= 0 ? src : nullptr, a.d, a.next_center, a.next_pack + row * a.next_pitch, a.next_pitch,
                        a.next_sqnorm + row, a.next_rounderr ? a.next_rounderr + row : nullptr, a.next_row_min + row,
-                       a.next_cand_cnt + row, lane);
+                       a.next_cand_cnt + row, lane,
+                       (a.seed.ub && b.pos >= 0) ? a.seed.ub[b.pos] : __int_as_float(0x7f800000), &a.seed);
 }
 
 // ---- kernel 1: one warp per query, candidate lists ----------------------------------------------
@@ -338,6 +340,11 @@ static int launch_rerank(const RerankArgs<T>& a, cudaStream_t st) {
 
 using namespace tip;
 
+static int next_pitch_k16(int64_t d) {     // K=16 steps of the one-segment packed row (pair_tc.cu: k16_of(d, 1))
+  const int64_t d16 = (d + 15) & ~(int64_t)15;
+  return (int)((d16 + 16) / 16);
+}
+
 extern "C" int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype) {
   if (m < 0) return -1;
   const int64_t cap = m + kScanUnitTarget;
@@ -350,8 +357,9 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
                              void* out_dist, int32_t* out_pos, int32_t* out_gid, void* out_rows, int32_t* work,
                              int64_t* stats, const float* next_center, void* next_pack, float* next_sqnorm,
                              float* next_rounderr, uint32_t* next_row_min_bits, int32_t* next_cand_cnt,
-                             void* stream) {
+                             const float* next_seed_ub, float next_t_rmax, float next_t_errmax, void* stream) {
   TIP_REQUIRE(q && t && out_dist && out_pos && work, "null pointer");
+  TIP_REQUIRE(next_seed_ub == nullptr || (next_pack && next_rounderr), "seeds need the next-stage query state incl. rounderr");
   TIP_REQUIRE(class_off && n_classes >= 1, "class offsets");
   TIP_REQUIRE(m >= 0 && m < (1LL << 31) - 8 && n >= 0 && n < (1LL << 31) && d >= 1 && d < (1LL << 31), "shape");
   TIP_REQUIRE(mode == TIP_RANGE_SAME_CLASS || mode == TIP_RANGE_OTHER_CLASSES, "mode");
@@ -361,18 +369,20 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
   if (m == 0) return TIP_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t next_pitch = tip_pair_pitch(d, 1);
+  // gamma of tip_nn_filter for this trace width (packed width + 16 fp32 accumulation steps)
+  const SeedParams seed{next_seed_ub, next_t_rmax, next_t_errmax, (float)(next_pitch_k16(d) * 16 + 16) * 1.1920929e-7f};
   if (dtype == TIP_F32) {
     RerankArgs<float> a{(const float*)q, (const float*)t, m, n, (int)d, cand_idx, cand_cnt, cap, q_class, class_off,
                         n_classes, mode, t_gid, (float*)out_dist, out_pos, out_gid, (float*)out_rows, work,
                         (unsigned long long*)stats, next_center, (__nv_bfloat16*)next_pack, next_pitch, next_sqnorm,
-                        next_rounderr, next_row_min_bits, next_cand_cnt};
+                        next_rounderr, next_row_min_bits, next_cand_cnt, seed};
     return launch_rerank<float>(a, st);
   }
   if (dtype == TIP_F64) {
     RerankArgs<double> a{(const double*)q, (const double*)t, m, n, (int)d, cand_idx, cand_cnt, cap, q_class,
                          class_off, n_classes, mode, t_gid, (double*)out_dist, out_pos, out_gid, (double*)out_rows,
                          work, (unsigned long long*)stats, next_center, (__nv_bfloat16*)next_pack, next_pitch,
-                         next_sqnorm, next_rounderr, next_row_min_bits, next_cand_cnt};
+                         next_sqnorm, next_rounderr, next_row_min_bits, next_cand_cnt, seed};
     return launch_rerank<double>(a, st);
   }
   TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");

@@ -32,6 +32,7 @@ POOL_MIN_TILES = 32       # tiles per CTA below which work lists stay purely sta
 POOL_TILES = int(os.environ.get("B200TIP_POOL_TILES", "4"))      # train tiles per dynamic item
 DEFAULT_CAP = 64          # candidate chunks per query (short traces)
 DEFAULT_CAP_LONG = 256    # long traces: distances concentrate, more rows fall inside the window
+SEEDS = os.environ.get("B200TIP_SEEDS", "1") != "0"      # fit-time upper bounds that seed stage 2's running minima
 
 # bench.py sets this to a list to collect (kernel name, algorithmic flops, start event, end event)
 # around the tensor-core launches; None (default) records nothing.
@@ -550,7 +551,8 @@ class TrainShardComm:
 # nearest-neighbour engine (DSA)
 # ------------------------------------------------------------------------------------------
 class NnEngine:
-    def __init__(self, t_sorted: torch.Tensor, class_off: np.ndarray, t_gid: torch.Tensor, cap: Optional[int] = None):
+    def __init__(self, t_sorted: torch.Tensor, class_off: np.ndarray, t_gid: torch.Tensor, cap: Optional[int] = None,
+                 seeds: bool = True):
         """t_sorted: [n, d] float32/float64 on the GPU, rows grouped by class (offsets class_off,
         ascending original index inside a class); t_gid[n] int32 original indices."""
         self.dev = require_cuda()
@@ -593,6 +595,28 @@ class NnEngine:
         else:
             self.center = torch.zeros(self.d, dtype=torch.float32, device=self.dev)
             self.t_pack, self.rmax, self.errmax = None, 0.0, 0.0
+        # Stage-2 seeds (short traces / resident-query kernel, where the warm-up of the running minima costs ~15 % of
+        # the filter): for every train row an upper bound on the distance to its nearest other-class row = the exact
+        # distance to the nearest one inside a fixed stratified sample of the training set, found once at fit time
+        # with this very engine machinery.
+        self.seed_b = None
+        if seeds and SEEDS and self.n >= 4096 and self.num_classes >= 2 and self.row_tile == 256:
+            self.seed_b = self._other_class_seeds()
+
+    def _other_class_seeds(self, sample_rows: int = 8192) -> Optional[torch.Tensor]:
+        step = max(1, self.n // sample_rows)
+        pick = torch.arange(0, self.n, step, device=self.dev)
+        cls_of_row = np.repeat(np.arange(self.num_classes), np.diff(self.class_off))
+        sub_cls = cls_of_row[::step][:pick.shape[0]]
+        sub_off = np.concatenate([[0], np.cumsum(np.bincount(sub_cls, minlength=self.num_classes))]).astype(np.int64)
+        if np.count_nonzero(np.diff(sub_off)) < 2:
+            return None
+        sub = NnEngine(self.t.index_select(0, pick), sub_off, self.t_gid.index_select(0, pick), seeds=False)
+        q_class = torch.from_numpy(cls_of_row.astype(np.int32)).to(self.dev)
+        ub = sub.search(self.t, q_class, self.class_off, _lib.RANGE_OTHER_CLASSES)[0].to(torch.float32)
+        ub = torch.where(torch.isnan(ub), torch.full_like(ub, float("inf")), ub).contiguous()
+        torch.cuda.current_stream().synchronize()
+        return ub
 
     @classmethod
     def from_host(cls, train: np.ndarray, labels: np.ndarray, num_classes: int, gids: Optional[np.ndarray] = None,
@@ -735,11 +759,16 @@ class NnEngine:
                                                   self.class_off_dev, self.center,
                                                   items_dev if (use_filter and self.n > 0) else None) if t is not None)
         nq = [_p(t) for t in next_query] if next_query is not None else [None] * 5
+        # stage 1 -> stage 2 hand-over: the winners' fit-time bounds seed the other-class search's running minima
+        seed = self.seed_b if (next_query is not None and mode == _lib.RANGE_SAME_CLASS) else None
+        if self._capture_refs is not None and seed is not None:
+            self._capture_refs.append(seed)
         _lib.check(lib.tip_nn_rerank(_p(q), _p(self.t), tip_dtype(q.dtype), m, self.n, self.d, _p(cand_idx),
                                      _p(cand_cnt), self.cap, _p(q_class), _p(self.class_off_dev), self.num_classes,
                                      mode, _p(self.t_gid), _p(out_dist), _p(out_pos), _p(out_gid), _p(out_rows),
                                      _p(work), _p(self.stats),
-                                     _p(self.center) if next_query is not None else None, *nq, _stream()),
+                                     _p(self.center) if next_query is not None else None, *nq,
+                                     _p(seed), self.rmax, self.errmax, _stream()),
                    "tip_nn_rerank")
         self.last_cand_cnt = cand_cnt
         if cand_cnt is not None:
