@@ -521,7 +521,7 @@ def run_ours(args):
     others = None
     if rank == 0 and world == 1 and not args.no_others:
         others = {}
-        for wl in ("c1", "c3", "c4"):
+        for wl in ("c1", "c3", "c4", "cam"):
             try:
                 others[wl] = secondary(wl, args, tm, dev, steps=min(args.steps, 10), with_cpu=not args.no_cpu)
             except Exception as e:   # pragma: no cover
@@ -717,6 +717,61 @@ def secondary(wl, args, tm: Timer, dev, steps: int, with_cpu: bool = True):
             return {"value": 1.0 / (per_section * 1000), "unit": "inputs/s", "cores": 1, "kind": "port",
                     "sample": f"{n_s} inputs at sections={k_s} ({dt:.2f} s), cost scaled linearly to 1000 sections "
                               "(the reference loops over sections, neuron_coverage.py:90-93)"}
+    elif wl == "cam":
+        # the step after every coverage score in the study (handler_coverage.py:122-124): CAM over NAC_0.75 profiles at
+        # MNIST's 36 384 neurons (case_study_mnist.py:50-62) and over KMNC bucket ids at C4's shape, neither leaving HBM
+        from simple_tip_b200.core.neuron_coverage import KMNC, NAC
+        from simple_tip_b200.core.prioritizers import cam_from_bits, cam_from_buckets
+
+        rng = np.random.default_rng(6)
+        n, d = 10000, 36384
+        act = torch.clamp(torch.randn((n, d), device=dev, generator=torch.Generator(device=dev).manual_seed(6)) * 0.5 + 0.1, min=0)
+        nac = NAC(0.75)
+        score_d, bits = nac.packed(act)
+        score = score_d.cpu().numpy()
+        order = np.array(list(cam_from_bits(score, bits)))
+        chk = np.sort(rng.choice(n, 300, replace=False))          # a sub-problem small enough for the NumPy restatement
+        s_s, b_s = nac.packed(act[torch.from_numpy(chk).to(dev)][:, :4096].contiguous())
+        _, p_s = nac(act[torch.from_numpy(chk).to(dev)][:, :4096].contiguous())
+        ok_bits = bool(np.array_equal(np.array(list(cam_from_bits(s_s.cpu().numpy(), b_s))),
+                                      np_oracle.cam_oracle(s_s.cpu().numpy(), p_s)))
+        st = torch.zeros(4, dtype=torch.int32)
+        t0 = time.perf_counter()
+        greedy_rounds = 0
+        for _ in range(3):
+            greedy_rounds = sum(1 for _ in cam_from_bits(score, bits))
+        torch.cuda.synchronize()
+        dt_bits = (time.perf_counter() - t0) / 3
+        words = int(bits.shape[1])
+        # rounds actually run by the greedy loop: samples yielded before the tail = picks with positive gain
+        from simple_tip_b200.core import prioritizers as P
+        picks_bits = int(P.LAST_GREEDY_PICKS)
+        actk, mins, maxs = np_oracle.synth_relu(10000, 4096, seed=4)
+        km = KMNC([mins], [maxs], 1000)
+        ks, kb = km.buckets([torch.from_numpy(actk).to(dev)], device_out=True)
+        ksn = ks.cpu().numpy()
+        t0 = time.perf_counter()
+        n_b = sum(1 for _ in cam_from_buckets(ksn, kb, 1000))
+        torch.cuda.synchronize()
+        dt_bk = time.perf_counter() - t0
+        picks_bk = int(P.LAST_GREEDY_PICKS)
+        sub = kb[:200, :512].contiguous()
+        ss = ((sub >= 0).sum(dim=1)).cpu().numpy()
+        ok_bk = bool(np.array_equal(np.array(list(cam_from_buckets(ss, sub, 1000))),
+                                    np_oracle.cam_from_buckets_oracle(ss, sub.cpu().numpy().astype(np.int32), 1000)))
+        return {"metric": "cam_greedy_rounds_per_sec", "unit": "rounds/s", "data": "synthetic", "n_gpus": 1,
+                "bits": {"workload": f"CAM over NAC_0.75 profiles, {n} samples x {d} neurons, bit-packed in HBM ({words} words per sample)",
+                         "kernel": "cam_bits_kernel (one persistent cooperative launch for all rounds)", "greedy_rounds": picks_bits,
+                         "ms_total": 1e3 * dt_bits, "rounds_per_s": picks_bits / dt_bits if dt_bits > 0 else None,
+                         "bytes_per_round_worst_case": int(n * words * 4), "order_is_a_permutation": bool(sorted(order.tolist()) == list(range(n))),
+                         "sub_problem_equals_numpy_restatement": ok_bits,
+                         "note": "a round reads only the non-zero words of the pick's new coverage for samples with gain left, "
+                                 "so the worst-case bytes are an upper bound"},
+                "buckets": {"workload": "CAM over KMNC bucket ids, 10000 x 4096, 1000 sections (C4's profile: 41 GB dense)",
+                            "kernel": "cam_pick / cam_collect / cam_update (3 launches per round)", "greedy_rounds": picks_bk,
+                            "ms_total": 1e3 * dt_bk, "rounds_per_s": picks_bk / dt_bk if dt_bk > 0 else None,
+                            "sub_problem_equals_numpy_restatement": ok_bk},
+                "value": picks_bits / dt_bits if dt_bits > 0 else None, "higher_is_better": True}
     else:   # c1
         from simple_tip_b200.core.apfd import apfd_from_order
         from simple_tip_b200.core.deepgini import DeepGini
@@ -810,7 +865,7 @@ def main():
                     help="multi-GPU layout of the C2 headline: test = N_test sharded, train replicated (default: the "
                          "train set is 30.7 MB); train = N_train sharded (what C5 needs; always measured on the C5-shaped "
                          "slice in n_train_sharded)")
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5s"],
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5s", "cam"],
                     help="c2 (default) = the configuration the headline metric is quoted on (its line also carries the "
                          "others); c1/c3/c4/c5s = one of the other configurations alone, single GPU")
     args = ap.parse_args()

@@ -16,6 +16,9 @@ def ctm(scores: np.ndarray) -> Generator[int, None, None]:
     yield from np.argsort(-scores)
 
 
+LAST_GREEDY_PICKS = 0      # greedy rounds of the most recent CAM call (bench / diagnostics)
+
+
 def _tail_by_score(scores: np.ndarray, greedy: np.ndarray):
     """prioritizers.py:47-59: the samples the greedy loop did not yield, by `np.argsort(-scores)` — NumPy's
     own (unstable) sort on the host, so ties fall exactly as in the reference."""
@@ -65,6 +68,8 @@ def cam_from_bits(scores: np.ndarray, bits, rounds_per_launch: int = 4096) -> Ge
             st = state.cpu().numpy()
             picks, done = int(st[0]), bool(st[1])
         greedy = order[:picks].cpu().numpy().astype(np.int64)
+    global LAST_GREEDY_PICKS
+    LAST_GREEDY_PICKS = int(greedy.shape[0])
     yield from (int(i) for i in greedy)
     yield from _tail_by_score(scores, greedy)
 
@@ -142,5 +147,7 @@ def cam_from_buckets(scores: np.ndarray, bucket, sections: int) -> Generator[int
         greedy = order[:picks].cpu().numpy().astype(np.int64)
     else:
         greedy = np.zeros(0, dtype=np.int64)
+    global LAST_GREEDY_PICKS
+    LAST_GREEDY_PICKS = int(greedy.shape[0])
     yield from (int(i) for i in greedy)
     yield from _tail_by_score(scores, greedy)
