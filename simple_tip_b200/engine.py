@@ -572,6 +572,7 @@ class NnEngine:
         qt, tt = C.c_int32(0), C.c_int32(0)
         _lib.check(self.lib.tip_nn_filter_tile(self.d, C.byref(qt), C.byref(tt)), "tip_nn_filter_tile")
         self.row_tile, self.col_tile = qt.value, tt.value
+        self.resident = int(self.lib.tip_nn_filter_kind(self.d)) == 1     # resident-query kernel (short traces)
         self.stats = torch.zeros(2, dtype=torch.int64, device=self.dev)
         self._item_cache = {}
         self._plans = {}
@@ -600,7 +601,7 @@ class NnEngine:
         # distance to the nearest one inside a fixed stratified sample of the training set, found once at fit time
         # with this very engine machinery.
         self.seed_b = None
-        if seeds and SEEDS and self.n >= 4096 and self.num_classes >= 2 and self.row_tile == 256:
+        if seeds and SEEDS and self.n >= 4096 and self.num_classes >= 2 and self.resident:
             self.seed_b = self._other_class_seeds()
 
     def _other_class_seeds(self, sample_rows: int = 8192) -> Optional[torch.Tensor]:
@@ -703,7 +704,7 @@ class NnEngine:
                 # few queries per class: tile across class boundaries (full tiles), per-query masking;
                 # many: class-aligned tiles never touch their own class's rows
                 mixed = mode == _lib.RANGE_OTHER_CLASSES and m < 2 * self.row_tile * max(1, populated)
-                if self.row_tile == 256:
+                if self.resident:
                     # resident-query kernel: one or two long items per CTA, equal tile counts
                     tiles = query_tiles(q_off, ranges, self.class_off, self.row_tile, mixed)
                     items, n_static = build_balanced_items(tiles, self.col_tile, self.sms, pool_frac=POOL_FRAC,
@@ -1078,7 +1079,8 @@ class KdeEngine:
         if plan is None:
             q_off = np.array([0, m], dtype=np.int64)
             ranges = [[(0, self.n)]]
-            items, slots = build_items(q_off, ranges, span_tiles_for(count_tile_pairs(q_off, ranges), self.sms))
+            rt = int(self.lib.tip_kde_tile_rows())
+            items, slots = build_items(q_off, ranges, span_tiles_for(count_tile_pairs(q_off, ranges, rt), self.sms), rt)
             items = span_major(items)
             if len(self._items) > 16:
                 self._items.clear()
