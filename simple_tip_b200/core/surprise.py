@@ -407,7 +407,12 @@ class DSA(SA):
     dsa = dist_a / dist_b with dist_a the distance from the test trace to the nearest training
     trace of its predicted class and dist_b the distance from THAT TRAINING TRACE to the nearest
     training trace of any other class (surprise.py:615-631).  Distances and the winner are
-    bit-identical to the reference's NumPy (`np.linalg.norm(axis=2)`, `np.argmin`)."""
+    bit-identical to the reference's NumPy (`np.linalg.norm(axis=2)`, `np.argmin`).
+
+    dtypes: float32 and float64 traces are scored in their own dtype; float64 test traces against float32 training
+    traces are scored in float64 like NumPy's promotion does (a float64 twin of the engine is built on first use);
+    float16 / bfloat16 traces are widened exactly and scored in float32 (the reference would keep float16
+    arithmetic — a documented deviation)."""
 
     def __init__(self, activations: Activations, predictions: Predictions, badge_size: int = 10,
                  subsampling: Union[int, float] = 1.0, subsampling_seed: int = 0, *, comm=None):
@@ -429,6 +434,8 @@ class DSA(SA):
         self._seen_shapes = set()
         self._comm = comm
         self._engine = None
+        self._engine_wide = None      # float64 twin for float64 test traces against float32 training traces
+        self._last_dtype = None
         self._build_engine()
 
     def _class_matrix(self) -> List[np.ndarray]:
@@ -467,21 +474,32 @@ class DSA(SA):
         from .. import engine as E
 
         target_pred = _class_predictions(E.host_array(predictions))
-        torch_dtype = torch.float64 if self._compute_dtype == np.float64 else torch.float32
         dev_ats = E.device_matrix(activations)        # traces already in HBM: no host round trip
+        # NumPy promotes `from_ats[:, None] - to_ats` (surprise.py:638): float64 test traces against float32
+        # training traces are scored in float64 (the training traces widened exactly) -> a float64 twin of the
+        # engine, built on first use
+        wide = (dev_ats.dtype == torch.float64) if dev_ats is not None else \
+            (np.result_type(_flatten_layers(activations).dtype, self._compute_dtype) == np.float64)
+        compute = np.dtype(np.float64) if wide else self._compute_dtype
+        eng = self._engine
+        if compute != self._compute_dtype:
+            if self._comm is not None and self._comm.world > 1:
+                raise TypeError("N_train-sharded DSA scores in the dtype of the training traces "
+                                f"({self._compute_dtype}); got float64 test traces")
+            if self._engine_wide is None:
+                train = self.train_activations
+                train = train.to(torch.float64) if isinstance(train, torch.Tensor) else np.asarray(train, dtype=np.float64)
+                self._engine_wide = E.NnEngine.from_host(train, self.train_predictions, int(self.num_classes),
+                                                         np.arange(train.shape[0]))
+            eng = self._engine_wide
+        torch_dtype = torch.float64 if compute == np.float64 else torch.float32
         if dev_ats is not None:
-            if dev_ats.dtype == torch.float64 and torch_dtype != torch.float64:
-                raise TypeError(f"test traces need the dtype of the training traces ({self._compute_dtype}), "
-                                "got float64")
             target_ats = dev_ats.to(torch_dtype)
         else:
             target_ats = _flatten_layers(activations)
-            if target_ats.dtype != self._compute_dtype:
-                target_ats = target_ats.astype(np.result_type(target_ats.dtype, self._compute_dtype))
-                if target_ats.dtype != self._compute_dtype:
-                    raise TypeError("test traces need the dtype of the training traces "
-                                    f"({self._compute_dtype}), got {target_ats.dtype}")
-        eng = self._engine
+            if target_ats.dtype != compute:
+                target_ats = target_ats.astype(compute)
+        self._last_dtype = compute
         dev = eng.dev
         if target_ats.ndim != 2 or int(target_ats.shape[1]) != eng.d:
             # the reference's `from_ats[:, None] - to_ats` raises the same kind of error (surprise.py:638)
@@ -549,8 +567,8 @@ class DSA(SA):
     def _finish(self, res: np.ndarray) -> np.ndarray:
         """res[3, n]: dist_a, dist_b, winner index as float64 (exact widenings) in the caller's order."""
         self._last_raw = res
-        a = res[0].astype(self._compute_dtype)
-        b = res[1].astype(self._compute_dtype)
+        a = res[0].astype(self._last_dtype or self._compute_dtype)
+        b = res[1].astype(self._last_dtype or self._compute_dtype)
         with np.errstate(divide="ignore", invalid="ignore"):
             # the reference divides in the input dtype and widens on store (surprise.py:595,611)
             return (a / b).astype(np.float64)
@@ -558,11 +576,11 @@ class DSA(SA):
     # Results of the most recent call (exact widenings of the device values; valid until the next call)
     @property
     def last_dist_a(self) -> np.ndarray:
-        return self._last_raw[0].astype(self._compute_dtype)
+        return self._last_raw[0].astype(self._last_dtype or self._compute_dtype)
 
     @property
     def last_dist_b(self) -> np.ndarray:
-        return self._last_raw[1].astype(self._compute_dtype)
+        return self._last_raw[1].astype(self._last_dtype or self._compute_dtype)
 
     @property
     def last_winner_index(self) -> np.ndarray:

@@ -874,3 +874,20 @@ def test_lsa_fast_pass_is_verified_and_falls_back():
     res = LSA(xtr)(far)
     assert np.isinf(res[:5]).all() or np.isfinite(res[5:]).all()
     _close(res[5:][sub[sub >= 5] - 5], np_oracle.lsa_oracle(xtr, far[5:][sub[sub >= 5] - 5]))
+
+
+def test_dsa_mixed_dtypes_follow_numpy_promotion():
+    """float64 test traces against float32 training traces: NumPy promotes the difference to float64
+    (surprise.py:638) — same bits here; float16 traces are widened and scored in float32 (documented)."""
+    from src.core.surprise import DSA
+
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(3000, 260, 40, 4, seed=61)
+    sa = DSA(xtr, ytr)
+    x64 = xte.astype(np.float64) + 1e-9
+    want = np_oracle.dsa_oracle(xtr, ytr, x64, pte)
+    got = sa(x64, pte)
+    assert want["dist_a"].dtype == np.float64 and np.array_equal(got, want["dsa"])
+    assert np.array_equal(sa.last_dist_a, want["dist_a"]) and np.array_equal(sa.last_winner_index, want["idx_a"])
+    assert np.array_equal(sa(xte, pte), np_oracle.dsa_oracle(xtr, ytr, xte, pte)["dsa"])       # float32 path unaffected
+    h = xte.astype(np.float16)
+    assert np.array_equal(sa(h, pte), np_oracle.dsa_oracle(xtr, ytr, h.astype(np.float32), pte)["dsa"])
