@@ -123,9 +123,12 @@ class StableGaussianKDE:
 
     def evaluate_rows(self, rows: np.ndarray) -> np.ndarray:
         """rows: (m, all source columns); the kept columns are gathered on the GPU."""
+        return self.evaluate_rows_begin(rows).finish()
+
+    def evaluate_rows_begin(self, rows):
         if self.prepare_failed:
-            return np.zeros(rows.shape[0])
-        return self._density(rows, preselected=self.source_columns is None)
+            return _PendingDensity(self, None, -int(rows.shape[0]), 0, None, None)
+        return self._density_begin(rows, preselected=self.source_columns is None)
 
     # Fast pass (one fp16 segment) is accepted when, on a sample of the queries, its -log density agrees with the
     # three-segment pass to 4e-5 relative.  The error is measured on the data at hand, not assumed from a model:
@@ -138,6 +141,13 @@ class StableGaussianKDE:
     FAST_RTOL = 4e-5
 
     def _density(self, rows: np.ndarray, preselected: bool) -> np.ndarray:
+        return self._density_begin(rows, preselected).finish()
+
+    def _density_begin(self, rows, preselected: bool) -> "_PendingDensity":
+        """Launches everything a density evaluation needs and starts the device->host copy of its partials into
+        pinned memory WITHOUT synchronising; `finish()` waits for that copy and does the float64 host math (and,
+        if the fast pass fails its check, the three-segment re-run).  Lets `MultiModalSA` keep the per-class KDEs of
+        a batch in flight together (handler_surprise.py:26: one LSA per class)."""
         import torch
 
         from .. import engine as E
@@ -150,11 +160,12 @@ class StableGaussianKDE:
             rows = rows.astype(np.float64)
         m = rows.shape[0]
         if m == 0:
-            return np.zeros(0)
+            return _PendingDensity(self, None, 0, 0, None, None)
         x = E.to_device(rows, eng.dev)
         q = E.whiten(x, None if preselected else self._cols_dev, self._mu_dev, self._w_dev)
         self.last_operands = "split-bf16 x3"
-        if eng.fast_ok and m >= self.FAST_MIN_ROWS:
+        fast = eng.fast_ok and m >= self.FAST_MIN_ROWS
+        if fast:
             eng.flags.zero_()
             mx, sm, qsq = eng.log_kernel_sum(q, fast=True)
             sel = torch.arange(0, m, max(1, m // self.FAST_SAMPLE), device=eng.dev)[:self.FAST_SAMPLE]
@@ -162,28 +173,31 @@ class StableGaussianKDE:
             packed = torch.cat([torch.stack([mx.to(torch.float64) - 0.5 * qsq.to(torch.float64), sm.to(torch.float64)]),
                                 torch.stack([mx3.to(torch.float64) - 0.5 * qsq3.to(torch.float64), sm3.to(torch.float64)]),
                                 torch.stack([sel.to(torch.float64), eng.flags.to(torch.float64).expand(sel.shape[0])])],
-                               dim=1).cpu().numpy()
-            n_s = sel.shape[0]
-            fast_lm, fast_rs = packed[0, :m], packed[1, :m]
-            ref_lm, ref_rs = packed[0, m:m + n_s], packed[1, m:m + n_s]
-            idx = packed[0, m + n_s:].astype(np.int64)
-            overflow = packed[1, m + n_s] != 0
-            with np.errstate(divide="ignore", invalid="ignore", under="ignore"):
-                l_fast = -(self.log_norm - math.log(self.n) + fast_lm[idx] + np.log(fast_rs[idx]))
-                l_ref = -(self.log_norm - math.log(self.n) + ref_lm + np.log(ref_rs))
-                both = np.isfinite(l_fast) & np.isfinite(l_ref)
-                worst = float(np.max(np.abs(l_fast[both] - l_ref[both]) / np.abs(l_ref[both]))) if both.any() else 0.0
-            same_inf = np.array_equal(np.isfinite(l_fast), np.isfinite(l_ref))
-            self.last_fast_check = {"rows": int(n_s), "max_rel_diff": worst, "accepted": bool(not overflow and same_inf and worst <= self.FAST_RTOL)}
-            if self.last_fast_check["accepted"]:
-                self.last_operands = "fp16 x1 (verified on %d sampled rows: max rel diff %.2e)" % (n_s, worst)
-                # (the sampled rows keep their fast values too: a row's score must not depend on where it sits in the batch)
-                return self._finish(fast_lm, fast_rs)
-            eng.fast_ok = False
-        mx, sm, qsq = eng.log_kernel_sum(q)
-        mx = mx.to(torch.float64) - 0.5 * qsq.to(torch.float64)
-        packed = torch.stack([mx, sm.to(torch.float64)]).cpu().numpy()
-        return self._finish(packed[0], packed[1])
+                               dim=1)
+            n_s = int(sel.shape[0])
+        else:
+            mx, sm, qsq = eng.log_kernel_sum(q)
+            packed = torch.stack([mx.to(torch.float64) - 0.5 * qsq.to(torch.float64), sm.to(torch.float64)])
+            n_s = 0
+        host = self._pinned(packed.shape)
+        host.copy_(packed, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        return _PendingDensity(self, host, m, n_s, done, q if fast else None)
+
+    def _pinned(self, shape):
+        """pinned landing buffers, recycled per shape (cudaHostAlloc is slow)"""
+        import torch
+
+        key = tuple(shape)
+        pool = self.__dict__.setdefault("_pinned_pool", {})
+        buf = pool.get(key)
+        if buf is None:
+            if len(pool) > 32:
+                pool.clear()
+            buf = torch.empty(key, dtype=torch.float64, pin_memory=True)
+            pool[key] = buf
+        return buf
 
     def _finish(self, log_max: np.ndarray, rel_sum: np.ndarray) -> np.ndarray:
         """float64 density from the log-domain partials, with the reference's underflow:
@@ -197,3 +211,44 @@ class StableGaussianKDE:
         density[largest_term == 0] = 0.0
         density[~np.isfinite(log_max)] = 0.0
         return density
+
+
+class _PendingDensity:
+    """A density evaluation in flight (see StableGaussianKDE._density_begin)."""
+
+    def __init__(self, kde, host, m, n_s, done, q):
+        self.kde, self.host, self.m, self.n_s, self.done, self.q = kde, host, m, n_s, done, q
+
+    def finish(self) -> np.ndarray:
+        import torch
+
+        kde = self.kde
+        if self.m <= 0:
+            return np.zeros(-self.m)               # empty batch, or a KDE whose fit failed: all densities 0
+        self.done.synchronize()
+        packed = self.host.numpy().copy()
+        m, n_s = self.m, self.n_s
+        if n_s == 0:
+            return kde._finish(packed[0], packed[1])
+        fast_lm, fast_rs = packed[0, :m], packed[1, :m]
+        ref_lm, ref_rs = packed[0, m:m + n_s], packed[1, m:m + n_s]
+        idx = packed[0, m + n_s:].astype(np.int64)
+        overflow = packed[1, m + n_s] != 0
+        with np.errstate(divide="ignore", invalid="ignore", under="ignore"):
+            l_fast = -(kde.log_norm - math.log(kde.n) + fast_lm[idx] + np.log(fast_rs[idx]))
+            l_ref = -(kde.log_norm - math.log(kde.n) + ref_lm + np.log(ref_rs))
+            both = np.isfinite(l_fast) & np.isfinite(l_ref)
+            worst = float(np.max(np.abs(l_fast[both] - l_ref[both]) / np.abs(l_ref[both]))) if both.any() else 0.0
+        same_inf = np.array_equal(np.isfinite(l_fast), np.isfinite(l_ref))
+        kde.last_fast_check = {"rows": int(n_s), "max_rel_diff": worst,
+                               "accepted": bool(not overflow and same_inf and worst <= kde.FAST_RTOL)}
+        if kde.last_fast_check["accepted"]:
+            kde.last_operands = "fp16 x1 (verified on %d sampled rows: max rel diff %.2e)" % (n_s, worst)
+            # (the sampled rows keep their fast values too: a row's score must not depend on where it sits in the batch)
+            return kde._finish(fast_lm, fast_rs)
+        eng = kde._engine
+        eng.fast_ok = False
+        mx, sm, qsq = eng.log_kernel_sum(self.q)
+        mx = mx.to(torch.float64) - 0.5 * qsq.to(torch.float64)
+        out = torch.stack([mx, sm.to(torch.float64)]).cpu().numpy()
+        return kde._finish(out[0], out[1])

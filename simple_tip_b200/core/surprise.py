@@ -139,9 +139,22 @@ class SA(abc.ABC):
     def score(self, activations, predictions=None, **kw) -> np.ndarray:
         return self(activations, predictions, **kw)
 
+    def score_begin(self, activations, predictions=None):
+        """Start scoring and return an object whose `finish()` yields the scores.  Default: score synchronously.
+        Scorers that can keep their kernels and the result copy in flight override this (LSA)."""
+        return _Finished(self(activations, predictions))
+
     @classmethod
     def fit(cls, *args, **kw):
         return cls(*args, **kw)
+
+
+class _Finished:
+    def __init__(self, value):
+        self.value = value
+
+    def finish(self):
+        return self.value
 
 
 class MultiModalSA(SA):
@@ -189,13 +202,36 @@ class MultiModalSA(SA):
         if len(modal) == 0:
             return np.ndarray(shape=(0,))
         present = np.unique(modal)
-        # One CUDA stream serves all modals; the per-modal calls are issued in order (the
-        # reference's thread pool, surprise.py:345, only overlapped CPU work).
-        per_modal = []
-        for mid in present:
-            sa = self._get_sa_for_modal_id(mid)
-            rows = modal == mid
-            per_modal.append(sa(acts[rows], None if preds is None else preds[rows], num_threads=num_threads))
+        sas = [self._get_sa_for_modal_id(mid) for mid in present]
+        # One CUDA stream serves all modals (the reference's thread pool, surprise.py:345, only overlapped CPU
+        # work).  The traces are uploaded ONCE and split by modal on the device; every modal's kernels and its
+        # result copy are launched before the first result is waited for (`score_begin` / `finish`).
+        per_modal = None
+        if isinstance(acts, np.ndarray) and acts.dtype in (np.float32, np.float64) and len(present) > 1:
+            try:
+                import torch
+
+                from .. import engine as E
+
+                dev = E.require_cuda()
+                order = np.argsort(modal, kind="stable")
+                counts = [int(np.count_nonzero(modal == mid)) for mid in present]
+                x_sorted = E.to_device(acts, dev).index_select(0, torch.from_numpy(order).to(dev))
+                pending, lo = [], 0
+                for sa, mid, cnt in zip(sas, present, counts):
+                    rows = order[lo:lo + cnt]
+                    pending.append(sa.score_begin(x_sorted[lo:lo + cnt], None if preds is None else preds[rows]))
+                    lo += cnt
+                per_modal = [p.finish() for p in pending]
+            except RuntimeError as e:
+                if "CUDA device" not in str(e):
+                    raise
+                per_modal = None      # no GPU: let the per-modal calls raise their own (loud) error below
+        if per_modal is None:
+            per_modal = []
+            for sa, mid in zip(sas, present):
+                rows = modal == mid
+                per_modal.append(sa(acts[rows], None if preds is None else preds[rows], num_threads=num_threads))
         res = np.full(fill_value=-np.inf, shape=modal.shape, dtype=per_modal[0].dtype)
         for mid, vals in zip(present, per_modal):
             res[modal == mid] = vals
@@ -381,6 +417,9 @@ class LSA(SA):
         return tr_activations
 
     def __call__(self, activations, predictions=None, num_threads: int = 0) -> np.ndarray:
+        return self.score_begin(activations, predictions).finish()
+
+    def score_begin(self, activations, predictions=None):
         from .. import engine as E
 
         dev = E.device_matrix(activations)            # traces already in HBM stay there
@@ -391,11 +430,19 @@ class LSA(SA):
             raise ValueError(f"activation traces have {tuple(activations.shape)[1:]} features per sample, "
                              f"this LSA was fitted on {self._source_width}")
         if self.kde is None:
-            return np.zeros(shape=(activations.shape[0],))
+            return _Finished(np.zeros(shape=(activations.shape[0],)))
         # column removal happens on the GPU (the kde knows which source columns it was fitted on)
-        density = self.kde.evaluate_rows(activations)
+        return _PendingLsa(self.kde.evaluate_rows_begin(activations))
+
+
+class _PendingLsa:
+    def __init__(self, pending_density):
+        self.pending = pending_density
+
+    def finish(self) -> np.ndarray:
+        density = self.pending.finish()
         with np.errstate(divide="ignore"):
-            return -np.log(density)
+            return -np.log(density)                  # surprise.py:494-495
 
 
 # ------------------------------------------------------------------------------------------

@@ -180,3 +180,51 @@ def test_mdsa_mlsa_kmeans_paths():
     assert len(set(disc(pts, None))) == 2
     mm = MultiModalSA.build_with_kmeans(two, None, lambda x, _: MDSA(x), potential_k=[2, 3, 4])
     assert np.all(mm(pts + 2, None) > mm(pts, None))
+
+
+# ---- reference tests/test_prioritizers.py:11-135 (paper example under every shape / shuffle, fuzzer) ------------
+def _paper_example(seed):
+    import random
+
+    rows = [[True, True, True, False, False, True, True, True], [True, True, True, False, False, False, True, True],
+            [True, True, True, True, False, False, False, False], [False, False, False, False, True, True, True, True]]
+    names = ["A", "B", "C", "D"]
+    random.Random(seed).shuffle(rows)
+    random.Random(seed).shuffle(names)
+    return np.array(rows, dtype=bool), names
+
+
+@pytest.mark.gpu
+def test_cam_paper_example_every_shape_and_shuffle():
+    for seed in range(10):
+        profile, names = _paper_example(seed)
+        scores = np.sum(profile, axis=1)
+        assert [names[i] for i in ctm(scores)] in (["A", "B", "C", "D"], ["A", "B", "D", "C"])
+        for shape in [(4, 8), (4, 8, 1), (4, 4, 2), (4, 2, 2, 2), (-1, 2, 4)]:
+            got = [names[i] for i in cam(scores, np.reshape(profile, shape))]
+            assert got in (["A", "D", "C", "B"], ["A", "C", "D", "B"]), (seed, shape, got)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape, prob", [((20, 100), 0.1), ((200, 1000), 0.0001), ((2000, 10000), 0.01), ((4000, 40000), 0.01)])
+def test_cam_fuzzer_invariants(shape, prob):
+    """The consistency checks of the reference's test_cam_fuzzer: a permutation; coverage increments weakly
+    decreasing while coverage grows; afterwards scores weakly decreasing."""
+    rng = np.random.default_rng(1)
+    profile = rng.random(shape) < prob
+    scores = np.sum(profile, axis=1)
+    order = [i for i in cam(scores, profile.copy())]
+    assert sorted(order) == list(range(shape[0]))
+    covered = np.zeros(shape[1], dtype=bool)
+    last_inc, prev_sum, last_score, tail = np.inf, 0, np.inf, False
+    for i in order:
+        covered |= profile[i]
+        new_sum = int(covered.sum())
+        inc = new_sum - prev_sum
+        assert inc <= last_inc
+        if inc == 0:
+            tail = True
+        if tail:
+            assert inc == 0 and scores[i] <= last_score
+            last_score = scores[i]
+        last_inc, prev_sum = inc, new_sum
