@@ -232,14 +232,16 @@ __device__ __forceinline__ uint32_t seed_row_min_bits(float ub, float nx, float 
 // One query row -> packed bf16 operand of tip_nn_filter (one segment) + reset filter state, by a full
 // warp: the arithmetic of pair_prep_kernel (query role): centre in fp32, round to bf16, |h|^2 and
 // the dropped part's norm accumulated in double.  src == nullptr packs a zero row.
-template <typename T>
+template <typename T, int NL = 32>
 __device__ __forceinline__ void warp_pack_query(const T* __restrict__ src, int d, const float* __restrict__ center,
                                                 __nv_bfloat16* __restrict__ out, int64_t pitch, float* sqnorm,
                                                 float* rounderr, uint32_t* row_min, int32_t* cand_cnt, int lane,
-                                                float seed_ub = 3.4e38f, const SeedParams* sp = nullptr) {
+                                                float seed_ub = 3.4e38f, const SeedParams* sp = nullptr,
+                                                unsigned mask = 0xffffffffu) {
+  // NL cooperating lanes (a full warp, or one 8-lane group of it: `lane` in [0, NL), `mask` names the group)
   const int d16 = (d + 15) & ~15;
   double acc = 0.0, err = 0.0;
-  for (int c = lane; c < d16; c += 32) {
+  for (int c = lane; c < d16; c += NL) {
     float v = 0.f;
     if (c < d) {
       const T xv = src ? src[c] : (T)0;
@@ -253,9 +255,12 @@ __device__ __forceinline__ void warp_pack_query(const T* __restrict__ src, int d
     err += (double)res * (double)res;
     out[c] = h;
   }
-  acc = warp_sum(acc);
-  err = warp_sum(err);
-  for (int c = d16 + lane; c < pitch; c += 32) out[c] = __float2bfloat16_rn(c - d16 < 3 ? 1.f : 0.f);
+#pragma unroll
+  for (int o = NL / 2; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(mask, acc, o);
+    err += __shfl_xor_sync(mask, err, o);
+  }
+  for (int c = d16 + lane; c < pitch; c += NL) out[c] = __float2bfloat16_rn(c - d16 < 3 ? 1.f : 0.f);
   if (lane == 0) {
     const float nx = (float)acc;
     const float qe = (float)sqrt(err) * 1.000001f;
