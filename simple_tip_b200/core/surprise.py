@@ -510,7 +510,7 @@ class DSA(SA):
                 full = full.to(torch.float32)
             keep = E.shard_rows(labels, int(self.num_classes), self._comm.rank, self._comm.world)
             shard = full.index_select(0, torch.from_numpy(keep).to(dev))
-            self._engine = E.NnEngine.from_host(shard, labels[keep], int(self.num_classes), keep)
+            self._engine = E.NnEngine.from_host(shard, labels[keep], int(self.num_classes), keep, seeds=False)
             self._engine.t_full = full.contiguous()
         else:
             self._engine = E.NnEngine.from_host(train, labels, int(self.num_classes), np.arange(train.shape[0]))

@@ -621,7 +621,7 @@ class NnEngine:
 
     @classmethod
     def from_host(cls, train: np.ndarray, labels: np.ndarray, num_classes: int, gids: Optional[np.ndarray] = None,
-                  cap: Optional[int] = None) -> "NnEngine":
+                  cap: Optional[int] = None, seeds: bool = True) -> "NnEngine":
         dev = require_cuda()
         order, off = class_layout(labels, num_classes)
         t = to_device(train, dev)
@@ -629,7 +629,7 @@ class NnEngine:
         gid = idx if gids is None else torch.from_numpy(np.asarray(gids)[order]).to(dev)
         if t.dtype not in (torch.float32, torch.float64):
             t = t.to(torch.float32)          # device-resident bf16 / fp16 traces: exact widening
-        return cls(t.index_select(0, idx), off, gid, cap)
+        return cls(t.index_select(0, idx), off, gid, cap, seeds)
 
     def work_buffer(self, m: int, dtype: torch.dtype) -> torch.Tensor:
         """Scratch of tip_nn_rerank for m queries: zero-filled once, every call leaves it re-armed."""
