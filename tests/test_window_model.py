@@ -104,3 +104,47 @@ def test_window_is_tight_enough_for_aligned_rounding(d):
             me._check(x, Y, mu, rng)
     finally:
         me._threshold = orig
+
+
+def _seed_s(ub, nx, q_err, t_rmax, t_err, gamma):
+    """seed_row_min_bits() of csrc/common.cuh in float32."""
+    r = F32(F32(np.sqrt(nx, dtype=F32)) + t_rmax)
+    e = F32(F32(q_err + t_err + F32(1.2e-7) * r) * F32(1.00001))
+    g = F32(gamma * r * r)
+    d = F32(F32(ub * F32(1.000004)) + e)
+    return F32(F32(d * d + g) * F32(1.000002))
+
+
+@pytest.mark.parametrize("d", [3, 64, 128])
+def test_seed_from_any_in_range_row_never_undercuts_that_rows_accumulator(d):
+    """Stage-2 seeds (tip_nn_rerank next_seed_ub): the running minimum of a query starts at a value derived from
+    its NumPy distance to SOME row of the range.  For the window proof that value must be >= the approximate squared
+    distance the filter can compute for that row (worst-case accumulation error included): then every threshold
+    derived from the seed is at least as wide as one the scan itself would reach, and the seed row is itself emitted."""
+    rng = np.random.default_rng(100 + d)
+    for trial in range(30):
+        n = int(rng.integers(2, 200))
+        scale = float(rng.choice([1e-3, 1.0, 50.0]))
+        offset = rng.normal(size=d).astype(F32) * F32(rng.choice([0.0, 5.0, 300.0]))
+        Y = (rng.normal(size=(n, d)).astype(F32) * F32(scale) + offset).astype(F32)
+        x = Y[int(rng.integers(0, n))].copy() if trial % 3 == 0 else (rng.normal(size=d).astype(F32) * F32(scale) + offset).astype(F32)
+        mu = Y.mean(axis=0, dtype=np.float64).astype(F32)
+        xt, Yt = (x - mu).astype(F32), (Y - mu).astype(F32)
+        xb, Yb = _bf16(xt), _bf16(Yt)
+        errq = F32(np.sqrt(np.sum((xt.astype(np.float64) - xb) ** 2))) * F32(1.000001)
+        errt = F32(np.sqrt(np.max(np.sum((Yt.astype(np.float64) - Yb) ** 2, axis=1)))) * F32(1.000001) * F32(1.000001)
+        nx = F32(np.sum(xb.astype(np.float64) ** 2))
+        rmax = F32(np.sqrt(np.max(np.sum(Yb.astype(np.float64) ** 2, axis=1)))) * F32(1.000001)
+        k = ((d + 15) // 16) * 16 + 16
+        gamma = F32((k + 16) * 2.0 ** -23)
+        r = F32(np.sqrt(nx) + rmax)
+        g = float(F32(gamma * r * r))
+        dist_np = np.linalg.norm((x[None, None, :] - Y[None, :, :]).astype(F32), axis=2)[0]
+        acc_exact = np.sum(Yb.astype(np.float64) ** 2, axis=1) - 2.0 * (Yb.astype(np.float64) @ xb.astype(np.float64))
+        s_worst = acc_exact + g + float(nx)                      # the largest s the filter may compute for each row
+        for j in rng.integers(0, n, size=5):
+            seed = _seed_s(F32(dist_np[j]), nx, errq, rmax, errt, gamma)
+            assert float(seed) >= s_worst[j], (d, trial, j, float(seed), s_worst[j])
+            # and the threshold from the seed admits the seed row (it will be emitted as a candidate)
+            e2 = F32(F32(2.0) * F32(errq + errt + F32(1.2e-7) * r) * F32(1.00001))
+            assert acc_exact[j] + g <= _threshold(seed, nx, e2, F32(g))
