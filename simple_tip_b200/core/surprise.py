@@ -207,7 +207,8 @@ class MultiModalSA(SA):
         # work).  The traces are uploaded ONCE and split by modal on the device; every modal's kernels and its
         # result copy are launched before the first result is waited for (`score_begin` / `finish`).
         per_modal = None
-        if isinstance(acts, np.ndarray) and acts.dtype in (np.float32, np.float64) and len(present) > 1:
+        ours = all(isinstance(sa, (LSA, MDSA, MLSA, DSA)) for sa in sas)    # user-defined SAs keep getting NumPy arrays
+        if ours and isinstance(acts, np.ndarray) and acts.dtype in (np.float32, np.float64) and len(present) > 1:
             try:
                 import torch
 
