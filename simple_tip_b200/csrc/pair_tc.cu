@@ -97,10 +97,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded spin: a protocol bug must surface as a trapped kernel, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t max_spins = 200000000u) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 200000000u) __trap();
+    if (++spins > max_spins) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -606,6 +606,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // accumulator stage on the leader's barrier.
 // =============================================================================================
 constexpr int kP2Stages = 6;
+constexpr uint32_t kP2Spins = 20000000u;   // a protocol bug traps within seconds
 constexpr int kP2ABytes = 128 * BK * 2;
 constexpr int kP2BBytes = 128 * BK * 2;
 constexpr int kP2StageBytes = kP2ABytes + kP2BBytes;
@@ -664,7 +665,7 @@ pair2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int ntiles = (it.col1 - it.col0 + BN - 1) / BN;
         for (int t = 0; t < ntiles; t++) {
           for (int c = 0; c < nchunks; c++) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_wait(empty_bar(stage), phase ^ 1u, kP2Spins);
             const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
             if (leader_cta) mbar_expect_tx(full_bar(stage), 2 * kP2StageBytes);
             const uint32_t a_dst = base + stage * kP2StageBytes;
@@ -688,11 +689,11 @@ pair2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const tip_work_item it = args.items[w];
         const int ntiles = (it.col1 - it.col0 + BN - 1) / BN;
         for (int t = 0; t < ntiles; t++) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u, kP2Spins);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
           for (int c = 0; c < nchunks; c++) {
-            mbar_wait(full_bar(stage), phase);
+            mbar_wait(full_bar(stage), phase, kP2Spins);
             tc_fence_after();
             const uint32_t a_addr = base + stage * kP2StageBytes;
             const uint64_t adesc = smem_desc(a_addr);
@@ -751,7 +752,7 @@ pair2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         st.thr = nn_threshold(st.s_ref, st.nx, st.e2, st.g);
       }
       for (int t = 0; t < ntiles; t++) {
-        mbar_wait(tfull_bar(acc), acc_phase);
+        mbar_wait(tfull_bar(acc), acc_phase, kP2Spins);
         tc_fence_after();
         const int col_base = it.col0 + t * BN + half * (BN / 2);
         const bool partial = col_base + BN / 2 > it.col1;
