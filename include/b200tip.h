@@ -180,10 +180,11 @@ int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d, const flo
                   float* sqnorm, float* rounderr, void* stream);
 
 /* Query side of tip_nn_filter in one launch: packs the queries (segments = 1, no scaling) and
- * resets the per-query filter state (row_min_bits = +inf, cand_cnt = 0). */
+ * resets the per-query filter state (row_min_bits = +inf, cand_cnt = 0).  q_idx (may be NULL): packed row r is
+ * taken from q + q_idx[r]*d — the class-sorting gather of DSA.__call__ (surprise.py:580-587) fused into the pack. */
 int tip_nn_query_prep(const void* q, int dtype, int64_t m, int64_t d, const float* center,
                       void* q_pack, float* q_sqnorm, float* q_rounderr, uint32_t* row_min_bits,
-                      int32_t* cand_cnt, void* stream);
+                      int32_t* cand_cnt, const int32_t* q_idx, void* stream);
 
 /* ---- nearest-neighbour candidate filter (tcgen05 + TMA) ------------------------------
  * q_pack: m x pitch, t_pack: n x pitch (tip_pair_prep, scale=-2, norm_coef=1).
@@ -245,12 +246,25 @@ int tip_kde_tile_rows(void);
  * also emitted as the packed queries and reset filter state of a following tip_nn_filter call —
  * exactly what tip_nn_query_prep(out_rows, center = next_center) would write — so DSA's second
  * stage (whose queries are stage 1's winners, surprise.py:627-629) needs no pack launch.
+ * extras (optional, host struct read at launch time):
+ * q_idx: the queries are rows q_idx[r] of q (no separately gathered copy needed); fin_*: fused result scatter.
  * next_seed_ub (optional, with next_rounderr): n floats, for every train row an upper bound on its exact
  * distance to SOME row the next search will scan for it (e.g. its nearest other-class row inside a fixed sample
  * of the training set, computed once at fit time; +inf = none).  The winner's bound, widened by the filter's own
  * error terms (next_t_rmax / next_t_errmax = the t_rmax / t_errmax of the next tip_nn_filter call), becomes the
  * initial next_row_min_bits instead of +inf: the next filter collects no far-away candidates while its running
  * minima warm up.  A seed never narrows the proven window below the final one. */
+typedef struct tip_rerank_extras {
+  const int32_t* q_idx;       /* query row r is q + q_idx[r]*d (e.g. class-sorted order over the caller's buffer) */
+  const float* next_seed_ub;  /* see above */
+  float next_t_rmax;
+  float next_t_errmax;
+  const void* fin_dist_a;     /* fused result scatter: with fin_out != NULL this search's distance is taken as dist_b */
+  const int32_t* fin_gid;     /* and out[0..3][fin_idx[r]] = dist_a, dist_b, gid, dist_a / dist_b as tip_dsa_pack_out */
+  const int32_t* fin_idx;     /* writes them (fin_idx == NULL: r itself); fin_dist_a in `dtype`, fin_out 4*fin_n_total */
+  int64_t fin_n_total;        /* doubles */
+  double* fin_out;
+} tip_rerank_extras;
 int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype);
 int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n, int64_t d,
                   const int32_t* cand_idx, const int32_t* cand_cnt, int32_t cap,
@@ -258,8 +272,8 @@ int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n,
                   const int32_t* t_gid, void* out_dist, int32_t* out_pos, int32_t* out_gid,
                   void* out_rows, int32_t* work, int64_t* stats, const float* next_center,
                   void* next_pack, float* next_sqnorm, float* next_rounderr,
-                  uint32_t* next_row_min_bits, int32_t* next_cand_cnt, const float* next_seed_ub,
-                  float next_t_rmax, float next_t_errmax, void* stream);
+                  uint32_t* next_row_min_bits, int32_t* next_cand_cnt, const tip_rerank_extras* extras,
+                  void* stream);
 
 /* DSA result packing (surprise.py:576-611 scatter by index): for i < m,
  *   out[0*n_total + j] = dist_a[i], out[1*n_total + j] = dist_b[i], out[2*n_total + j] = gid[i],

@@ -21,6 +21,13 @@ RANGE_SAME_CLASS, RANGE_OTHER_CLASSES = 0, 1
 ROW_TILE, COL_TILE = 128, 256
 
 
+class RerankExtras(C.Structure):
+    """tip_rerank_extras of include/b200tip.h"""
+    _fields_ = [("q_idx", C.c_void_p), ("next_seed_ub", C.c_void_p), ("next_t_rmax", C.c_float),
+                ("next_t_errmax", C.c_float), ("fin_dist_a", C.c_void_p), ("fin_gid", C.c_void_p),
+                ("fin_idx", C.c_void_p), ("fin_n_total", C.c_int64), ("fin_out", C.c_void_p)]
+
+
 class WorkItem(C.Structure):
     _fields_ = [("q_row0", C.c_int32), ("q_rows", C.c_int32), ("col0", C.c_int32), ("col1", C.c_int32),
                 ("slot", C.c_int32), ("reserved", C.c_int32)]
@@ -48,9 +55,9 @@ _SIGNATURES = {
     "tip_nn_filter": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _f32, _vp, _vp,
                                 _vp, _i32, _i32, _vp, _vp]),
     "tip_nn_rerank_work_bytes": (_i64, [_i64, C.c_int]),
-    "tip_nn_query_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tip_nn_query_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tip_nn_rerank": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, C.c_int,
-                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp]),
+                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tip_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "tip_dsa_pack_out": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _i64, _i64, _vp, _vp]),
     "tip_comm_bytes": (_i64, [_i32, _i64]),

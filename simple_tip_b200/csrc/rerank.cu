@@ -80,16 +80,39 @@ struct RerankArgs {
   uint32_t* next_row_min;
   int32_t* next_cand_cnt;
   SeedParams seed;    // optional: per-train-row upper bounds that seed the next stage's running minima
+  const int32_t* q_idx;   // optional: query row r lives at q + q_idx[r] * d (class-sorted order over the caller's buffer)
+  // optional fused result scatter (what tip_dsa_pack_out does): this search's distance is dist_b
+  const T* fin_dist_a;
+  const int32_t* fin_gid;
+  const int32_t* fin_idx;
+  int64_t fin_n_total;
+  double* fin_out;
 };
+
+template <typename T>
+__device__ __forceinline__ const T* query_row(const RerankArgs<T>& a, int64_t row) {
+  return a.q + (a.q_idx ? (int64_t)a.q_idx[row] : row) * (int64_t)a.d;
+}
 
 template <typename T, int NL = 32>
 __device__ __forceinline__ void write_result(const RerankArgs<T>& a, int64_t row, const Best<T>& b, int lane, int nlanes,
                                              unsigned mask = 0xffffffffu) {
   // all `nlanes` (== NL) threads of the caller hold the same `b`; `lane` in [0, NL)
   if (lane == 0) {
-    a.out_dist[row] = b.pos >= 0 ? b.dist : (T)NAN;   // empty range -> NaN / -1
+    const T dist = b.pos >= 0 ? b.dist : (T)NAN;   // empty range -> NaN / -1
+    a.out_dist[row] = dist;
     a.out_pos[row] = b.pos;
     if (a.out_gid) a.out_gid[row] = b.pos >= 0 ? (a.t_gid ? a.t_gid[b.pos] : b.pos) : -1;
+    if (a.fin_out) {   // dist_a, dist_b, winner index, dist_a / dist_b in the caller's row order (surprise.py:595,611)
+      const int64_t j = a.fin_idx ? a.fin_idx[row] : row;
+      if (j >= 0 && j < a.fin_n_total) {
+        const T da = a.fin_dist_a[row];
+        a.fin_out[j] = (double)da;
+        a.fin_out[a.fin_n_total + j] = (double)dist;
+        a.fin_out[2 * a.fin_n_total + j] = (double)a.fin_gid[row];
+        a.fin_out[3 * a.fin_n_total + j] = (double)Rn<T>::div(da, dist);
+      }
+    }
   }
   const T* src = a.t + (int64_t)(b.pos < 0 ? 0 : b.pos) * a.d;
   if (a.out_rows) {
@@ -122,7 +145,7 @@ __global__ void __launch_bounds__(256, (SMALL && sizeof(T) == 4) ? 4 : 1) rerank
   const bool spec = a.cand_cnt != nullptr && a.cap >= 4;
   int2 first = make_int2(0, 0);
   if (spec) first = *reinterpret_cast<const int2*>(a.cand_idx + (row * (int64_t)a.cap + grp) * 2);
-  const T* x = a.q + row * (int64_t)a.d;
+  const T* x = query_row(a, row);
   const int n = a.d;
   const int lim = n - (n % 8);
   T xr[SMALL ? 16 : 1], xt[SMALL ? 7 : 1];
@@ -233,7 +256,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 4 : 1) rerank_group_kern
   const bool spec = a.cand_cnt != nullptr;
   int2 first = make_int2(0, 0);
   if (spec) first = *reinterpret_cast<const int2*>(a.cand_idx + row * (int64_t)a.cap * 2);
-  const T* x = a.q + row * (int64_t)a.d;
+  const T* x = query_row(a, row);
   const int n = a.d;
   const int lim = n - (n % 8);
   T xr[16], xt[7];
@@ -372,7 +395,7 @@ __global__ void __launch_bounds__(kScanThreads) rerank_scan_kernel(const RerankA
     const int w = (int)(u / S), sl = (int)(u % S);
     const int64_t row = a.work[1 + w];
     const int cls = a.q_class ? a.q_class[row] : 0;
-    const T* x = a.q + row * (int64_t)a.d;
+    const T* x = query_row(a, row);
     Best<T> best{Rn<T>::inf(), 0x7fffffff, -1};
     const int c0 = a.class_off[cls], c1 = a.class_off[cls + 1], cn = a.class_off[a.n_classes];
     // SAME_CLASS: [c0, c1);  OTHER_CLASSES: [0, c0) U [c1, cn) — as one linear index space
@@ -424,7 +447,8 @@ static int launch_rerank(const RerankArgs<T>& a, cudaStream_t st) {
   else if (a.d <= 128) rerank_list_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(a);
   else rerank_list_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(a);
   TIP_LAUNCH_CHECK();
-  rerank_scan_kernel<T><<<sm_count() * 8, kScanThreads, 0, st>>>(a);
+  // normally an empty queue: every block returns at once, so keep the grid small (the fallback itself is rare)
+  rerank_scan_kernel<T><<<sm_count() * 2, kScanThreads, 0, st>>>(a);
   TIP_LAUNCH_CHECK();
   return TIP_OK;
 }
@@ -450,9 +474,13 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
                              void* out_dist, int32_t* out_pos, int32_t* out_gid, void* out_rows, int32_t* work,
                              int64_t* stats, const float* next_center, void* next_pack, float* next_sqnorm,
                              float* next_rounderr, uint32_t* next_row_min_bits, int32_t* next_cand_cnt,
-                             const float* next_seed_ub, float next_t_rmax, float next_t_errmax, void* stream) {
+                             const tip_rerank_extras* extras, void* stream) {
   TIP_REQUIRE(q && t && out_dist && out_pos && work, "null pointer");
+  const tip_rerank_extras ex = extras ? *extras : tip_rerank_extras{};
+  const float* next_seed_ub = ex.next_seed_ub;
+  const float next_t_rmax = ex.next_t_rmax, next_t_errmax = ex.next_t_errmax;
   TIP_REQUIRE(next_seed_ub == nullptr || (next_pack && next_rounderr), "seeds need the next-stage query state incl. rounderr");
+  TIP_REQUIRE(ex.fin_out == nullptr || (ex.fin_dist_a && ex.fin_gid && ex.fin_n_total >= 0), "fused result scatter: dist_a, gid, n_total");
   TIP_REQUIRE(class_off && n_classes >= 1, "class offsets");
   TIP_REQUIRE(m >= 0 && m < (1LL << 31) - 8 && n >= 0 && n < (1LL << 31) && d >= 1 && d < (1LL << 31), "shape");
   TIP_REQUIRE(mode == TIP_RANGE_SAME_CLASS || mode == TIP_RANGE_OTHER_CLASSES, "mode");
@@ -468,14 +496,16 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
     RerankArgs<float> a{(const float*)q, (const float*)t, m, n, (int)d, cand_idx, cand_cnt, cap, q_class, class_off,
                         n_classes, mode, t_gid, (float*)out_dist, out_pos, out_gid, (float*)out_rows, work,
                         (unsigned long long*)stats, next_center, (__nv_bfloat16*)next_pack, next_pitch, next_sqnorm,
-                        next_rounderr, next_row_min_bits, next_cand_cnt, seed};
+                        next_rounderr, next_row_min_bits, next_cand_cnt, seed, ex.q_idx, (const float*)ex.fin_dist_a,
+                        ex.fin_gid, ex.fin_idx, ex.fin_n_total, ex.fin_out};
     return launch_rerank<float>(a, st);
   }
   if (dtype == TIP_F64) {
     RerankArgs<double> a{(const double*)q, (const double*)t, m, n, (int)d, cand_idx, cand_cnt, cap, q_class,
                          class_off, n_classes, mode, t_gid, (double*)out_dist, out_pos, out_gid, (double*)out_rows,
                          work, (unsigned long long*)stats, next_center, (__nv_bfloat16*)next_pack, next_pitch,
-                         next_sqnorm, next_rounderr, next_row_min_bits, next_cand_cnt, seed};
+                         next_sqnorm, next_rounderr, next_row_min_bits, next_cand_cnt, seed, ex.q_idx, (const double*)ex.fin_dist_a,
+                         ex.fin_gid, ex.fin_idx, ex.fin_n_total, ex.fin_out};
     return launch_rerank<double>(a, st);
   }
   TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");

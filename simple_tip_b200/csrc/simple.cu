@@ -492,12 +492,13 @@ __global__ void __launch_bounds__(256) pair_prep_kernel(const T* __restrict__ sr
                                                         int segments, float scale, float norm_coef,
                                                         __nv_bfloat16* __restrict__ dst, int64_t pitch,
                                                         float* __restrict__ sqnorm, float* __restrict__ rounderr,
-                                                        uint32_t* __restrict__ row_min, int32_t* __restrict__ cand_cnt) {
+                                                        uint32_t* __restrict__ row_min, int32_t* __restrict__ cand_cnt,
+                                                        const int32_t* __restrict__ src_idx) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int d16 = (d + 15) & ~15;
-  const T* x = src + row * (int64_t)d;
+  const T* x = src + (src_idx ? (int64_t)src_idx[row] : row) * (int64_t)d;
   __nv_bfloat16* out = dst + row * pitch;
   double acc = 0.0, err = 0.0;   // err: squared norm of what the bf16 operand drops (v - h, exact in fp32)
   for (int c = lane; c < d16; c += 32) {
@@ -816,7 +817,7 @@ extern "C" int64_t tip_pair_pitch(int64_t d, int segments) {
 
 static int pair_prep_impl(const void* src, int dtype, int64_t rows, int64_t d, const float* center, int role,
                           int segments, float scale, float norm_coef, void* dst, float* sqnorm, float* rounderr,
-                          uint32_t* row_min, int32_t* cand_cnt, void* stream) {
+                          uint32_t* row_min, int32_t* cand_cnt, const int32_t* src_idx, void* stream) {
   TIP_REQUIRE(src && dst, "null pointer");
   TIP_REQUIRE(segments == 1 || segments == 3, "segments must be 1 or 3");
   TIP_REQUIRE(role == TIP_ROLE_QUERY || role == TIP_ROLE_TRAIN, "role");
@@ -830,11 +831,11 @@ static int pair_prep_impl(const void* src, int dtype, int64_t rows, int64_t d, c
   if (dtype == TIP_F32)
     pair_prep_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)src, rows, (int)d, center, role, segments,
                                                              scale, norm_coef, (__nv_bfloat16*)dst, pitch, sqnorm,
-                                                             rounderr, row_min, cand_cnt);
+                                                             rounderr, row_min, cand_cnt, src_idx);
   else if (dtype == TIP_F64)
     pair_prep_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double*)src, rows, (int)d, center, role,
                                                               segments, scale, norm_coef, (__nv_bfloat16*)dst, pitch,
-                                                              sqnorm, rounderr, row_min, cand_cnt);
+                                                              sqnorm, rounderr, row_min, cand_cnt, src_idx);
   else
     TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
   TIP_LAUNCH_CHECK();
@@ -845,7 +846,7 @@ extern "C" int tip_pair_prep(const void* src, int dtype, int64_t rows, int64_t d
                              int segments, float scale, float norm_coef, void* dst, float* sqnorm, float* rounderr,
                              void* stream) {
   return pair_prep_impl(src, dtype, rows, d, center, role, segments, scale, norm_coef, dst, sqnorm, rounderr, nullptr,
-                        nullptr, stream);
+                        nullptr, nullptr, stream);
 }
 
 extern "C" int tip_pair_prep_f16(const void* src, int dtype, int64_t rows, int64_t d, const float* center, int role,
@@ -875,10 +876,10 @@ extern "C" int tip_pair_prep_f16(const void* src, int dtype, int64_t rows, int64
 
 extern "C" int tip_nn_query_prep(const void* q, int dtype, int64_t m, int64_t d, const float* center, void* q_pack,
                                  float* q_sqnorm, float* q_rounderr, uint32_t* row_min_bits, int32_t* cand_cnt,
-                                 void* stream) {
+                                 const int32_t* q_idx, void* stream) {
   TIP_REQUIRE(q_sqnorm && row_min_bits && cand_cnt, "null pointer");
   return pair_prep_impl(q, dtype, m, d, center, TIP_ROLE_QUERY, 1, 1.0f, 0.0f, q_pack, q_sqnorm, q_rounderr,
-                        row_min_bits, cand_cnt, stream);
+                        row_min_bits, cand_cnt, q_idx, stream);
 }
 
 template <typename T>

@@ -679,14 +679,16 @@ class NnEngine:
                    for c in range(self.num_classes))
 
     def search(self, q: torch.Tensor, q_class: torch.Tensor, q_off: np.ndarray, mode: int, use_filter: bool = True,
-               want_rows: bool = False, prepacked=None, next_query=None):
+               want_rows: bool = False, prepacked=None, next_query=None, q_idx: Optional[torch.Tensor] = None, fin=None):
         """q: [m, d] queries grouped by class (q_off), q_class[m] int32.  Returns, per query, the
         exact NumPy-order distance to its nearest train row in the range selected by `mode`
         (NaN when the range is empty on this shard), that row's position (-1 when empty), its
         original index, and (want_rows) a copy of the winning train rows.
         prepacked: query_state() already filled for q (by a previous search's next_query);
-        next_query: query_state() to fill with the winning rows as the next search's queries."""
-        m = q.shape[0]
+        next_query: query_state() to fill with the winning rows as the next search's queries.
+        q_idx: int32 [m] — the queries are rows q_idx[r] of q (class-sorted order over the caller's buffer; no gathered
+        copy); fin: (dist_a, gid, idx, n_total, out) — fused result scatter of DSA's last stage (tip_rerank_extras)."""
+        m = q.shape[0] if q_idx is None else q_idx.shape[0]
         out_dist = torch.empty(m, dtype=q.dtype, device=self.dev)
         out_pos = torch.empty(m, dtype=torch.int32, device=self.dev)
         out_gid = torch.empty(m, dtype=torch.int32, device=self.dev)
@@ -734,7 +736,7 @@ class NnEngine:
                 else:
                     q_pack, q_sq, q_err, row_min, cand_cnt = self.query_state(m)
                     _lib.check(lib.tip_nn_query_prep(_p(q), tip_dtype(q.dtype), m, self.d, _p(self.center), _p(q_pack),
-                                                     _p(q_sq), _p(q_err), _p(row_min), _p(cand_cnt), _stream()),
+                                                     _p(q_sq), _p(q_err), _p(row_min), _p(cand_cnt), _p(q_idx), _stream()),
                                "tip_nn_query_prep")
                 cand_idx = torch.empty((m, self.cap, 2), dtype=torch.int32, device=self.dev)
                 ev = None
@@ -764,12 +766,21 @@ class NnEngine:
         seed = self.seed_b if (next_query is not None and mode == _lib.RANGE_SAME_CLASS) else None
         if self._capture_refs is not None and seed is not None:
             self._capture_refs.append(seed)
+        ex = _lib.RerankExtras()
+        ex.q_idx = 0 if q_idx is None else q_idx.data_ptr()
+        ex.next_seed_ub = 0 if seed is None else seed.data_ptr()
+        ex.next_t_rmax, ex.next_t_errmax = self.rmax, self.errmax
+        if fin is not None:
+            f_a, f_gid, f_idx, f_n, f_out = fin
+            ex.fin_dist_a, ex.fin_gid = f_a.data_ptr(), f_gid.data_ptr()
+            ex.fin_idx = 0 if f_idx is None else f_idx.data_ptr()
+            ex.fin_n_total, ex.fin_out = int(f_n), f_out.data_ptr()
         _lib.check(lib.tip_nn_rerank(_p(q), _p(self.t), tip_dtype(q.dtype), m, self.n, self.d, _p(cand_idx),
                                      _p(cand_cnt), self.cap, _p(q_class), _p(self.class_off_dev), self.num_classes,
                                      mode, _p(self.t_gid), _p(out_dist), _p(out_pos), _p(out_gid), _p(out_rows),
                                      _p(work), _p(self.stats),
                                      _p(self.center) if next_query is not None else None, *nq,
-                                     _p(seed), self.rmax, self.errmax, _stream()),
+                                     C.byref(ex), _stream()),
                    "tip_nn_rerank")
         self.last_cand_cnt = cand_cnt
         if cand_cnt is not None:
@@ -803,20 +814,24 @@ def winner_queries(engine: "NnEngine", p2p: Optional[P2PExchange], gdist: Option
 
 
 def dsa_distances(engine: NnEngine, x: torch.Tensor, q_class: torch.Tensor, q_off: np.ndarray,
-                  comm: Optional[TrainShardComm] = None, use_filter: bool = True
-                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                  comm: Optional[TrainShardComm] = None, use_filter: bool = True, q_idx: Optional[torch.Tensor] = None,
+                  scatter=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """surprise.py:615-631 for class-sorted queries x: (dist_a, dist_b, winner original index).
-    Eager launches (the CUDA-graph plans below replay the same sequence)."""
+    Eager launches (the CUDA-graph plans below replay the same sequence).  Single shard only: q_idx — the
+    class-sorted queries are rows q_idx[r] of x (the gather is fused into the pack and the re-rank); scatter =
+    (idx, n_total, out) — the last re-rank also writes dist_a, dist_b, winner, dist_a / dist_b into out[4, n_total]."""
     sharded = comm is not None and comm.world > 1
-    m = x.shape[0]
+    m = x.shape[0] if q_idx is None else q_idx.shape[0]
     if not sharded:
         # single shard: stage 1's re-rank also emits its winners as the packed queries of stage 2
         fuse = use_filter and engine.has_items(q_off, _lib.RANGE_OTHER_CLASSES)
         state2 = engine.query_state(m) if fuse else None
         dist_a, _, gid, winners = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter, want_rows=True,
-                                                next_query=state2)
-        dist_b = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter, prepacked=state2)[0]
+                                                next_query=state2, q_idx=q_idx)
+        fin = None if scatter is None else (dist_a, gid, scatter[0], scatter[1], scatter[2])
+        dist_b = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter, prepacked=state2, fin=fin)[0]
         return dist_a, dist_b, gid
+    assert q_idx is None and scatter is None
     replica = engine.t_full is not None
     p2p = comm.p2p(engine.dev, m) if replica else None
     local_a, _, local_gid, local_rows = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter,
@@ -924,7 +939,17 @@ class DsaPlan:
                                             self.n_total, _p(self.out), _stream()), "tip_dsa_pack_out")
             self.dist_a, self.dist_b, self.gid = a, b, gid
 
-        if not sharded or self.p2p is not None:
+        if not sharded:
+            def whole():
+                # gather fused into the pack / re-rank (q_idx), result scatter fused into the last re-rank
+                if self.n_total != self.m:         # which rows are unscored can change between calls
+                    self.out.fill_(float("nan"))
+                    self.out[2].fill_(-1.0)
+                self.dist_a, self.dist_b, self.gid = dsa_distances(engine, self.x_in, self.q_class, self.q_off, None, use_filter,
+                                                                   q_idx=self.idx, scatter=(self.idx, self.n_total, self.out))
+
+            segments = [(whole, True)]
+        elif self.p2p is not None:
             def whole():
                 gather()
                 scatter(*dsa_distances(engine, self.x, self.q_class, self.q_off, self.comm, use_filter))
