@@ -57,7 +57,7 @@ _SIGNATURES = {
     "tip_nn_rerank_work_bytes": (_i64, [_i64, C.c_int]),
     "tip_nn_query_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tip_nn_rerank": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, C.c_int,
-                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tip_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "tip_dsa_pack_out": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _i64, _i64, _vp, _vp]),
     "tip_comm_bytes": (_i64, [_i32, _i64]),
