@@ -265,6 +265,7 @@ typedef struct tip_rerank_extras {
   int64_t fin_n_total;        /* doubles */
   double* fin_out;
 } tip_rerank_extras;
+int32_t tip_sizeof_rerank_extras(void);   /* bindings check their struct layout against this */
 int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype);
 int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m, int64_t n, int64_t d,
                   const int32_t* cand_idx, const int32_t* cand_cnt, int32_t cap,

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "tip_pair_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, C.c_int, C.c_int, _f32, _f32, _vp, _vp, _vp, _vp]),
     "tip_nn_filter": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _f32, _vp, _f32, _vp, _vp,
                                 _vp, _i32, _i32, _vp, _vp]),
+    "tip_sizeof_rerank_extras": (_i32, []),
     "tip_nn_rerank_work_bytes": (_i64, [_i64, C.c_int]),
     "tip_nn_query_prep": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tip_nn_rerank": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, C.c_int,
@@ -108,6 +109,8 @@ def load() -> C.CDLL:
             for name, (res, args) in _SIGNATURES.items():
                 fn = getattr(lib, name)
                 fn.restype, fn.argtypes = res, args
+            if lib.tip_sizeof_rerank_extras() != C.sizeof(RerankExtras):
+                raise RuntimeError("libb200tip.so and simple_tip_b200/_lib.py disagree on tip_rerank_extras: rebuild the library")
             _lib = lib
     return _lib
 

@@ -462,6 +462,8 @@ static int next_pitch_k16(int64_t d) {     // K=16 steps of the one-segment pack
   return (int)((d16 + 16) / 16);
 }
 
+extern "C" int32_t tip_sizeof_rerank_extras(void) { return (int32_t)sizeof(tip_rerank_extras); }
+
 extern "C" int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype) {
   if (m < 0) return -1;
   const int64_t cap = m + kScanUnitTarget;
