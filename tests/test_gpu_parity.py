@@ -501,6 +501,15 @@ def test_dsa_eager_capture_replay_give_the_same_bits():
     # a different batch in between does not disturb the captured plan
     assert np.array_equal(sa(xte[:300], pte[:300]), want["dsa"][:300])
     assert np.array_equal(sa(xte, pte), want["dsa"])
+    # labels beyond the training classes: those rows stay NaN / -1 through the captured plan's fused scatter too
+    p2 = pte.copy()
+    p2[::50] = 99
+    for call in range(3):
+        got = sa(xte, p2)
+        assert np.isnan(got[::50]).all() and (sa.last_winner_index[::50] == -1).all(), call
+        keep = np.ones(pte.shape[0], dtype=bool)
+        keep[::50] = False
+        assert np.array_equal(got[keep], want["dsa"][keep]), call
     eager_first = DSA(xtr, ytr)
     eager_first.capture_on_first_call = True
     assert np.array_equal(eager_first(xte, pte), want["dsa"]) and len(eager_first._engine._plans) == 1
