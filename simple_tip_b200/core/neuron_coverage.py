@@ -198,25 +198,79 @@ class KMNC(CoverageMethod):
         if self._dev_stats is None:
             self._dev_stats = (E.to_device(self._lo.astype(stat_dt), dev), E.to_device(self._jumps, dev))
         lo_dev, jump_dev = self._dev_stats
-        a_dev = E.to_device(act, dev)
         small = self.sections <= np.iinfo(np.int16).max
-        bucket = torch.empty((n, d), dtype=torch.int16 if small else torch.int32, device=dev)
+        bdt, btag = (torch.int16, _lib.TIP_I16) if small else (torch.int32, _lib.TIP_I32)
+
+        def launch(a_chunk, bucket_chunk, score_chunk):
+            _lib.check(lib.tip_kmnc(E._p(a_chunk), E.tip_dtype(act_np_dtype), a_chunk.shape[0], d, E._p(lo_dev), E._p(jump_dev),
+                                    E.tip_dtype(stat_dt), self.sections, E._p(bucket_chunk), btag, E._p(score_chunk),
+                                    E._stream()), "tip_kmnc")
+
+        if device_out or dev_act is not None or n * d * act.dtype.itemsize < self.PIPELINE_BYTES:
+            a_dev = E.to_device(act, dev)
+            bucket = torch.empty((n, d), dtype=bdt, device=dev)
+            score = torch.empty(n, dtype=torch.int32, device=dev)
+            launch(a_dev, bucket, score)
+            if device_out:
+                return score, bucket
+            hb, hs = self._host_buffers(n, d, bdt)
+            hb.copy_(bucket, non_blocking=True)
+            hs.copy_(score, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return hs.numpy().copy(), hb.numpy().copy()
+        # Large host batches: PCIe is the bound (C4: 164 MB up, 82 MB down), so rows go through in chunks with the
+        # upload of chunk i+1, the kernel of chunk i and the download of chunk i-1 in flight together (full duplex).
+        hb, hs = self._host_buffers(n, d, bdt)
+        src = torch.from_numpy(np.ascontiguousarray(act))
+        main = torch.cuda.current_stream()
+        up, down = self._side_streams(dev)
+        rows = max(256, -(-n // self.PIPELINE_CHUNKS))
+        a_dev = torch.empty((n, d), dtype=src.dtype, device=dev)
+        bucket = torch.empty((n, d), dtype=bdt, device=dev)
         score = torch.empty(n, dtype=torch.int32, device=dev)
-        _lib.check(lib.tip_kmnc(E._p(a_dev), E.tip_dtype(act_np_dtype), n, d, E._p(lo_dev), E._p(jump_dev),
-                                E.tip_dtype(stat_dt), self.sections, E._p(bucket),
-                                _lib.TIP_I16 if small else _lib.TIP_I32, E._p(score), E._stream()), "tip_kmnc")
-        if device_out:
-            return score, bucket
-        # D2H into cached pinned buffers (the bucket ids are the bulk of the traffic of this call)
-        key = (n, d, bucket.dtype)
+        up.wait_stream(main)
+        down.wait_stream(main)
+        for r0 in range(0, n, rows):
+            r1 = min(n, r0 + rows)
+            with torch.cuda.stream(up):
+                a_dev[r0:r1].copy_(src[r0:r1], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record()
+            main.wait_event(ready)
+            launch(a_dev[r0:r1], bucket[r0:r1], score[r0:r1])
+            done = torch.cuda.Event()
+            done.record()
+            down.wait_event(done)
+            with torch.cuda.stream(down):
+                hb[r0:r1].copy_(bucket[r0:r1], non_blocking=True)
+                hs[r0:r1].copy_(score[r0:r1], non_blocking=True)
+        down.synchronize()
+        main.wait_stream(up)
+        for t in (a_dev, bucket, score):
+            t.record_stream(up)
+            t.record_stream(down)
+        return hs.numpy().copy(), hb.numpy().copy()
+
+    PIPELINE_BYTES = 32 << 20
+    PIPELINE_CHUNKS = 8
+
+    def _host_buffers(self, n, d, bdt):
+        """pinned result buffers, recycled per shape (the bucket ids are the bulk of the D2H traffic of a call)"""
+        import torch
+
+        key = (n, d, bdt)
         if getattr(self, "_host_key", None) != key:
-            self._host_bucket = torch.empty((n, d), dtype=bucket.dtype, pin_memory=True)
+            self._host_bucket = torch.empty((n, d), dtype=bdt, pin_memory=True)
             self._host_score = torch.empty(n, dtype=torch.int32, pin_memory=True)
             self._host_key = key
-        self._host_bucket.copy_(bucket, non_blocking=True)
-        self._host_score.copy_(score, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return self._host_score.numpy().copy(), self._host_bucket.numpy().copy()
+        return self._host_bucket, self._host_score
+
+    def _side_streams(self, dev):
+        import torch
+
+        if getattr(self, "_streams", None) is None:
+            self._streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        return self._streams
 
     def __call__(self, activations: List[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
         score, bucket = self.buckets(activations)
