@@ -165,7 +165,8 @@ class KMNC(CoverageMethod):
         return [lo + self._jumps * i for i in range(self.sections + 1)]
 
     def buckets(self, activations, device_out: bool = False):
-        """(scores int32 [N], bucket ids [N, D] int16/int32; -1 = no section covered).
+        """(scores [N] in the reference's score dtype — int32 CUDA tensor with device_out —, bucket ids [N, D] int16/int32;
+        -1 = no section covered).
         Activations may be NumPy arrays or device-resident torch tensors (one or a list);
         device_out=True returns the two results as CUDA tensors (no D2H of the N x D bucket ids)."""
         import torch
@@ -217,7 +218,9 @@ class KMNC(CoverageMethod):
             hb.copy_(bucket, non_blocking=True)
             hs.copy_(score, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return hs.numpy().copy(), hb.numpy().copy()
+            # scores in the dtype the reference's sum_score picks (int16 / int32 / int64 by D * sections): np.argsort's tie
+            # order — and with it ctm / the tail of cam — depends on the dtype
+            return hs.numpy().astype(_score_dtype(d * self.sections)), hb.numpy().copy()
         # Large host batches: PCIe is the bound (C4: 164 MB up, 82 MB down), so rows go through in chunks with the
         # upload of chunk i+1, the kernel of chunk i and the download of chunk i-1 in flight together (full duplex).
         hb, hs = self._host_buffers(n, d, bdt)
@@ -225,9 +228,14 @@ class KMNC(CoverageMethod):
         main = torch.cuda.current_stream()
         up, down = self._side_streams(dev)
         rows = max(256, -(-n // self.PIPELINE_CHUNKS))
-        a_dev = torch.empty((n, d), dtype=src.dtype, device=dev)
-        bucket = torch.empty((n, d), dtype=bdt, device=dev)
-        score = torch.empty(n, dtype=torch.int32, device=dev)
+        # device staging recycled per shape: side-stream use would otherwise keep the caching allocator from reusing
+        # the blocks (fresh cudaMalloc of 250 MB per call)
+        dkey = (n, d, src.dtype, bdt)
+        if getattr(self, "_dev_key2", None) != dkey:
+            self._dev_bufs = (torch.empty((n, d), dtype=src.dtype, device=dev), torch.empty((n, d), dtype=bdt, device=dev),
+                              torch.empty(n, dtype=torch.int32, device=dev))
+            self._dev_key2 = dkey
+        a_dev, bucket, score = self._dev_bufs
         up.wait_stream(main)
         down.wait_stream(main)
         for r0 in range(0, n, rows):
@@ -246,10 +254,7 @@ class KMNC(CoverageMethod):
                 hs[r0:r1].copy_(score[r0:r1], non_blocking=True)
         down.synchronize()
         main.wait_stream(up)
-        for t in (a_dev, bucket, score):
-            t.record_stream(up)
-            t.record_stream(down)
-        return hs.numpy().copy(), hb.numpy().copy()
+        return hs.numpy().astype(_score_dtype(d * self.sections)), hb.numpy().copy()
 
     PIPELINE_BYTES = 32 << 20
     PIPELINE_CHUNKS = 8
@@ -277,7 +282,7 @@ class KMNC(CoverageMethod):
         n, d = bucket.shape
         profiles = np.zeros((n, d, self.sections), dtype=bool)
         np.put_along_axis(profiles, np.maximum(bucket, 0).astype(np.int64)[..., None], (bucket >= 0)[..., None], axis=2)
-        return score.astype(_score_dtype(d * self.sections)), profiles
+        return score, profiles
 
 
 class NBC(_ThresholdCoverage):

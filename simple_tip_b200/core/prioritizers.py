@@ -17,6 +17,7 @@ def ctm(scores: np.ndarray) -> Generator[int, None, None]:
 
 
 LAST_GREEDY_PICKS = 0      # greedy rounds of the most recent CAM call (bench / diagnostics)
+LAST_GREEDY_MS = 0.0       # device time of its greedy loop (CUDA events around the launches)
 
 
 def _tail_by_score(scores: np.ndarray, greedy: np.ndarray):
@@ -61,13 +62,18 @@ def cam_from_bits(scores: np.ndarray, bits, rounds_per_launch: int = 4096) -> Ge
         state = torch.zeros(4, dtype=torch.int32, device=dev)
         picks, done, first = 0, False, 1
         rounds = max(2, int(rounds_per_launch) & ~1)              # even: the covered set is double-buffered by parity
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
         while not done and picks < n:
             _lib.check(lib.tip_cam_bits(E._p(bits), n, words, E._p(gain), E._p(covered), E._p(cand), E._p(order),
                                         E._p(state), rounds, first, E._stream()), "tip_cam_bits")
             first = 0
+            ev1.record()
             st = state.cpu().numpy()
             picks, done = int(st[0]), bool(st[1])
         greedy = order[:picks].cpu().numpy().astype(np.int64)
+        global LAST_GREEDY_MS
+        LAST_GREEDY_MS = float(ev0.elapsed_time(ev1))
     global LAST_GREEDY_PICKS
     LAST_GREEDY_PICKS = int(greedy.shape[0])
     yield from (int(i) for i in greedy)

@@ -190,12 +190,20 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma2_acc(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_first(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
 }
 // arrives (once the MMAs issued so far retire) on the barrier at the same offset in BOTH CTAs of the pair
@@ -700,7 +708,17 @@ pair2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const uint64_t bdesc = smem_desc(a_addr + kP2ABytes);
             const int nm = min(4, k16 - 4 * c);
             if (leader) {
-              for (int k = 0; k < nm; k++) umma2_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (c | k) != 0);
+              // straight-line issue (a single thread's dependent stream costs ~45 cycles per instruction: no loop
+              // counters, no runtime predicates on the common path)
+              if (c == 0) umma2_first(d_tmem, adesc, bdesc, idesc);
+              else umma2_acc(d_tmem, adesc, bdesc, idesc);
+              if (nm == 4) {
+                umma2_acc(d_tmem, adesc + 2u, bdesc + 2u, idesc);
+                umma2_acc(d_tmem, adesc + 4u, bdesc + 4u, idesc);
+                umma2_acc(d_tmem, adesc + 6u, bdesc + 6u, idesc);
+              } else {
+                for (int k = 1; k < nm; k++) umma2_acc(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc);
+              }
               umma2_commit(empty_bar(stage));
               if (c == nchunks - 1) umma2_commit(tfull_bar(acc));
             }

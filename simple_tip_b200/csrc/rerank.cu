@@ -438,10 +438,12 @@ template <typename T>
 static int launch_rerank(const RerankArgs<T>& a, cudaStream_t st) {
   // precondition (and postcondition): work[0] == 0 and work[1 + m] == 0
   const int64_t blocks = (a.m + 7) / 8;
-  static int group_mode = -1;     // B200TIP_RERANK_GROUPS=0 keeps one warp per query for short traces too
+  // B200TIP_RERANK_GROUPS=1: one 8-lane group per query (measured SLOWER at C2: 0.216 vs 0.199 ms per step — four
+  // divergent queries per warp serialise more than the extra resident queries buy); default: one warp per query
+  static int group_mode = -1;
   if (group_mode < 0) {
     const char* e = getenv("B200TIP_RERANK_GROUPS");
-    group_mode = (e && e[0] == '0') ? 0 : 1;
+    group_mode = (e && e[0] == '1') ? 1 : 0;
   }
   if (a.d <= 128 && group_mode) rerank_group_kernel<T><<<(unsigned)((a.m + 31) / 32), 256, 0, st>>>(a);
   else if (a.d <= 128) rerank_list_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(a);

@@ -368,12 +368,16 @@ struct KmncFast {
 };
 // A neuron that can never be covered (jump <= 0 or NaN: constant / inverted range) costs nothing extra: its
 // inv is 0, its bias -3 and its lim +inf, so every finite activation lands on "section -3" = not covered.
-__device__ __forceinline__ KmncFast kmnc_fast(float a, float lo, float inv, float bias, float lim, int k) {
+__device__ __forceinline__ KmncFast kmnc_fast(float a, float lo, float inv, float bias, float lim, float zfr, int k) {
   constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
-  const float eh = __fmaf_rn(__fsub_rn(a, lo), inv, bias);
+  const float x = __fsub_rn(a, lo);
+  const float eh = __fmaf_rn(x, inv, bias);
   const float m = __fadd_rn(eh, kMagic);
-  const float fr = __fsub_rn(eh, __fsub_rn(m, kMagic));       // distance of e - 1/2 to the nearest integer
-  const int i = __float_as_int(m) - 0x4B400000;
+  float fr = __fsub_rn(eh, __fsub_rn(m, kMagic));             // distance of e - 1/2 to the nearest integer
+  // a == min exactly (every zero of a ReLU layer whose minimum is 0): e = 0 with no rounding anywhere and
+  // T_0 = min, so section 0 is certain as long as T_1 = fl(min + jump) > min (zfr = 0; else zfr = 1 -> exact path)
+  fr = x == 0.f ? zfr : fr;
+  const int i = __float_as_int(m) - 0x4B400000;               // (x == 0: e - 1/2 = -1/2 ties to even -> 0)
   KmncFast r;
   r.ok = fabsf(fr) <= lim;                                    // NaN / inf / huge values fail -> exact path
   r.i = (unsigned)i < (unsigned)k ? i : -1;
@@ -383,11 +387,12 @@ __device__ __forceinline__ KmncFast kmnc_fast(float a, float lo, float inv, floa
 // one sample row x four neurons of this thread: sections, optional store, number of covered neurons
 template <typename TB>
 __device__ __forceinline__ int kmnc_strip_row(const float4 v, const float4 lo, const float4 jp, const float4 inv,
-                                              const float4 bias, const float4 lim, int k, TB* __restrict__ bp) {
-  const KmncFast f0 = kmnc_fast(v.x, lo.x, inv.x, bias.x, lim.x, k);
-  const KmncFast f1 = kmnc_fast(v.y, lo.y, inv.y, bias.y, lim.y, k);
-  const KmncFast f2 = kmnc_fast(v.z, lo.z, inv.z, bias.z, lim.z, k);
-  const KmncFast f3 = kmnc_fast(v.w, lo.w, inv.w, bias.w, lim.w, k);
+                                              const float4 bias, const float4 lim, const float4 zfr, int k,
+                                              TB* __restrict__ bp) {
+  const KmncFast f0 = kmnc_fast(v.x, lo.x, inv.x, bias.x, lim.x, zfr.x, k);
+  const KmncFast f1 = kmnc_fast(v.y, lo.y, inv.y, bias.y, lim.y, zfr.y, k);
+  const KmncFast f2 = kmnc_fast(v.z, lo.z, inv.z, bias.z, lim.z, zfr.z, k);
+  const KmncFast f3 = kmnc_fast(v.w, lo.w, inv.w, bias.w, lim.w, zfr.w, k);
   int i0 = f0.i, i1 = f1.i, i2 = f2.i, i3 = f3.i;
   if (!(f0.ok && f1.ok && f2.ok && f3.ok)) {   // within delta of a section edge, NaN, inf
     if (!f0.ok) i0 = kmnc_bucket_slow(v.x, lo.x, jp.x, k);
@@ -437,6 +442,9 @@ __global__ void __launch_bounds__(256) kmnc_strip_kernel(const float* __restrict
     return dead_c ? __int_as_float(0x7f800000) : (delta == delta ? 0.5f - delta : -1.0f);
   };
   const float4 lim = make_float4(limit(lo.x, inv.x, dx), limit(lo.y, inv.y, dy), limit(lo.z, inv.z, dz), limit(lo.w, inv.w, dw));
+  // a == min: certain section 0 iff NumPy's second threshold fl(min + jump*1) lies above min (dead neurons: -3 anyway)
+  auto zero_fr = [](float lo_c, float jp_c, bool dead_c) { return (dead_c || __fadd_rn(lo_c, __fmul_rn(jp_c, 1.0f)) > lo_c) ? 0.f : 1.f; };
+  const float4 zfr = make_float4(zero_fr(lo.x, jp.x, dx), zero_fr(lo.y, jp.y, dy), zero_fr(lo.z, jp.z, dz), zero_fr(lo.w, jp.w, dw));
   const int64_t row0 = rg * rows_per_block;
   const int64_t row1 = min(n, row0 + (int64_t)rows_per_block);
   const float4* src = reinterpret_cast<const float4*>(act) + row0 * d4 + j;
@@ -449,7 +457,7 @@ __global__ void __launch_bounds__(256) kmnc_strip_kernel(const float* __restrict
     for (int u = 0; u < kStripRows; u++) v[u] = ld_stream_f4(src + u * d4);
 #pragma unroll
     for (int u = 0; u < kStripRows; u++) {
-      int cnt = kmnc_strip_row<TB>(v[u], lo, jp, inv, bias, lim, k, dst ? dst + u * d : nullptr);
+      int cnt = kmnc_strip_row<TB>(v[u], lo, jp, inv, bias, lim, zfr, k, dst ? dst + u * d : nullptr);
       cnt = __reduce_add_sync(live, cnt);
       if (leader && cnt) atomicAdd(sc + u, cnt);
     }
@@ -459,7 +467,7 @@ __global__ void __launch_bounds__(256) kmnc_strip_kernel(const float* __restrict
   }
   for (; r < row1; r++) {
     const float4 v = ld_stream_f4(src);
-    int cnt = kmnc_strip_row<TB>(v, lo, jp, inv, bias, lim, k, dst);
+    int cnt = kmnc_strip_row<TB>(v, lo, jp, inv, bias, lim, zfr, k, dst);
     cnt = __reduce_add_sync(live, cnt);
     if (leader && cnt) atomicAdd(sc, cnt);
     src += d4;

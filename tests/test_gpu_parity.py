@@ -835,8 +835,8 @@ def test_forward_hook_traces_to_scores_to_result_files(tmp_path):
     R.persist(out, "toy", "nominal", "is_misclassified", 0, mis)
     R.persist(out, "toy", "nominal", "uncertainty_deep_gini", 0, gini)
     R.persist_tip(out, "toy", "nominal", 0, "dsa", dsa)
-    R.persist_tip(out, "toy", "nominal", 0, "KMNC_2", k_score.cpu().numpy(),
-                  list(cam_from_buckets(k_score.cpu().numpy(), k_bucket, 2)))
+    # (scores in the reference's dtype: np.argsort's tie order, which decides the tail of cam, depends on it)
+    R.persist_tip(out, "toy", "nominal", 0, "KMNC_2", ws, list(cam_from_buckets(k_score.cpu().numpy().astype(ws.dtype), k_bucket, 2)))
     R.persist_tip(out, "toy", "nominal", 0, "NAC_0.75", os_, list(cam_from_bits(os_, n_bits)))
     apfd = R.load_apfd_values(out, "toy", "nominal")
     assert apfd["dsa"][0] == apfd_from_order(mis, np.argsort(-want["dsa"]))

@@ -7,7 +7,7 @@ echo "== pytest (all gpu tests) =="; timeout 900 python -m pytest tests -m gpu -
 echo "== bench default =="; timeout 600 python bench.py > $O/r2_bench_full.json 2> $O/r2_bench_full.err; echo rc=$?; tail -2 $O/r2_bench_full.err | cut -c1-300
 echo "== pc-lsa profile =="; timeout 300 python tools/pc_lsa_profile.py > $O/r2_pclsa.txt 2>&1; head -12 $O/r2_pclsa.txt | cut -c1-200
 echo "== A/B: seeds / group re-rank =="
-for cfg in "B200TIP_SEEDS=0 B200TIP_RERANK_GROUPS=0" "B200TIP_SEEDS=1 B200TIP_RERANK_GROUPS=0" "B200TIP_SEEDS=0 B200TIP_RERANK_GROUPS=1" "B200TIP_SEEDS=1 B200TIP_RERANK_GROUPS=1"; do
+for cfg in "B200TIP_SEEDS=0 B200TIP_RERANK_GROUPS=0" "B200TIP_SEEDS=1 B200TIP_RERANK_GROUPS=0"; do
   env $cfg timeout 200 python bench.py --no-c5 --no-others --no-cpu --steps 20 > $O/ab.json 2> $O/ab.err
   python - "$cfg" <<'PY'
 import json,sys
@@ -35,10 +35,11 @@ PY
 done
 echo "== ncu =="
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches_bench_c2.csv python bench.py --no-c5 --no-others --no-cpu --steps 2 --warmup 1 > $O/r2_bench_under_ncu.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:pair_rs_kernel --launch-skip 4 --launch-count 2 -o $O/r2_prof_rs -f python tools/ncu_target.py > $O/r2_ncu_rs.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:pair.*kernel -s 4 -c 2 -o $O/r2_prof_lse -f python tools/ncu_lse.py > $O/r2_ncu_lse.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:pair_rs_kernel --launch-skip 5 --launch-count 2 -o $O/r2_prof_rs -f python tools/ncu_target.py > $O/r2_ncu_rs.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:pair_kernel -s 4 -c 2 -o $O/r2_prof_lse -f python tools/ncu_lse.py > $O/r2_ncu_lse.log 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:kmnc_ --launch-skip 2 --launch-count 1 -o $O/r2_prof_kmnc -f python tools/ncu_kmnc.py > $O/r2_ncu_kmnc.log 2>&1
-timeout 400 ncu --set full --clock-control none -k regex:pair.*kernel -s 3 -c 1 -o $O/r2_prof_c5 -f python tools/ncu_c5.py > $O/r2_ncu_c5.log 2>&1
-timeout 300 ncu --set full --clock-control none -k regex:rerank_group -s 4 -c 2 -o $O/r2_prof_rerank -f python tools/ncu_target.py > $O/r2_ncu_rerank.log 2>&1
+timeout 400 ncu --set full --clock-control none -k regex:pair_kernel -s 3 -c 1 -o $O/r2_prof_c5 -f python tools/ncu_c5.py > $O/r2_ncu_c5.log 2>&1
+timeout 300 ncu --set full --clock-control none -k regex:rerank_list -s 5 -c 2 -o $O/r2_prof_rerank -f python tools/ncu_target.py > $O/r2_ncu_rerank.log 2>&1
+B200TIP_PAIR2=1 timeout 400 ncu --set full --clock-control none -k regex:pair2_kernel -s 3 -c 1 -o $O/r2_prof_c5_pair2 -f python tools/ncu_c5.py > $O/r2_ncu_c5_pair2.log 2>&1
 ls -la $O/*.ncu-rep | tail -8
 echo done
