@@ -34,6 +34,32 @@ for mode in ("auto", "slow"):
         torch.cuda.synchronize()
         print("  class", c, rows.shape, "ms:", 1e3 * (time.perf_counter() - t0) / 5, getattr(sa.kde, "last_operands", None),
               getattr(sa.kde, "last_fast_check", None))
+# bench-like variants: bf16-rounded traces, pinned source, L2 flush + CUDA-event timing as bench.py does
+rb = lambda a: torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+xtr2, xte2 = rb(xtr), rb(xte)
+pc2 = MultiModalSA.build_by_class(xtr2, ytr, lambda x, y: LSA(x))
+pinned = torch.from_numpy(xte2).pin_memory().numpy()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for name, src in (("pageable", xte2), ("pinned", pinned)):
+    for _ in range(3):
+        pc2(src, pte)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        pc2(src, pte)
+    torch.cuda.synchronize()
+    wall = 1e3 * (time.perf_counter() - t0) / 5
+    ev = []
+    for _ in range(5):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        pc2(src, pte)
+        b.record()
+        torch.cuda.synchronize()
+        ev.append(a.elapsed_time(b))
+    print("bench-like", name, "wall ms", wall, "event ms (after L2 flush)", sum(ev) / 5,
+          [getattr(sa.kde, "last_operands", None) for sa in list(pc2.modal_sa.values())[:3]])
 from torch.profiler import ProfilerActivity, profile
 
 for sa in pc.modal_sa.values():
