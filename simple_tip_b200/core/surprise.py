@@ -531,15 +531,7 @@ class DSA(SA):
         compute = np.dtype(np.float64) if wide else self._compute_dtype
         eng = self._engine
         if compute != self._compute_dtype:
-            if self._comm is not None and self._comm.world > 1:
-                raise TypeError("N_train-sharded DSA scores in the dtype of the training traces "
-                                f"({self._compute_dtype}); got float64 test traces")
-            if self._engine_wide is None:
-                train = self.train_activations
-                train = train.to(torch.float64) if isinstance(train, torch.Tensor) else np.asarray(train, dtype=np.float64)
-                self._engine_wide = E.NnEngine.from_host(train, self.train_predictions, int(self.num_classes),
-                                                         np.arange(train.shape[0]))
-            eng = self._engine_wide
+            return self._call_promoted(activations, dev_ats, target_pred)
         torch_dtype = torch.float64 if compute == np.float64 else torch.float32
         if dev_ats is not None:
             target_ats = dev_ats.to(torch_dtype)
@@ -611,6 +603,50 @@ class DSA(SA):
         full[2].fill_(-1.0)
         full.index_copy_(1, idx, packed)
         return self._finish(full.cpu().numpy())
+
+    def _call_promoted(self, activations, dev_ats, target_pred) -> np.ndarray:
+        """float64 test traces against float32 training traces, exactly as NumPy promotes them in the reference:
+        stage 1 (`from_ats[:, None] - to_ats`, surprise.py:638) runs in float64 on the exactly widened training traces
+        (a float64 twin of the engine, built on first use); stage 2's operands are both float32 TRAINING rows, so it
+        stays float32 (surprise.py:627-629); dsa = dist_a (f64) / dist_b (f32 -> f64).  Eager launches."""
+        import torch
+
+        from .. import _lib
+        from .. import engine as E
+
+        if self._comm is not None and self._comm.world > 1:
+            raise TypeError("N_train-sharded DSA scores in the dtype of the training traces "
+                            f"({self._compute_dtype}); got float64 test traces")
+        if self._engine_wide is None:
+            train = self.train_activations
+            train = train.to(torch.float64) if isinstance(train, torch.Tensor) else np.asarray(train, dtype=np.float64)
+            self._engine_wide = E.NnEngine.from_host(train, self.train_predictions, int(self.num_classes),
+                                                     np.arange(train.shape[0]), seeds=False)
+        eng, wide = self._engine, self._engine_wide
+        dev = eng.dev
+        x_all = dev_ats.to(torch.float64) if dev_ats is not None else \
+            E.to_device(_flatten_layers(activations).astype(np.float64), dev)
+        if x_all.ndim != 2 or int(x_all.shape[1]) != eng.d:
+            raise ValueError(f"operands could not be broadcast together: test traces have shape {tuple(x_all.shape)}, "
+                             f"training traces have {eng.d} features")
+        n_total = target_pred.shape[0]
+        order, q_off = E.class_layout(target_pred, int(self.num_classes))
+        for c in range(int(self.num_classes)):
+            if q_off[c + 1] > q_off[c] and len(self.class_matrix[c]) in (0, self.train_predictions.shape[0]):
+                raise ValueError("zero-size array to reduction operation minimum which has no identity")
+        self._last_dtype = np.dtype(np.float64)
+        full = np.full((3, n_total), np.nan)
+        full[2] = -1.0
+        if order.size:
+            idx = torch.from_numpy(order).to(dev)
+            x = x_all.index_select(0, idx)
+            q_class = torch.from_numpy(target_pred[order].astype(np.int32)).to(dev)
+            dist_a, pos, gid, _ = wide.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, self.use_filter)
+            winners = eng.gather(pos)                      # float32 training rows (same class-sorted positions)
+            dist_b = eng.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, self.use_filter)[0]
+            packed = torch.stack([dist_a, dist_b.to(torch.float64), gid.to(torch.float64)]).cpu().numpy()
+            full[:, order] = packed
+        return self._finish(full)
 
     def _finish(self, res: np.ndarray) -> np.ndarray:
         """res[3, n]: dist_a, dist_b, winner index as float64 (exact widenings) in the caller's order."""

@@ -893,10 +893,12 @@ def test_dsa_mixed_dtypes_follow_numpy_promotion():
     xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(3000, 260, 40, 4, seed=61)
     sa = DSA(xtr, ytr)
     x64 = xte.astype(np.float64) + 1e-9
-    want = np_oracle.dsa_oracle(xtr, ytr, x64, pte)
+    want = np_oracle.dsa_oracle(xtr, ytr, x64, pte)          # stage 1 in float64, stage 2 (train rows only) in float32
     got = sa(x64, pte)
-    assert want["dist_a"].dtype == np.float64 and np.array_equal(got, want["dsa"])
-    assert np.array_equal(sa.last_dist_a, want["dist_a"]) and np.array_equal(sa.last_winner_index, want["idx_a"])
+    assert np.array_equal(got, want["dsa"]) and np.array_equal(sa.last_winner_index, want["idx_a"])
+    assert np.array_equal(sa.last_dist_b.astype(np.float32), want["dist_b"])
+    f32 = np_oracle.dsa_oracle(xtr, ytr, xte, pte)
+    assert not np.array_equal(got, f32["dsa"])                # the promotion is visible in the bits
     assert np.array_equal(sa(xte, pte), np_oracle.dsa_oracle(xtr, ytr, xte, pte)["dsa"])       # float32 path unaffected
     h = xte.astype(np.float16)
     assert np.array_equal(sa(h, pte), np_oracle.dsa_oracle(xtr, ytr, h.astype(np.float32), pte)["dsa"])
