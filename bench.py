@@ -244,6 +244,8 @@ def run_c5_slice(args, tm: Timer, dev, rank, world, comm, steps: int, cfg=None):
     from simple_tip_b200 import engine as E
 
     cfg = dict(C5S if cfg is None else cfg)
+    if os.environ.get("B200TIP_C5S_TRAIN"):          # profiling aid: one rank's share of the slice on one GPU
+        cfg["n_train"] = int(os.environ["B200TIP_C5S_TRAIN"])
     n_train, n_test, d, classes, seed = cfg["n_train"], cfg["n_test"], cfg["d"], cfg["classes"], cfg["seed"]
     tflops_peak, _, peak_src = _peaks()
     torch.cuda.synchronize()
