@@ -18,6 +18,9 @@
 // is the query of DSA's second stage (surprise.py:627-629, 648).
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace tip {
@@ -87,6 +90,9 @@ struct RerankArgs {
   const int32_t* fin_idx;
   int64_t fin_n_total;
   double* fin_out;
+  // long traces: NumPy's pairwise-sum schedule for this trace width, flattened on the host (common.cuh)
+  const uint32_t* sum_prog;
+  int sum_leaves;
 };
 
 template <typename T>
@@ -131,7 +137,7 @@ __device__ __forceinline__ void write_result(const RerankArgs<T>& a, int64_t row
 // query elements of the stride-8 accumulator it owns in registers — loaded once, in the same
 // round trip as the candidate count — and a candidate row costs 16 loads + 47 flops per lane.
 template <typename T, bool SMALL>
-__global__ void __launch_bounds__(256, (SMALL && sizeof(T) == 4) ? 4 : 1) rerank_list_kernel(const RerankArgs<T> a) {
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? (SMALL ? 4 : 2) : 1) rerank_list_kernel(const RerankArgs<T> a) {
   using R = Rn<T>;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -218,7 +224,8 @@ __global__ void __launch_bounds__(256, (SMALL && sizeof(T) == 4) ? 4 : 1) rerank
           }
           s = r;
         } else {
-          s = np_sumsq_g8<T>(x, y, a.d, sub, gmask);
+          s = a.sum_prog ? np_sumsq_prog_g8<T>(x, y, a.sum_prog, a.sum_leaves, sub, gmask)
+                         : np_sumsq_g8<T>(x, y, a.d, sub, gmask);
         }
         const bool in_range = a.mode == TIP_RANGE_SAME_CLASS ? (j >= c0 && j < c1) : (j < cn && (j < c0 || j >= c1));
         if (in_range) consider(best, Rn<T>::sqrt(s), gid, j);   // all 8 lanes agree
@@ -406,7 +413,8 @@ __global__ void __launch_bounds__(kScanThreads) rerank_scan_kernel(const RerankA
     const int64_t lo = total * sl / S, hi = total * (sl + 1) / S;
     for (int64_t li = lo + grp; li < hi; li += kGroups) {
       const int j = li < len0 ? base0 + (int)li : c1 + (int)(li - len0);
-      const T s = np_sumsq_g8<T>(x, a.t + (int64_t)j * a.d, a.d, sub, gmask);
+      const T s = a.sum_prog ? np_sumsq_prog_g8<T>(x, a.t + (int64_t)j * a.d, a.sum_prog, a.sum_leaves, sub, gmask)
+                             : np_sumsq_g8<T>(x, a.t + (int64_t)j * a.d, a.d, sub, gmask);
       consider(best, Rn<T>::sqrt(s), a.t_gid ? a.t_gid[j] : j, j);
     }
     if (sub == 0) { s_dist[grp] = best.dist; s_gid[grp] = best.gid; s_pos[grp] = best.pos; }
@@ -464,6 +472,47 @@ static int next_pitch_k16(int64_t d) {     // K=16 steps of the one-segment pack
   return (int)((d16 + 16) / 16);
 }
 
+// NumPy's pairwise schedule for width d as one word per leaf (common.cuh: np_sumsq_prog_g8), cached per
+// (device, d) in device memory.  Built outside stream capture: the first search of an engine is eager.
+static void build_sum_prog(int off, int n, std::vector<uint32_t>& prog) {
+  if (n <= 128) {
+    prog.push_back((uint32_t)(off / 8) | ((uint32_t)(n - 1) << 20));
+    return;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  build_sum_prog(off, n2, prog);
+  build_sum_prog(off + n2, n - n2, prog);
+  prog.back() += 1u << 27;          // after the right subtree: merge it with the left one
+}
+
+static int get_sum_prog(int64_t d, const uint32_t** dev_prog, int* n_leaves) {
+  static std::mutex mu;
+  static std::map<std::pair<int, int64_t>, std::pair<uint32_t*, int>> cache;
+  *dev_prog = nullptr;
+  *n_leaves = 0;
+  if (d <= 128 || d > (8LL << 20)) return TIP_OK;      // short traces: register-resident leaf; absurd widths: generic routine
+  int dev = 0;
+  TIP_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find({dev, d});
+  if (it == cache.end()) {
+    std::vector<uint32_t> prog;
+    build_sum_prog(0, (int)d, prog);
+    for (uint32_t w : prog)
+      if ((w >> 27) >= 31) return TIP_OK;               // cannot happen below 2^31 elements; fall back if it does
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    uint32_t* p = nullptr;
+    TIP_CHECK_CUDA(cudaMalloc(&p, prog.size() * sizeof(uint32_t)));
+    TIP_CHECK_CUDA(cudaMemcpy(p, prog.data(), prog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    (void)cap;
+    it = cache.emplace(std::make_pair(dev, d), std::make_pair(p, (int)prog.size())).first;
+  }
+  *dev_prog = it->second.first;
+  *n_leaves = it->second.second;
+  return TIP_OK;
+}
+
 extern "C" int32_t tip_sizeof_rerank_extras(void) { return (int32_t)sizeof(tip_rerank_extras); }
 
 extern "C" int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype) {
@@ -494,6 +543,12 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
   if (m == 0) return TIP_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t next_pitch = tip_pair_pitch(d, 1);
+  const uint32_t* sum_prog = nullptr;
+  int sum_leaves = 0;
+  {
+    const int rc = get_sum_prog(d, &sum_prog, &sum_leaves);
+    if (rc != TIP_OK) return rc;
+  }
   // gamma of tip_nn_filter for this trace width (packed width + 16 fp32 accumulation steps)
   const SeedParams seed{next_seed_ub, next_t_rmax, next_t_errmax, (float)(next_pitch_k16(d) * 16 + 16) * 1.1920929e-7f};
   if (dtype == TIP_F32) {
@@ -501,7 +556,7 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
                         n_classes, mode, t_gid, (float*)out_dist, out_pos, out_gid, (float*)out_rows, work,
                         (unsigned long long*)stats, next_center, (__nv_bfloat16*)next_pack, next_pitch, next_sqnorm,
                         next_rounderr, next_row_min_bits, next_cand_cnt, seed, ex.q_idx, (const float*)ex.fin_dist_a,
-                        ex.fin_gid, ex.fin_idx, ex.fin_n_total, ex.fin_out};
+                        ex.fin_gid, ex.fin_idx, ex.fin_n_total, ex.fin_out, sum_prog, sum_leaves};
     return launch_rerank<float>(a, st);
   }
   if (dtype == TIP_F64) {
@@ -509,7 +564,7 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
                          class_off, n_classes, mode, t_gid, (double*)out_dist, out_pos, out_gid, (double*)out_rows,
                          work, (unsigned long long*)stats, next_center, (__nv_bfloat16*)next_pack, next_pitch,
                          next_sqnorm, next_rounderr, next_row_min_bits, next_cand_cnt, seed, ex.q_idx, (const double*)ex.fin_dist_a,
-                         ex.fin_gid, ex.fin_idx, ex.fin_n_total, ex.fin_out};
+                         ex.fin_gid, ex.fin_idx, ex.fin_n_total, ex.fin_out, sum_prog, sum_leaves};
     return launch_rerank<double>(a, st);
   }
   TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");
