@@ -343,11 +343,12 @@ __global__ void __launch_bounds__(256) kmnc_vec4_kernel(const float* __restrict_
 }
 
 // Column-strip variant of the above for the hot configuration (many samples): a block owns a strip
-// of 1024 neurons and a group of samples; every thread keeps the statistics of its four neurons in
-// registers and walks down the samples with kStripRows independent 16-byte loads in flight, so the
-// inner loop is load -> ~18 ALU instructions per value -> 8-byte store with no index arithmetic and
-// no statistics traffic.  Per-sample counts: warp shuffle -> shared memory -> one atomic per
-// (sample, strip).
+// of 1024 neurons and a contiguous share of the samples; every thread keeps the fast-path constants of its
+// four neurons in registers and walks down its samples with kStripRows independent 16-byte loads in flight,
+// so the inner loop is load -> ~12 ALU instructions per value -> 8-byte store with no index arithmetic and
+// no statistics traffic.  Per-sample counts: REDUX over the warp -> one `red` per (sample, warp).  The grid is
+// one resident wave (occupancy x SMs, rounded down to a multiple of the strip count) and the samples are split
+// evenly over the blocks of a strip, so there is no partial last wave.
 constexpr int kStripRows = 8;
 
 // Section index without threshold arithmetic on the common path.  e = (a - lo) / jump is estimated as
@@ -362,52 +363,75 @@ constexpr int kStripRows = 8;
 //   delta = 1.01 u (5.1 (k + 1) + |min| / jumps + 2)      — 3e-4 at k = 1000: 0.06 % of the values take the exact path
 // (kmnc_bucket_slow: the two NumPy-rounded thresholds around the estimate, then a walk).  Below the range the
 // sign of a - lo is exact (T_0 = min), above it e >= k + delta puts a beyond T_k: both yield -1 without a test.
-struct KmncFast {
-  int i;
-  bool ok;
-};
+//
+// a == min exactly (every zero of a ReLU layer whose minimum is 0) sits ON the edge T_0 and would fail the margin
+// test, but e = 0 there with no rounding anywhere: section 0 is certain as long as T_1 = fl(min + jump) > min, and
+// the rounded estimate is 0 as well (-1/2 + 1.5 * 2^23 ties to even).  Neurons for which that does not hold, or
+// whose delta exceeds 1/2 or is not a number, get lo = NaN on the fast path: then neither a - lo == 0 nor the margin test can
+// pass and every value of that neuron takes the exact path (which reads the true statistics from memory).
 // A neuron that can never be covered (jump <= 0 or NaN: constant / inverted range) costs nothing extra: its
-// inv is 0, its bias -3 and its lim +inf, so every finite activation lands on "section -3" = not covered.
-__device__ __forceinline__ KmncFast kmnc_fast(float a, float lo, float inv, float bias, float lim, float zfr, int k) {
+// inv is 0 and its lim +inf, so every finite activation passes the test, and its section count kk = 0 (k for the
+// others) turns the result into -1.
+struct KmncLane {
+  float lo, inv, lim;
+  int kk;
+};
+
+__device__ __forceinline__ KmncLane kmnc_lane(float lo, float jp, int k) {
+  KmncLane s;
+  const bool dead = !(jp > 0.f);
+  s.inv = dead ? 0.f : 1.0f / jp;
+  const float delta = 1.01f * 5.9604645e-8f * (5.1f * (float)(k + 1) + fabsf(lo) * fabsf(s.inv) * 1.0001f + 2.0f);
+  // (delta > 1/2 or NaN: jump underflows, 1/jump overflows, |min| / jump is huge — nothing can pass the margin test)
+  const bool exact_only = !dead && (!(delta <= 0.5f) || !(__fadd_rn(lo, __fmul_rn(jp, 1.0f)) > lo));
+  s.lim = dead ? __int_as_float(0x7f800000) : 0.5f - delta;   // negative: only a == min passes
+  s.lo = exact_only ? __int_as_float(0x7fc00000) : lo;
+  s.kk = dead ? 0 : k;
+  asm volatile("" : "+r"(s.kk));   // keep it a register: recomputing it from jump costs two instructions per value
+  return s;
+}
+
+__device__ __forceinline__ int kmnc_fast(float a, const KmncLane& s, bool& ok) {
   constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
-  const float x = __fsub_rn(a, lo);
-  const float eh = __fmaf_rn(x, inv, bias);
+  const float x = __fsub_rn(a, s.lo);
+  const float eh = __fmaf_rn(x, s.inv, -0.5f);
   const float m = __fadd_rn(eh, kMagic);
-  float fr = __fsub_rn(eh, __fsub_rn(m, kMagic));             // distance of e - 1/2 to the nearest integer
-  // a == min exactly (every zero of a ReLU layer whose minimum is 0): e = 0 with no rounding anywhere and
-  // T_0 = min, so section 0 is certain as long as T_1 = fl(min + jump) > min (zfr = 0; else zfr = 1 -> exact path)
-  fr = x == 0.f ? zfr : fr;
-  const int i = __float_as_int(m) - 0x4B400000;               // (x == 0: e - 1/2 = -1/2 ties to even -> 0)
-  KmncFast r;
-  r.ok = fabsf(fr) <= lim;                                    // NaN / inf / huge values fail -> exact path
-  r.i = (unsigned)i < (unsigned)k ? i : -1;
-  return r;
+  const float fr = __fsub_rn(eh, __fsub_rn(m, kMagic));       // distance of e - 1/2 to the nearest integer
+  ok = (fabsf(fr) <= s.lim) || (x == 0.f);                    // NaN / inf / huge values fail -> exact path
+  const int i = __float_as_int(m) - 0x4B400000;
+  return (unsigned)i < (unsigned)s.kk ? i : -1;
+}
+
+__device__ __forceinline__ void red_add_s32_if(int32_t* p, int v, bool on) {   // predicated, no branch
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p red.global.add.s32 [%0], %1; }" ::"l"(p), "r"(v), "r"((int)on)
+               : "memory");
 }
 
 // one sample row x four neurons of this thread: sections, optional store, number of covered neurons
-template <typename TB>
-__device__ __forceinline__ int kmnc_strip_row(const float4 v, const float4 lo, const float4 jp, const float4 inv,
-                                              const float4 bias, const float4 lim, const float4 zfr, int k,
+template <typename TB, bool STORE>
+__device__ __forceinline__ int kmnc_strip_row(const float4 v, const KmncLane& s0, const KmncLane& s1,
+                                              const KmncLane& s2, const KmncLane& s3, int k,
+                                              const float* __restrict__ lo_g, const float* __restrict__ jp_g,
                                               TB* __restrict__ bp) {
-  const KmncFast f0 = kmnc_fast(v.x, lo.x, inv.x, bias.x, lim.x, zfr.x, k);
-  const KmncFast f1 = kmnc_fast(v.y, lo.y, inv.y, bias.y, lim.y, zfr.y, k);
-  const KmncFast f2 = kmnc_fast(v.z, lo.z, inv.z, bias.z, lim.z, zfr.z, k);
-  const KmncFast f3 = kmnc_fast(v.w, lo.w, inv.w, bias.w, lim.w, zfr.w, k);
-  int i0 = f0.i, i1 = f1.i, i2 = f2.i, i3 = f3.i;
-  if (!(f0.ok && f1.ok && f2.ok && f3.ok)) {   // within delta of a section edge, NaN, inf
-    if (!f0.ok) i0 = kmnc_bucket_slow(v.x, lo.x, jp.x, k);
-    if (!f1.ok) i1 = kmnc_bucket_slow(v.y, lo.y, jp.y, k);
-    if (!f2.ok) i2 = kmnc_bucket_slow(v.z, lo.z, jp.z, k);
-    if (!f3.ok) i3 = kmnc_bucket_slow(v.w, lo.w, jp.w, k);
+  bool ok0, ok1, ok2, ok3;
+  int i0 = kmnc_fast(v.x, s0, ok0);
+  int i1 = kmnc_fast(v.y, s1, ok1);
+  int i2 = kmnc_fast(v.z, s2, ok2);
+  int i3 = kmnc_fast(v.w, s3, ok3);
+  if (!(ok0 && ok1 && ok2 && ok3)) {   // within delta of a section edge, NaN, inf: NumPy's thresholds decide
+    if (!ok0) i0 = kmnc_bucket_slow(v.x, __ldg(lo_g + 0), __ldg(jp_g + 0), k);
+    if (!ok1) i1 = kmnc_bucket_slow(v.y, __ldg(lo_g + 1), __ldg(jp_g + 1), k);
+    if (!ok2) i2 = kmnc_bucket_slow(v.z, __ldg(lo_g + 2), __ldg(jp_g + 2), k);
+    if (!ok3) i3 = kmnc_bucket_slow(v.w, __ldg(lo_g + 3), __ldg(jp_g + 3), k);
   }
-  if (bp) {
+  if (STORE) {
     if (sizeof(TB) == 2) {
       *reinterpret_cast<short4*>(bp) = make_short4((short)i0, (short)i1, (short)i2, (short)i3);
     } else {
       *reinterpret_cast<int4*>(bp) = make_int4(i0, i1, i2, i3);
     }
   }
-  return (i0 >= 0) + (i1 >= 0) + (i2 >= 0) + (i3 >= 0);
+  return 4 + (i0 >> 31) + (i1 >> 31) + (i2 >> 31) + (i3 >> 31);   // sections are -1 or >= 0
 }
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
@@ -418,60 +442,67 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   return v;
 }
 
-template <typename TB>
+template <typename TB, bool STORE, int ROWS>
+__device__ __forceinline__ void kmnc_strip_batch(const float4* __restrict__ src, int64_t d4, int64_t d,
+                                                 const KmncLane& s0, const KmncLane& s1, const KmncLane& s2,
+                                                 const KmncLane& s3, int k, const float* __restrict__ lo_g,
+                                                 const float* __restrict__ jp_g, TB* __restrict__ dst,
+                                                 int32_t* __restrict__ sc, unsigned live, bool leader) {
+  float4 v[ROWS];
+#pragma unroll
+  for (int u = 0; u < ROWS; u++) v[u] = ld_stream_f4(src + u * d4);
+#pragma unroll
+  for (int u = 0; u < ROWS; u++) {
+    int cnt = kmnc_strip_row<TB, STORE>(v[u], s0, s1, s2, s3, k, lo_g, jp_g, STORE ? dst + u * d : nullptr);
+    cnt = __reduce_add_sync(live, cnt);
+    red_add_s32_if(sc + u, cnt, leader);
+  }
+}
+
+// grid = nstrips * lanes; block b: strip b % nstrips, samples [n * l / lanes, n * (l + 1) / lanes) with l = b / nstrips
+template <typename TB, bool STORE>
 __global__ void __launch_bounds__(256) kmnc_strip_kernel(const float* __restrict__ act, int64_t n, int64_t d,
                                                          const float* __restrict__ mins,
                                                          const float* __restrict__ jumps, int k,
                                                          TB* __restrict__ bucket, int32_t* __restrict__ score,
-                                                         int nstrips, int rows_per_block) {
+                                                         int nstrips, int lanes) {
   const int lane = threadIdx.x & 31;
   const int strip = blockIdx.x % nstrips;
-  const int64_t rg = blockIdx.x / nstrips;
+  const int64_t l = blockIdx.x / nstrips;
   const int64_t d4 = d >> 2;
   const int64_t j = (int64_t)strip * 256 + threadIdx.x;   // float4 column
   const unsigned live = __ballot_sync(0xffffffffu, j < d4);   // lanes of this warp that own columns
   if (j >= d4) return;                                         // no block-wide barriers below
   const bool leader = lane == __ffs(live) - 1;
-  const float4 lo = __ldg(reinterpret_cast<const float4*>(mins) + j);
-  const float4 jp = __ldg(reinterpret_cast<const float4*>(jumps) + j);
-  const bool dx = !(jp.x > 0.f), dy = !(jp.y > 0.f), dz = !(jp.z > 0.f), dw = !(jp.w > 0.f);   // never covered
-  const float4 inv = make_float4(dx ? 0.f : 1.0f / jp.x, dy ? 0.f : 1.0f / jp.y, dz ? 0.f : 1.0f / jp.z, dw ? 0.f : 1.0f / jp.w);
-  const float4 bias = make_float4(dx ? -3.f : -0.5f, dy ? -3.f : -0.5f, dz ? -3.f : -0.5f, dw ? -3.f : -0.5f);
-  auto limit = [k](float lo_c, float inv_c, bool dead_c) {   // 1/2 - delta (see kmnc_fast); negative = always the exact path
-    const float delta = 1.01f * 5.9604645e-8f * (5.1f * (float)(k + 1) + fabsf(lo_c) * fabsf(inv_c) * 1.0001f + 2.0f);
-    return dead_c ? __int_as_float(0x7f800000) : (delta == delta ? 0.5f - delta : -1.0f);
-  };
-  const float4 lim = make_float4(limit(lo.x, inv.x, dx), limit(lo.y, inv.y, dy), limit(lo.z, inv.z, dz), limit(lo.w, inv.w, dw));
-  // a == min: certain section 0 iff NumPy's second threshold fl(min + jump*1) lies above min (dead neurons: -3 anyway)
-  auto zero_fr = [](float lo_c, float jp_c, bool dead_c) { return (dead_c || __fadd_rn(lo_c, __fmul_rn(jp_c, 1.0f)) > lo_c) ? 0.f : 1.f; };
-  const float4 zfr = make_float4(zero_fr(lo.x, jp.x, dx), zero_fr(lo.y, jp.y, dy), zero_fr(lo.z, jp.z, dz), zero_fr(lo.w, jp.w, dw));
-  const int64_t row0 = rg * rows_per_block;
-  const int64_t row1 = min(n, row0 + (int64_t)rows_per_block);
+  const float* lo_g = mins + (j << 2);
+  const float* jp_g = jumps + (j << 2);
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(lo_g));
+  const float4 jp = __ldg(reinterpret_cast<const float4*>(jp_g));
+  const KmncLane s0 = kmnc_lane(lo.x, jp.x, k), s1 = kmnc_lane(lo.y, jp.y, k);
+  const KmncLane s2 = kmnc_lane(lo.z, jp.z, k), s3 = kmnc_lane(lo.w, jp.w, k);
+  const int64_t row0 = n * l / lanes;
+  const int64_t row1 = n * (l + 1) / lanes;
   const float4* src = reinterpret_cast<const float4*>(act) + row0 * d4 + j;
-  TB* dst = bucket ? bucket + row0 * d + (j << 2) : nullptr;
+  TB* dst = STORE ? bucket + row0 * d + (j << 2) : nullptr;
   int32_t* sc = score + row0;
   int64_t r = row0;
   for (; r + kStripRows <= row1; r += kStripRows) {
-    float4 v[kStripRows];
-#pragma unroll
-    for (int u = 0; u < kStripRows; u++) v[u] = ld_stream_f4(src + u * d4);
-#pragma unroll
-    for (int u = 0; u < kStripRows; u++) {
-      int cnt = kmnc_strip_row<TB>(v[u], lo, jp, inv, bias, lim, zfr, k, dst ? dst + u * d : nullptr);
-      cnt = __reduce_add_sync(live, cnt);
-      if (leader && cnt) atomicAdd(sc + u, cnt);
-    }
+    kmnc_strip_batch<TB, STORE, kStripRows>(src, d4, d, s0, s1, s2, s3, k, lo_g, jp_g, dst, sc, live, leader);
     src += kStripRows * d4;
-    if (dst) dst += kStripRows * d;
+    if (STORE) dst += kStripRows * d;
     sc += kStripRows;
   }
+  if (r + 4 <= row1) {
+    kmnc_strip_batch<TB, STORE, 4>(src, d4, d, s0, s1, s2, s3, k, lo_g, jp_g, dst, sc, live, leader);
+    src += 4 * d4;
+    if (STORE) dst += 4 * d;
+    sc += 4;
+    r += 4;
+  }
   for (; r < row1; r++) {
-    const float4 v = ld_stream_f4(src);
-    int cnt = kmnc_strip_row<TB>(v, lo, jp, inv, bias, lim, zfr, k, dst);
-    cnt = __reduce_add_sync(live, cnt);
-    if (leader && cnt) atomicAdd(sc, cnt);
+    kmnc_strip_batch<TB, STORE, 1>(src, d4, d, s0, s1, s2, s3, k, lo_g, jp_g, dst, sc, live, leader);
     src += d4;
-    if (dst) dst += d;
+    if (STORE) dst += d;
     sc++;
   }
 }
@@ -779,19 +810,31 @@ extern "C" int tip_kmnc(const void* act, int act_dtype, int64_t n, int64_t d, co
       TIP_CHECK_CUDA(cudaMemsetAsync(score, 0, (size_t)n * sizeof(int32_t), st));
       const int64_t nstrips = ((d >> 2) + 255) / 256;
       if (n >= 4 * kStripRows && nstrips <= 65535 && sections <= (1 << 22)) {
-        // enough samples to amortise the per-block statistics load: column-strip kernel
-        int64_t rpb = (n * nstrips + (int64_t)sm_count() * 16 - 1) / ((int64_t)sm_count() * 16);
-        rpb = std::max<int64_t>(kStripRows, (rpb + kStripRows - 1) / kStripRows * kStripRows);
-        const int64_t blocks = nstrips * ((n + rpb - 1) / rpb);
-        TIP_REQUIRE(blocks < (1LL << 31), "too many blocks");
-        if (bucket == nullptr || bucket_dtype == TIP_I16)
-          kmnc_strip_kernel<int16_t><<<(unsigned)blocks, 256, 0, st>>>((const float*)act, n, d, (const float*)mins,
-                                                                      (const float*)jumps, sections, (int16_t*)bucket,
-                                                                      score, (int)nstrips, (int)rpb);
-        else
-          kmnc_strip_kernel<int32_t><<<(unsigned)blocks, 256, 0, st>>>((const float*)act, n, d, (const float*)mins,
-                                                                      (const float*)jumps, sections, (int32_t*)bucket,
-                                                                      score, (int)nstrips, (int)rpb);
+        // enough samples to amortise the per-block statistics load: column-strip kernel, one resident wave
+        const bool i16 = bucket == nullptr || bucket_dtype == TIP_I16;
+        const void* fn = bucket == nullptr ? (const void*)kmnc_strip_kernel<int16_t, false>
+                         : i16             ? (const void*)kmnc_strip_kernel<int16_t, true>
+                                           : (const void*)kmnc_strip_kernel<int32_t, true>;
+        const int which = bucket == nullptr ? 0 : (i16 ? 1 : 2);
+        static int per_sm_of[3] = {0, 0, 0};   // occupancy of each instance (same on every device of a box)
+        static int waves = 0;                   // B200TIP_KMNC_WAVES: grid in resident waves (bring-up knob, default 1)
+        if (per_sm_of[which] == 0) {
+          int v = 0;
+          TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, fn, 256, 0));
+          per_sm_of[which] = std::max(v, 1);
+        }
+        if (waves == 0) {
+          const char* e = getenv("B200TIP_KMNC_WAVES");
+          waves = (e && atoi(e) >= 1 && atoi(e) <= 64) ? atoi(e) : 1;
+        }
+        const int64_t resident = (int64_t)sm_count() * per_sm_of[which] * waves;
+        const int64_t lanes = std::max<int64_t>(1, std::min<int64_t>(resident / nstrips, n / (2 * kStripRows)));
+        const int ns = (int)nstrips, ln = (int)lanes;
+        const float* a = (const float*)act;
+        const float* lo = (const float*)mins;
+        const float* jp = (const float*)jumps;
+        void* args[] = {&a, &n, &d, &lo, &jp, &sections, &bucket, &score, (void*)&ns, (void*)&ln};
+        TIP_CHECK_CUDA(cudaLaunchKernel(fn, dim3((unsigned)(nstrips * lanes)), dim3(256), args, 0, st));
         TIP_LAUNCH_CHECK();
         return TIP_OK;
       }

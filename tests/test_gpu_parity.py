@@ -189,6 +189,53 @@ def test_kmnc_large_vs_c_oracle(n, d, k):
     assert np.all(ok | ((lo <= act) & (act < hi)))
 
 
+@pytest.mark.parametrize("k", [2, 37, 1000])
+def test_kmnc_adversarial_statistics_and_values(k):
+    """Every neuron kind the fast path folds into constants (regular, negative minimum, constant, inverted, NaN
+    statistics, minimum so large that min + jump rounds back to min, underflowing jump) against every value kind
+    (NumPy's own thresholds and their float neighbours, the minimum, the maximum, zeros of both signs, NaN, infinities,
+    FLT_MAX, denormals), enough rows for the column-strip kernel: dense NumPy restatement of the predicate, bit for bit."""
+    from src.core.neuron_coverage import KMNC
+
+    rng = np.random.default_rng(k)
+    n, d = 96, 512
+    kinds = rng.integers(0, 9, size=d)
+    mins = np.zeros(d, dtype=np.float32)
+    maxs = rng.uniform(0.5, 3.0, size=d).astype(np.float32)
+    mins[kinds == 1] = -2.0
+    mins[kinds == 2], maxs[kinds == 2] = 0.7, 0.7                       # constant neuron
+    mins[kinds == 3], maxs[kinds == 3] = 1.0, 0.0                       # inverted
+    mins[kinds == 4] = np.nan
+    mins[kinds == 5], maxs[kinds == 5] = 1e6, 1e6 + 1                   # fl(min + jump) == min for k >= 17
+    mins[kinds == 6], maxs[kinds == 6] = 4096.0, 4097.0
+    mins[kinds == 7], maxs[kinds == 7] = 0.0, 1e-38                     # jump is denormal, 1/jump overflows
+    mins[kinds == 8], maxs[kinds == 8] = -1e-3, 1e-38
+    with np.errstate(all="ignore"):
+        lo, jumps, thresh = np_oracle.kmnc_thresholds([mins], [maxs], k)
+        thresh = np.stack(thresh)
+        act = (mins + (maxs - mins) * rng.uniform(-0.1, 1.1, size=(n, d))).astype(np.float32)
+        pick = rng.integers(0, k + 1, size=(n, d))
+        edge = np.take_along_axis(thresh, pick, axis=0).astype(np.float32)
+        how = rng.integers(0, 12, size=(n, d))
+        act = np.where(how == 0, edge, act)
+        act = np.where(how == 1, np.nextafter(edge, np.float32(-np.inf)), act)
+        act = np.where(how == 2, np.nextafter(edge, np.float32(np.inf)), act)
+        act = np.where(how == 3, mins, act)
+        act = np.where(how == 4, maxs, act).astype(np.float32)
+        special = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 3.4028235e38, -3.4028235e38, 1e-45, -1e-45, 1e-39],
+                           dtype=np.float32)
+        act = np.where(how == 5, special[rng.integers(0, special.size, size=(n, d))], act).astype(np.float32)
+        want_b, hits = np_oracle.kmnc_buckets_oracle([mins], [maxs], k, act)
+    assert hits.max() <= 1
+    km = KMNC([mins], [maxs], k)
+    score, bucket = km.buckets([act])
+    assert np.array_equal(bucket, want_b)
+    assert np.array_equal(score, (want_b >= 0).sum(axis=1))
+    # and the same rows through the few-samples kernel
+    s2, b2 = km.buckets([act[:8]])
+    assert np.array_equal(b2, want_b[:8]) and np.array_equal(s2, score[:8])
+
+
 # ------------------------------------------------------------------------------------------
 # DSA
 # ------------------------------------------------------------------------------------------
