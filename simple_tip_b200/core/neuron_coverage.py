@@ -238,6 +238,7 @@ class KMNC(CoverageMethod):
         a_dev, bucket, score = self._dev_bufs
         up.wait_stream(main)
         down.wait_stream(main)
+        landed = []
         for r0 in range(0, n, rows):
             r1 = min(n, r0 + rows)
             with torch.cuda.stream(up):
@@ -252,9 +253,25 @@ class KMNC(CoverageMethod):
             with torch.cuda.stream(down):
                 hb[r0:r1].copy_(bucket[r0:r1], non_blocking=True)
                 hs[r0:r1].copy_(score[r0:r1], non_blocking=True)
-        down.synchronize()
+                here = torch.cuda.Event()
+                here.record()
+            landed.append((r0, r1, here))
+        # the caller's array is ordinary memory: every chunk is copied out of the recycled pinned buffer as soon as
+        # it has landed, by a few threads (NumPy releases the GIL), while the later chunks are still on the bus
+        out = np.empty((n, d), dtype=hb.numpy().dtype)
+        hb_np = hb.numpy()
+        pool = _copy_pool()
+        jobs = []
+        for r0, r1, here in landed:
+            here.synchronize()
+            step = max(1, -(-(r1 - r0) // _COPY_THREADS))
+            for c0 in range(r0, r1, step):
+                c1 = min(r1, c0 + step)
+                jobs.append(pool.submit(np.copyto, out[c0:c1], hb_np[c0:c1]))
+        for j in jobs:
+            j.result()
         main.wait_stream(up)
-        return hs.numpy().astype(_score_dtype(d * self.sections)), hb.numpy().copy()
+        return hs.numpy().astype(_score_dtype(d * self.sections)), out
 
     PIPELINE_BYTES = 32 << 20
     PIPELINE_CHUNKS = 8
@@ -283,6 +300,19 @@ class KMNC(CoverageMethod):
         profiles = np.zeros((n, d, self.sections), dtype=bool)
         np.put_along_axis(profiles, np.maximum(bucket, 0).astype(np.int64)[..., None], (bucket >= 0)[..., None], axis=2)
         return score, profiles
+
+
+_COPY_THREADS = 4
+_POOL = None
+
+
+def _copy_pool():
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _POOL = ThreadPoolExecutor(max_workers=_COPY_THREADS, thread_name_prefix="tip-copy")
+    return _POOL
 
 
 class NBC(_ThresholdCoverage):

@@ -489,6 +489,22 @@ class DSA(SA):
     def _class_matrix(self) -> List[np.ndarray]:
         return [np.argwhere(self.train_predictions == c).flatten() for c in range(self.num_classes)]
 
+    def fit_other_class_table(self) -> "DSA":
+        """Extension (not in the reference): tabulate, once per training set, every train row's distance to its
+        nearest row of another class.  dist_b of surprise.py:622-631 depends on the test input only through which
+        train row won stage 1, so later calls run stage 1 alone and look dist_b up — same bits, N_train x N_train
+        pairs moved from every call into the fit.  Single-GPU engines only; drop_other_class_table() reverts."""
+        if self._comm is not None and self._comm.world > 1:
+            raise NotImplementedError("fit_other_class_table: not available for an N_train-sharded DSA")
+        self._engine.build_other_class_table()
+        self._seen_shapes.clear()
+        return self
+
+    def drop_other_class_table(self) -> "DSA":
+        self._engine.table_b = None
+        self._seen_shapes.clear()
+        return self
+
     def _build_engine(self):
         from .. import engine as E
 

@@ -610,6 +610,24 @@ class NnEngine:
         self.seed_b = None
         if seeds and SEEDS and self.n >= 4096 and self.num_classes >= 2 and self.resident:
             self.seed_b = self._other_class_seeds()
+        # Optional fit-time table (build_other_class_table): dist_b of surprise.py:622-631 depends on the test input
+        # only through WHICH train row won stage 1, so it can be tabulated per train row once per training set.
+        self.table_b = None
+
+    def build_other_class_table(self, chunk_rows: int = 1 << 16) -> torch.Tensor:
+        """For every train row the exact NumPy-order distance to its nearest row of another class (NaN when there is
+        none): the second stage of DSA for any future winner, found with the same filter + re-rank as a scoring call.
+        N_train x N_train pairs once per training set; a call then only runs stage 1 and looks dist_b up."""
+        cls_of_row = np.repeat(np.arange(self.num_classes), np.diff(self.class_off)).astype(np.int32)
+        table = torch.empty(self.n, dtype=self.t.dtype, device=self.dev)
+        for s in range(0, self.n, chunk_rows):
+            e = min(self.n, s + chunk_rows)
+            q_off = (np.clip(self.class_off, s, e) - s).astype(np.int64)
+            q_class = torch.from_numpy(cls_of_row[s:e]).to(self.dev)
+            table[s:e] = self.search(self.t[s:e], q_class, q_off, _lib.RANGE_OTHER_CLASSES)[0]
+        torch.cuda.current_stream().synchronize()
+        self.table_b = table
+        return table
 
     def _other_class_seeds(self, sample_rows: int = 8192) -> Optional[torch.Tensor]:
         step = max(1, self.n // sample_rows)
@@ -840,6 +858,16 @@ def dsa_distances(engine: NnEngine, x: torch.Tensor, q_class: torch.Tensor, q_of
     (idx, n_total, out) — the last re-rank also writes dist_a, dist_b, winner, dist_a / dist_b into out[4, n_total]."""
     sharded = comm is not None and comm.world > 1
     m = x.shape[0] if q_idx is None else q_idx.shape[0]
+    if not sharded and engine.table_b is not None and engine.table_b.dtype == x.dtype:
+        # fit-time table: stage 1 only, dist_b looked up by the winner's position
+        dist_a, pos, gid, _ = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter, q_idx=q_idx)
+        found = pos >= 0
+        dist_b = torch.where(found, engine.table_b.index_select(0, pos.clamp_min(0).to(torch.int64)),
+                             torch.full_like(dist_a, float("nan")))
+        if scatter is not None:
+            _lib.check(engine.lib.tip_dsa_pack_out(_p(dist_a), _p(dist_b), tip_dtype(dist_a.dtype), _p(gid), _p(scatter[0]),
+                                                   m, int(scatter[1]), _p(scatter[2]), _stream()), "tip_dsa_pack_out")
+        return dist_a, dist_b, gid
     if not sharded:
         # single shard: stage 1's re-rank also emits its winners as the packed queries of stage 2
         fuse = use_filter and engine.has_items(q_off, _lib.RANGE_OTHER_CLASSES)
@@ -1061,7 +1089,8 @@ class DsaPlan:
 def dsa_plan(engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool,
              comm: Optional[TrainShardComm] = None, n_total: Optional[int] = None) -> DsaPlan:
     n_total = int(m if n_total is None else n_total)
-    key = (m, n_total, np.asarray(q_off, dtype=np.int64).tobytes(), dtype, use_filter, engine.cap, comm is not None)
+    key = (m, n_total, np.asarray(q_off, dtype=np.int64).tobytes(), dtype, use_filter, engine.cap, comm is not None,
+           engine.table_b is not None)
     plan = engine._plans.get(key)
     if plan is None:
         if len(engine._plans) >= 8:

@@ -259,6 +259,39 @@ def test_dsa_golden_bit_exact(golden):
         assert np.array_equal(sa(xte, pte), g[f"{name}.dsa"], equal_nan=True), name
 
 
+def test_dsa_fit_time_table_gives_the_same_bits(golden):
+    """Extension: DSA.fit_other_class_table() tabulates dist_b per train row at fit time; calls then run stage 1 only.
+    Same score, dist_a, dist_b and winner bits as the reference's golden vectors and as the two-stage call (eager
+    first call, captured second, replayed third), float32 and float64, including a class without other classes'
+    rows missing (every class present) and labels the reference never scores."""
+    from src.core.surprise import DSA
+
+    g = golden("dsa_reference.npz")
+    for name in case_names(g, "dsa"):
+        kw = ast.literal_eval(str(g[f"{name}.kw"]))
+        xtr, ytr, xte, pte = (g[f"{name}.{k}"] for k in ("xtr", "ytr", "xte", "pte"))
+        sa = DSA(xtr, ytr, **kw).fit_other_class_table()
+        for _ in range(3):
+            got = sa(xte, pte)
+            assert np.array_equal(got, g[f"{name}.dsa"], equal_nan=True), name
+            assert np.array_equal(sa.last_dist_a, g[f"{name}.dist_a"]), name
+            assert np.array_equal(sa.last_dist_b, g[f"{name}.dist_b"]), name
+    for dt in (np.float32, np.float64):
+        xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(9000, 2500, 96, 7, seed=31)
+        xtr, xte = xtr.astype(dt), xte.astype(dt)
+        pte = pte.copy()
+        pte[::97] = 11                                   # never scored (label outside the training classes)
+        sa = DSA(xtr, ytr)
+        want = [sa(xte, pte).copy(), sa.last_dist_a.copy(), sa.last_dist_b.copy(), sa.last_winner_index.copy()]
+        sa.fit_other_class_table()
+        for _ in range(3):
+            got = [sa(xte, pte), sa.last_dist_a, sa.last_dist_b, sa.last_winner_index]
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b, equal_nan=True)
+        sa.drop_other_class_table()
+        assert np.array_equal(sa(xte, pte), want[0], equal_nan=True)
+
+
 @pytest.mark.parametrize("n_train,n_test,d,classes,dt,seed", [
     (20000, 1500, 128, 10, np.float32, 2), (5000, 700, 64, 3, np.float32, 3), (3000, 257, 200, 7, np.float32, 4),
     (4000, 300, 128, 10, np.float64, 5), (1500, 100, 1600, 4, np.float32, 6), (900, 130, 9, 2, np.float32, 7)])
