@@ -746,9 +746,10 @@ def secondary(wl, args, tm: Timer, dev, steps: int, with_cpu: bool = True):
         score = torch.empty(10000, dtype=torch.int32, device=dev)
         n_units, metric, dtype = 10000, "kmnc_inputs_profiled_per_sec", "f32 compare, i16 bucket ids"
         workload = "C4: KMNC 10000 x 4096 ReLU traces, 1000 sections (seed 4); compact bucket ids + scores"
-        # device-resident steps alternate between two input / output sets: 164 MB in + 82 MB out per step exceed the
-        # 126 MB L2, so no step finds anything of its own in cache, and there is no flush write whose 126 MB of dirty
-        # lines would be written back to HBM underneath the measured kernel (the flushed figure is reported beside it)
+        # A second figure alternates between two input / output sets without the flush write (164 MB in + 82 MB out per
+        # step exceed the 126 MB L2 anyway): there the dirty lines written back underneath the kernel are the previous
+        # step's own bucket ids instead of the flush pattern.  Both are steady-state figures; ncu, which starts every
+        # launch from a CLEAN L2, sees 45 us (profiles/r02_kmnc_strip_kernel_ncu_full.json).
         sets = [(a_dev, bucket), (a_dev.clone(), torch.empty_like(bucket))]
         turn = [0]
 
@@ -876,11 +877,7 @@ def secondary(wl, args, tm: Timer, dev, steps: int, with_cpu: bool = True):
     launches = (_lib.launch_count() - l0) // max(1, steps)
     l2_note = "flushed between steps (256 MiB write)"
     if no_flush:
-        extra["ms_per_step_after_flush_write"] = t_dev / steps
-        t_dev = float(np.sum(tm.timed(step_device, steps, flush=False)))
-        l2_note = ("inputs larger than L2: two alternating input / output sets, 246 MB per step through a 126 MB L2, no "
-                   "flush write (ms_per_step_after_flush_write = same steps after a 256 MiB fill, whose dirty lines are "
-                   "written back during the step)")
+        extra["ms_per_step_alternating_sets_no_flush"] = float(np.sum(tm.timed(step_device, steps, flush=False))) / steps
     t_e2e_steps = tm.timed(step_e2e, steps)
     t_e2e = float(np.sum(t_e2e_steps))
     line = {"metric": metric, "value": n_units * steps / (t_dev * 1e-3), "unit": "inputs/s", "n_gpus": 1,
