@@ -39,6 +39,18 @@ void count_launch(int n = 1);
 
 int sm_count();
 
+// The kernels that run between two launches of the tcgen05 filter inside one scoring call ask for the same
+// shared-memory carve-out as the filter (max shared), so that the SMs are not re-partitioned at every kernel
+// boundary of the chain.  B200TIP_CARVEOUT=0 leaves the driver's default (A/B knob).
+bool carveout_enabled();
+template <typename K>
+inline void prefer_max_shared(K kernel, bool* done) {
+  if (*done) return;
+  *done = true;
+  if (carveout_enabled())
+    (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 // ---- IEEE arithmetic without FMA contraction (NumPy never fuses) --------------------------
 template <typename T> struct Rn;
 template <> struct Rn<float> {

@@ -931,6 +931,8 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     return idx;
   };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long t_entry = 0;
+  if (args.cta_clock && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_entry));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmAt); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBt);
@@ -951,7 +953,10 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   auto global_ns = [] { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
-  if (args.cta_clock && threadIdx.x == 0) args.cta_clock[blockIdx.x * 4] = global_ns();
+  if (args.cta_clock && threadIdx.x == 0) {
+    args.cta_clock[blockIdx.x * 4] = global_ns();
+    args.cta_clock[1024 + blockIdx.x] = t_entry;      // kernel entry, before barrier init / TMEM allocation
+  }
 
   if (warp == 0) {
     // ================= TMA producer =================

@@ -453,6 +453,9 @@ static int launch_rerank(const RerankArgs<T>& a, cudaStream_t st) {
     const char* e = getenv("B200TIP_RERANK_GROUPS");
     group_mode = (e && e[0] == '1') ? 1 : 0;
   }
+  static bool pref_list = false, pref_scan = false;
+  prefer_max_shared(rerank_list_kernel<T, true>, &pref_list);
+  prefer_max_shared(rerank_scan_kernel<T>, &pref_scan);
   if (a.d <= 128 && group_mode) rerank_group_kernel<T><<<(unsigned)((a.m + 31) / 32), 256, 0, st>>>(a);
   else if (a.d <= 128) rerank_list_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(a);
   else rerank_list_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(a);

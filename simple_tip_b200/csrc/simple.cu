@@ -25,6 +25,15 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+bool carveout_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("B200TIP_CARVEOUT");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 int sm_count() {
   static int cached = 0;
   if (!cached) {
@@ -879,6 +888,8 @@ static int pair_prep_impl(const void* src, int dtype, int64_t rows, int64_t d, c
   const int64_t blocks = (rows + 7) / 8;
   TIP_REQUIRE(blocks < (1LL << 31), "too many rows");
   cudaStream_t st = (cudaStream_t)stream;
+  static bool pref_f = false;
+  prefer_max_shared(pair_prep_kernel<float>, &pref_f);
   if (dtype == TIP_F32)
     pair_prep_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)src, rows, (int)d, center, role, segments,
                                                              scale, norm_coef, (__nv_bfloat16*)dst, pitch, sqnorm,

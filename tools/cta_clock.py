@@ -23,12 +23,20 @@ w = eng.gather(eng.search(x, qc, q_off, _lib.RANGE_SAME_CLASS)[1])
 for mode, q in ((_lib.RANGE_OTHER_CLASSES, w), (_lib.RANGE_SAME_CLASS, x)):
     for _ in range(2):
         eng.search(q, qc, q_off, mode)
-    buf = torch.zeros((256, 4), dtype=torch.int64, device=eng.dev)
+    buf = torch.zeros((320, 4), dtype=torch.int64, device=eng.dev)     # rows 0..255: per-CTA records, 256..: entry times
     lib.tip_debug_cta_clock(C.c_void_p(buf.data_ptr()))
+    E.PROFILE = []
     eng.search(q, qc, q_off, mode)
     torch.cuda.synchronize()
+    prof, E.PROFILE = E.PROFILE, None
     lib.tip_debug_cta_clock(None)
-    t = buf.cpu().numpy()
+    raw = buf.cpu().numpy()
+    entry = raw.reshape(-1)[1024:1024 + 148]
+    t = raw[:256]
+    pro = (t[:148, 0] - entry) / 1e3
+    print(f"mode {mode}: kernel entry -> post-allocation timestamp per CTA: min {pro.min():.2f} p50 {np.median(pro):.2f} max {pro.max():.2f} us; "
+          f"entry skew across CTAs {(entry.max() - entry.min()) / 1e3:.2f} us; first entry -> last CTA end {(t[:148, 1].max() - entry.min()) / 1e3:.1f} us; "
+          f"event-timed launches: {[(k, round(a.elapsed_time(b) * 1e3, 1)) for k, _, a, b in prof] if prof else None}")
     t = t[t[:, 1] > 0]
     items = t[:, 3] & 0xffffffff
     smid = t[:, 3] >> 32
