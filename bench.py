@@ -343,6 +343,9 @@ def run_c5_slice(args, tm: Timer, dev, rank, world, comm, steps: int, cfg=None):
         del train_np
     flops = 2.0 * d * n_test * n_train
     stats = eng.stats.cpu().numpy().tolist()
+    if plan.speculative:         # the replayed graph has no exhaustive-scan launches: its overflow counter must be 0
+        stats[0] = int(plan.overflow.item())
+        assert stats[0] == 0, "a candidate list overflowed: the timed graph did not produce the result"
     cand = {}
     for mode, (cnt, _) in eng.last_cand_cnt_by_mode.items():
         c = cnt.float()
@@ -480,6 +483,9 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     t_dev = tm.timed(step_device, args.steps)
+    if plan is not None and plan.speculative:
+        # the replayed graph carries no exhaustive-scan launches; it is only valid if no candidate list overflowed
+        assert int(plan.overflow.item()) == 0, "a candidate list overflowed: the timed graph did not produce the result"
     t_e2e = tm.timed(step_e2e, args.steps)
     t_page = tm.timed(step_e2e_pageable, args.steps)
     step_api_device()

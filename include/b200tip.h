@@ -264,6 +264,10 @@ typedef struct tip_rerank_extras {
   const int32_t* fin_idx;     /* writes them (fin_idx == NULL: r itself); fin_dist_a in `dtype`, fin_out 4*fin_n_total */
   int64_t fin_n_total;        /* doubles */
   double* fin_out;
+  int32_t count_overflow_only; /* != 0 (filtered searches only): queries whose candidate list is empty or overflowed are */
+  int32_t reserved;            /* only COUNTED in work[0] — no queue, no exhaustive-scan launch, their outputs are not    */
+                               /* written; the caller checks work[0] after the call, resets it and repeats without this   */
+                               /* flag if it is non-zero (speculative execution of the normal, fallback-free case)        */
 } tip_rerank_extras;
 int32_t tip_sizeof_rerank_extras(void);   /* bindings check their struct layout against this */
 int64_t tip_nn_rerank_work_bytes(int64_t m, int dtype);

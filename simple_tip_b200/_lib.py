@@ -25,7 +25,8 @@ class RerankExtras(C.Structure):
     """tip_rerank_extras of include/b200tip.h"""
     _fields_ = [("q_idx", C.c_void_p), ("next_seed_ub", C.c_void_p), ("next_t_rmax", C.c_float),
                 ("next_t_errmax", C.c_float), ("fin_dist_a", C.c_void_p), ("fin_gid", C.c_void_p),
-                ("fin_idx", C.c_void_p), ("fin_n_total", C.c_int64), ("fin_out", C.c_void_p)]
+                ("fin_idx", C.c_void_p), ("fin_n_total", C.c_int64), ("fin_out", C.c_void_p),
+                ("count_overflow_only", C.c_int32), ("reserved", C.c_int32)]
 
 
 class WorkItem(C.Structure):

@@ -603,11 +603,16 @@ class DSA(SA):
             plan.idx.copy_(plan.idx_host, non_blocking=True)
             plan.run()
             plan.out_host.copy_(plan.out, non_blocking=True)
+            plan.fetch_overflow()
             torch.cuda.current_stream().synchronize()
-            # the division already happened on the device in the trace dtype (surprise.py:595);
-            # last_dist_a / last_dist_b / last_winner_index read this buffer on demand
-            self._last_raw = plan.out_host.numpy()
-            return self._last_raw[3].copy()
+            if not plan.overflowed():
+                # the division already happened on the device in the trace dtype (surprise.py:595);
+                # last_dist_a / last_dist_b / last_winner_index read this buffer on demand
+                self._last_raw = plan.out_host.numpy()
+                return self._last_raw[3].copy()
+            # some candidate list was empty or overflowed (heavy ties): the replayed graph carries no exhaustive-scan
+            # launches, so this call is repeated on the eager path below, which does
+            plan.clear_overflow()
         idx = torch.from_numpy(order).to(dev, non_blocking=True)
         x = x_all.index_select(0, idx)
         q_class = torch.from_numpy(target_pred[order].astype(np.int32)).to(dev, non_blocking=True)

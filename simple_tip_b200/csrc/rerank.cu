@@ -93,6 +93,7 @@ struct RerankArgs {
   // long traces: NumPy's pairwise-sum schedule for this trace width, flattened on the host (common.cuh)
   const uint32_t* sum_prog;
   int sum_leaves;
+  int count_only;     // speculative call: overflowed / empty lists are only counted in work[0] (tip_rerank_extras)
 };
 
 template <typename T>
@@ -136,11 +137,16 @@ __device__ __forceinline__ void write_result(const RerankArgs<T>& a, int64_t row
 // SMALL = traces of at most 128 elements (one leaf of NumPy's pairwise sum): every lane keeps the
 // query elements of the stride-8 accumulator it owns in registers — loaded once, in the same
 // round trip as the candidate count — and a candidate row costs 16 loads + 47 flops per lane.
-template <typename T, bool SMALL>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? (SMALL ? 4 : 2) : 1) rerank_list_kernel(const RerankArgs<T> a) {
+// WPB = warps (queries) per block.  The warps of a block never talk to each other; a block's slot on the SM is
+// only handed to the next block when its SLOWEST query is done, and candidate lists differ in length, so small
+// blocks let the hardware scheduler balance the ~2 queries per resident warp slot (10 000 queries at C2).
+// FULL = the trace length is exactly 128 (one whole leaf, no tail): every bounds predicate of the SMALL path folds away.
+template <typename T, bool SMALL, int WPB, bool FULL = false>
+__global__ void __launch_bounds__(32 * WPB, (sizeof(T) == 4 ? (SMALL ? 32 : 16) : 8) / WPB)
+rerank_list_kernel(const RerankArgs<T> a) {
   using R = Rn<T>;
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t row = (int64_t)blockIdx.x * WPB + (threadIdx.x >> 5);
   if (row >= a.m) return;
   const int sub = lane & 7, grp = lane >> 3;
   // The work per query is a chain of dependent loads; issue everything that does not depend on
@@ -152,8 +158,8 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? (SMALL ? 4 : 2) : 1) rer
   int2 first = make_int2(0, 0);
   if (spec) first = *reinterpret_cast<const int2*>(a.cand_idx + (row * (int64_t)a.cap + grp) * 2);
   const T* x = query_row(a, row);
-  const int n = a.d;
-  const int lim = n - (n % 8);
+  const int n = FULL ? 128 : a.d;
+  const int lim = FULL ? 128 : n - (n % 8);
   T xr[SMALL ? 16 : 1], xt[SMALL ? 7 : 1];
   if (SMALL) {
 #pragma unroll
@@ -167,7 +173,10 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? (SMALL ? 4 : 2) : 1) rer
     return;
   }
   if (a.cand_cnt == nullptr || cnt < 1 || cnt > a.cap) {
-    if (lane == 0) a.work[1 + atomicAdd(a.work, 1)] = (int32_t)row;
+    if (lane == 0) {
+      if (a.count_only) atomicAdd(a.work, 1);
+      else a.work[1 + atomicAdd(a.work, 1)] = (int32_t)row;
+    }
     return;
   }
   const int c0 = a.class_off[cls], c1 = a.class_off[cls + 1], cn = a.class_off[a.n_classes];
@@ -277,7 +286,10 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 4 : 1) rerank_group_kern
     return;
   }
   if (a.cand_cnt == nullptr || cnt < 1 || cnt > a.cap) {
-    if (sub == 0) a.work[1 + atomicAdd(a.work, 1)] = (int32_t)row;
+    if (sub == 0) {
+      if (a.count_only) atomicAdd(a.work, 1);
+      else a.work[1 + atomicAdd(a.work, 1)] = (int32_t)row;
+    }
     return;
   }
   const int c0 = a.class_off[cls], c1 = a.class_off[cls + 1], cn = a.class_off[a.n_classes];
@@ -445,7 +457,6 @@ __global__ void __launch_bounds__(kScanThreads) rerank_scan_kernel(const RerankA
 template <typename T>
 static int launch_rerank(const RerankArgs<T>& a, cudaStream_t st) {
   // precondition (and postcondition): work[0] == 0 and work[1 + m] == 0
-  const int64_t blocks = (a.m + 7) / 8;
   // B200TIP_RERANK_GROUPS=1: one 8-lane group per query (measured SLOWER at C2: 0.216 vs 0.199 ms per step — four
   // divergent queries per warp serialise more than the extra resident queries buy); default: one warp per query
   static int group_mode = -1;
@@ -453,13 +464,32 @@ static int launch_rerank(const RerankArgs<T>& a, cudaStream_t st) {
     const char* e = getenv("B200TIP_RERANK_GROUPS");
     group_mode = (e && e[0] == '1') ? 1 : 0;
   }
-  static bool pref_list = false, pref_scan = false;
-  prefer_max_shared(rerank_list_kernel<T, true>, &pref_list);
+  static bool pref_scan = false;
   prefer_max_shared(rerank_scan_kernel<T>, &pref_scan);
+  static int wpb = 0;      // B200TIP_RERANK_WPB = 1 | 2 | 8 queries per block (bring-up A/B)
+  if (wpb == 0) {
+    const char* e = getenv("B200TIP_RERANK_WPB");
+    wpb = (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 8)) ? atoi(e) : -1;
+  }
+  // measured at C2 (one box, ms per step): 8 -> 0.1943, 2 -> 0.1926, 1 -> 0.1928; long traces (C5 slice): 40.4 / 40.6 / 40.9
+  const int w = wpb > 0 ? wpb : (a.d <= 128 ? 2 : 8);
+  const unsigned nb = (unsigned)((a.m + w - 1) / w);
   if (a.d <= 128 && group_mode) rerank_group_kernel<T><<<(unsigned)((a.m + 31) / 32), 256, 0, st>>>(a);
-  else if (a.d <= 128) rerank_list_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(a);
-  else rerank_list_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(a);
+  else if (a.d == 128) {
+    if (w == 1) rerank_list_kernel<T, true, 1, true><<<nb, 32, 0, st>>>(a);
+    else if (w == 2) rerank_list_kernel<T, true, 2, true><<<nb, 64, 0, st>>>(a);
+    else rerank_list_kernel<T, true, 8, true><<<nb, 256, 0, st>>>(a);
+  } else if (a.d <= 128) {
+    if (w == 1) rerank_list_kernel<T, true, 1><<<nb, 32, 0, st>>>(a);
+    else if (w == 2) rerank_list_kernel<T, true, 2><<<nb, 64, 0, st>>>(a);
+    else rerank_list_kernel<T, true, 8><<<nb, 256, 0, st>>>(a);
+  } else {
+    if (w == 1) rerank_list_kernel<T, false, 1><<<nb, 32, 0, st>>>(a);
+    else if (w == 2) rerank_list_kernel<T, false, 2><<<nb, 64, 0, st>>>(a);
+    else rerank_list_kernel<T, false, 8><<<nb, 256, 0, st>>>(a);
+  }
   TIP_LAUNCH_CHECK();
+  if (a.count_only) return TIP_OK;   // speculative call: no exhaustive-scan launch, the caller inspects work[0]
   // normally an empty queue: every block returns at once, so keep the grid small (the fallback itself is rare)
   rerank_scan_kernel<T><<<sm_count() * 2, kScanThreads, 0, st>>>(a);
   TIP_LAUNCH_CHECK();
@@ -543,7 +573,9 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
   TIP_REQUIRE(cand_cnt == nullptr || (cand_idx != nullptr && cap >= 1), "candidate buffers");
   TIP_REQUIRE(next_pack == nullptr || (next_sqnorm && next_row_min_bits && next_cand_cnt),
               "next-stage query state: pack, sqnorm, row_min_bits and cand_cnt go together");
+  TIP_REQUIRE(!ex.count_overflow_only || cand_cnt != nullptr, "count_overflow_only needs candidate lists");
   if (m == 0) return TIP_OK;
+  const int count_only = ex.count_overflow_only != 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t next_pitch = tip_pair_pitch(d, 1);
   const uint32_t* sum_prog = nullptr;
@@ -559,7 +591,7 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
                         n_classes, mode, t_gid, (float*)out_dist, out_pos, out_gid, (float*)out_rows, work,
                         (unsigned long long*)stats, next_center, (__nv_bfloat16*)next_pack, next_pitch, next_sqnorm,
                         next_rounderr, next_row_min_bits, next_cand_cnt, seed, ex.q_idx, (const float*)ex.fin_dist_a,
-                        ex.fin_gid, ex.fin_idx, ex.fin_n_total, ex.fin_out, sum_prog, sum_leaves};
+                        ex.fin_gid, ex.fin_idx, ex.fin_n_total, ex.fin_out, sum_prog, sum_leaves, count_only};
     return launch_rerank<float>(a, st);
   }
   if (dtype == TIP_F64) {
@@ -567,7 +599,7 @@ extern "C" int tip_nn_rerank(const void* q, const void* t, int dtype, int64_t m,
                          class_off, n_classes, mode, t_gid, (double*)out_dist, out_pos, out_gid, (double*)out_rows,
                          work, (unsigned long long*)stats, next_center, (__nv_bfloat16*)next_pack, next_pitch,
                          next_sqnorm, next_rounderr, next_row_min_bits, next_cand_cnt, seed, ex.q_idx, (const double*)ex.fin_dist_a,
-                         ex.fin_gid, ex.fin_idx, ex.fin_n_total, ex.fin_out, sum_prog, sum_leaves};
+                         ex.fin_gid, ex.fin_idx, ex.fin_n_total, ex.fin_out, sum_prog, sum_leaves, count_only};
     return launch_rerank<double>(a, st);
   }
   TIP_REQUIRE(false, "dtype must be TIP_F32 or TIP_F64");

@@ -28,6 +28,7 @@ import torch
 from . import _lib
 
 POOL_FRAC = float(os.environ.get("B200TIP_POOL_FRAC", "0.2"))   # share of the filter's work handed out dynamically
+SPECULATIVE = os.environ.get("B200TIP_SPECULATIVE", "1") != "0"   # graph plans without exhaustive-scan launches
 POOL_MIN_TILES = 32       # tiles per CTA below which work lists stay purely static
 POOL_TILES = int(os.environ.get("B200TIP_POOL_TILES", "4"))      # train tiles per dynamic item
 DEFAULT_CAP = 64          # candidate chunks per query (short traces)
@@ -715,7 +716,8 @@ class NnEngine:
                    for c in range(self.num_classes))
 
     def search(self, q: torch.Tensor, q_class: torch.Tensor, q_off: np.ndarray, mode: int, use_filter: bool = True,
-               want_rows: bool = False, prepacked=None, next_query=None, q_idx: Optional[torch.Tensor] = None, fin=None):
+               want_rows: bool = False, prepacked=None, next_query=None, q_idx: Optional[torch.Tensor] = None, fin=None,
+               speculative: bool = False):
         """q: [m, d] queries grouped by class (q_off), q_class[m] int32.  Returns, per query, the
         exact NumPy-order distance to its nearest train row in the range selected by `mode`
         (NaN when the range is empty on this shard), that row's position (-1 when empty), its
@@ -723,7 +725,9 @@ class NnEngine:
         prepacked: query_state() already filled for q (by a previous search's next_query);
         next_query: query_state() to fill with the winning rows as the next search's queries.
         q_idx: int32 [m] — the queries are rows q_idx[r] of q (class-sorted order over the caller's buffer; no gathered
-        copy); fin: (dist_a, gid, idx, n_total, out) — fused result scatter of DSA's last stage (tip_rerank_extras)."""
+        copy); fin: (dist_a, gid, idx, n_total, out) — fused result scatter of DSA's last stage (tip_rerank_extras).
+        speculative: queries whose candidate list is empty or overflowed are only counted in work_buffer(m)[0] (no
+        exhaustive-scan launch); the caller checks overflow_count() and repeats the call without it if non-zero."""
         m = q.shape[0] if q_idx is None else q_idx.shape[0]
         out_dist = torch.empty(m, dtype=q.dtype, device=self.dev)
         out_pos = torch.empty(m, dtype=torch.int32, device=self.dev)
@@ -806,6 +810,7 @@ class NnEngine:
         ex.q_idx = 0 if q_idx is None else q_idx.data_ptr()
         ex.next_seed_ub = 0 if seed is None else seed.data_ptr()
         ex.next_t_rmax, ex.next_t_errmax = self.rmax, self.errmax
+        ex.count_overflow_only = 1 if (speculative and cand_cnt is not None) else 0
         if fin is not None:
             f_a, f_gid, f_idx, f_n, f_out = fin
             ex.fin_dist_a, ex.fin_gid = f_a.data_ptr(), f_gid.data_ptr()
@@ -851,7 +856,7 @@ def winner_queries(engine: "NnEngine", p2p: Optional[P2PExchange], gdist: Option
 
 def dsa_distances(engine: NnEngine, x: torch.Tensor, q_class: torch.Tensor, q_off: np.ndarray,
                   comm: Optional[TrainShardComm] = None, use_filter: bool = True, q_idx: Optional[torch.Tensor] = None,
-                  scatter=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                  scatter=None, speculative: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """surprise.py:615-631 for class-sorted queries x: (dist_a, dist_b, winner original index).
     Eager launches (the CUDA-graph plans below replay the same sequence).  Single shard only: q_idx — the
     class-sorted queries are rows q_idx[r] of x (the gather is fused into the pack and the re-rank); scatter =
@@ -860,7 +865,8 @@ def dsa_distances(engine: NnEngine, x: torch.Tensor, q_class: torch.Tensor, q_of
     m = x.shape[0] if q_idx is None else q_idx.shape[0]
     if not sharded and engine.table_b is not None and engine.table_b.dtype == x.dtype:
         # fit-time table: stage 1 only, dist_b looked up by the winner's position
-        dist_a, pos, gid, _ = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter, q_idx=q_idx)
+        dist_a, pos, gid, _ = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter, q_idx=q_idx,
+                                            speculative=speculative)
         found = pos >= 0
         dist_b = torch.where(found, engine.table_b.index_select(0, pos.clamp_min(0).to(torch.int64)),
                              torch.full_like(dist_a, float("nan")))
@@ -873,9 +879,10 @@ def dsa_distances(engine: NnEngine, x: torch.Tensor, q_class: torch.Tensor, q_of
         fuse = use_filter and engine.has_items(q_off, _lib.RANGE_OTHER_CLASSES)
         state2 = engine.query_state(m) if fuse else None
         dist_a, _, gid, winners = engine.search(x, q_class, q_off, _lib.RANGE_SAME_CLASS, use_filter, want_rows=True,
-                                                next_query=state2, q_idx=q_idx)
+                                                next_query=state2, q_idx=q_idx, speculative=speculative)
         fin = None if scatter is None else (dist_a, gid, scatter[0], scatter[1], scatter[2])
-        dist_b = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter, prepacked=state2, fin=fin)[0]
+        dist_b = engine.search(winners, q_class, q_off, _lib.RANGE_OTHER_CLASSES, use_filter, prepacked=state2, fin=fin,
+                               speculative=speculative)[0]
         return dist_a, dist_b, gid
     assert q_idx is None and scatter is None
     replica = engine.t_full is not None
@@ -970,6 +977,12 @@ class DsaPlan:
         if sharded and engine.t_full is None:
             raise RuntimeError("the sharded plan needs the replicated training set (NnEngine.t_full)")
         self.p2p = self.comm.p2p(dev, self.m) if sharded else None
+        # Single shard with the filter on: the replayed graph has NO exhaustive-scan launches (two normally empty
+        # launches per call); queries whose candidate list is empty or overflowed are only counted, and the caller
+        # repeats such a call on the eager path (overflowed() / clear_overflow()).
+        self.speculative = bool(use_filter and not sharded and SPECULATIVE)
+        self.overflow = engine.work_buffer(self.m, dtype)[:4].view(torch.int32)
+        self.overflow_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._keep_alive = []
         S = self.state = {}
 
@@ -992,7 +1005,8 @@ class DsaPlan:
                     self.out.fill_(float("nan"))
                     self.out[2].fill_(-1.0)
                 self.dist_a, self.dist_b, self.gid = dsa_distances(engine, self.x_in, self.q_class, self.q_off, None, use_filter,
-                                                                   q_idx=self.idx, scatter=(self.idx, self.n_total, self.out))
+                                                                   q_idx=self.idx, scatter=(self.idx, self.n_total, self.out),
+                                                                   speculative=self.speculative)
 
             segments = [(whole, True)]
         elif self.p2p is not None:
@@ -1073,6 +1087,8 @@ class DsaPlan:
         self.graph = None
         if len(segments) == 1:
             self.graph = g
+        if self.speculative:
+            self.overflow.zero_()     # whatever the warm-up ran on (a stale landing buffer) does not count
 
     def load_sorted(self, x_sorted: torch.Tensor):
         """Device-resident input already in class-sorted order (benchmarks, tools)."""
@@ -1084,6 +1100,18 @@ class DsaPlan:
         for step in self.steps:
             step()
         return self.out
+
+    def fetch_overflow(self):
+        """enqueue the D2H copy of the overflow counter (speculative plans); read it with overflowed() after a sync"""
+        if self.speculative:
+            self.overflow_host.copy_(self.overflow, non_blocking=True)
+
+    def overflowed(self) -> bool:
+        return self.speculative and int(self.overflow_host[0]) != 0
+
+    def clear_overflow(self):
+        self.overflow.zero_()
+        self.overflow_host.zero_()
 
 
 def dsa_plan(engine: "NnEngine", m: int, q_off: np.ndarray, dtype: torch.dtype, use_filter: bool,

@@ -333,6 +333,16 @@ def test_dsa_heavy_ties_and_overflow_fallback():
     sa._engine.cap = 4                                  # force overflow -> exhaustive rows
     assert np.array_equal(sa(xte, pte), want["dsa"], equal_nan=True)
     assert sa._engine.stats.cpu().numpy()[0] > 0
+    # second sighting captures the plan, later calls replay it: the replayed graph carries no exhaustive-scan launches,
+    # counts the overflowed lists instead, and the call is repeated on the eager path — same bits every time
+    for _ in range(3):
+        assert np.array_equal(sa(xte, pte), want["dsa"], equal_nan=True)
+        assert np.array_equal(sa.last_winner_index, want["idx_a"])
+    plan = next(iter(sa._engine._plans.values()))
+    assert plan.speculative and int(plan.overflow.item()) == 0     # detected, cleared, repeated
+    sa._engine.cap = 64
+    for _ in range(3):                                             # and back to lists that fit: the graph's own result
+        assert np.array_equal(sa(xte, pte), want["dsa"], equal_nan=True)
 
 
 def test_dsa_edge_cases():

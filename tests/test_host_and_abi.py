@@ -26,7 +26,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert lib.tip_pair_pitch(128, 1) == 192 and lib.tip_pair_pitch(256, 3) == 832
     assert lib.tip_pair_pitch(5, 1) == 64 and lib.tip_pair_pitch(0, 1) == -1
     assert C.sizeof(_lib.WorkItem) == 24
-    assert C.sizeof(_lib.RerankExtras) == 64 == lib.tip_sizeof_rerank_extras()
+    assert C.sizeof(_lib.RerankExtras) == 72 == lib.tip_sizeof_rerank_extras()
 
 
 def test_ctypes_signatures_have_the_header_arity():
