@@ -495,6 +495,8 @@ def run_ours(args):
     launches0 = _lib.launch_count()
     _, prof = timed_profile(step_eager, args.steps)
     launches = (_lib.launch_count() - launches0) // max(1, args.steps)
+    if plan is not None and plan.speculative:
+        launches -= 2     # the replayed graph (what `value` times) carries no exhaustive-scan launches; the eager pass does
     tm.barrier()
     clocks = sampler.stop() if rank == 0 else None
     tot_dev_ms, tot_e2e_ms, tot_page_ms = tm.max_over_ranks([sum(t_dev), sum(t_e2e), sum(t_page)], dev)
