@@ -71,6 +71,9 @@ struct PairArgs {
   int timeline_tiles;
   // bring-up: per-CTA {globaltimer at start, at end, tiles, items} of the resident kernel, or nullptr
   long long* cta_clock;
+  // resident kernel: the query tile's full 64-element K chunks are copied into the free TMEM columns [192, 256) of each
+  // accumulator half once per query tile and the MMAs read A from there (the K tail stays in shared memory)
+  int a_tmem;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------
@@ -135,6 +138,28 @@ __device__ __forceinline__ void umma_bf16_first(uint32_t d_tmem, uint64_t adesc,
       "setp.eq.u32 p, 1, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+// A operand from tensor memory (lane = row, one 32-bit column = two consecutive K elements): shared memory is then
+// read for B only.  tcgen05.cp copies 128 rows x 256 bits (one K = 16 step of a K-major operand, described like an
+// MMA operand) into 8 columns; cp and mma of one thread execute in issue order, so no barrier is needed between them.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_acc(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_first(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc)
       : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
@@ -1044,6 +1069,22 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         prev_q0 = it.q_row0; prev_qn = it.q_rows;
         mbar_wait(bar(0), a_phase);
         a_phase ^= 1u;
+        if (args.a_tmem && NFULL > 0) {
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+#pragma unroll
+              for (int c = 0; c < NFULL; c++) {
+                const uint64_t adesc = smem_desc(a_base + (uint32_t)c * RS_BM * 128 + (uint32_t)h * 128 * 128);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  tmem_cp_128x256b(tmem_base + (uint32_t)(h * 256 + RS_BN + (c * 4 + k) * 8), adesc + 2u * k);
+              }
+            }
+          }
+          __syncwarp();
+        }
       }
       for (int t = 0; t < ntiles; t++) {
         if (leader) TL(0);
@@ -1057,14 +1098,27 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (leader) {
             TL(2 + 9 * h);   // slots 2 and 11
             const uint32_t d_tmem = tmem_base + (uint32_t)(h * 256);
+            if (args.a_tmem) {
+              const uint32_t a_t = d_tmem + (uint32_t)RS_BN;
 #pragma unroll
-            for (int c = 0; c < NFULL; c++) {
-              const uint64_t adesc = smem_desc(a_base + (uint32_t)c * RS_BM * 128 + (uint32_t)h * 128 * 128);
-              const uint64_t bdesc = smem_desc(b_src + (uint32_t)c * RS_BN * 128);
+              for (int c = 0; c < NFULL; c++) {
+                const uint64_t bdesc = smem_desc(b_src + (uint32_t)c * RS_BN * 128);
 #pragma unroll
-              for (int k = 0; k < 4; k++) {
-                if (c == 0 && k == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdescRs);
-                else umma_bf16_acc(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdescRs);
+                for (int k = 0; k < 4; k++) {
+                  if (c == 0 && k == 0) umma_bf16_ts_first(d_tmem, a_t, bdesc, kIdescRs);
+                  else umma_bf16_ts_acc(d_tmem, a_t + (uint32_t)((c * 4 + k) * 8), bdesc + 2u * k, kIdescRs);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < NFULL; c++) {
+                const uint64_t adesc = smem_desc(a_base + (uint32_t)c * RS_BM * 128 + (uint32_t)h * 128 * 128);
+                const uint64_t bdesc = smem_desc(b_src + (uint32_t)c * RS_BN * 128);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  if (c == 0 && k == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdescRs);
+                  else umma_bf16_acc(d_tmem, adesc + 2u * k, bdesc + 2u * k, kIdescRs);
+                }
               }
             }
 #pragma unroll
@@ -1296,6 +1350,8 @@ static int launch_pair2(const void* q_pack, int64_t m, const void* t_pack, int64
   return TIP_OK;
 }
 
+constexpr int kATmemDefault = 1;   // measured at C2: stage 2 0.124-0.132 -> 0.120 ms, step 0.186 -> 0.183 ms (A/B on one box)
+
 template <int MODE, bool EXCL = false>
 static int launch_pair_rs(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t pitch, PairArgs args,
                           cudaStream_t st) {
@@ -1326,6 +1382,12 @@ static int launch_pair_rs(const void* q_pack, int64_t m, const void* t_pack, int
   }
   const int grid = std::min(args.n_items, sm_count());
   const int smem_k = rs_smem_bytes(args.k16);
+  static int a_tmem = -1;      // B200TIP_A_TMEM=0|1: A operand of the resident kernel from tensor memory
+  if (a_tmem < 0) {
+    const char* e = getenv("B200TIP_A_TMEM");
+    a_tmem = e ? (e[0] == '1' ? 1 : 0) : kATmemDefault;
+  }
+  args.a_tmem = a_tmem;
 #define TIP_RS_CASE(K)                                                                                   \
   case K:                                                                                                \
     pair_rs_kernel<MODE, K, EXCL><<<grid, kRsThreads, smem_k, st>>>(ma, mat, mb, mbt, args);               \
