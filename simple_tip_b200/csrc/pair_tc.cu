@@ -887,9 +887,15 @@ constexpr int RS_BM = 256;
 constexpr int RS_BN = 192;
 constexpr int kRsMaxK16 = 9;
 constexpr int kRsEpiThreads = 512;            // 16 epilogue warps
-constexpr int kRsThreads = 64 + kRsEpiThreads;
+constexpr int kRsThreads = 64 + kRsEpiThreads + 32;   // TMA warp, MMA warp (query half 0), 16 epilogue warps, MMA warp (half 1)
+constexpr int kRsMmaWarp1 = 2 + kRsEpiThreads / 32;     // the second issuing warp sits behind the epilogue warps
 constexpr int kRsStages = 2;
-constexpr uint32_t kIdescRs = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(RS_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// MMA shape M128 x N96 x K16: every (query half, column half) QUARTER of the tile is its own accumulator with its own
+// full / empty barriers, so a quarter is handed back to the tensor pipe as soon as ITS four epilogue warps have
+// drained it (accumulator round trip 432 + ~830 cycles of latency against a 1728-cycle tile, instead of 864 + ~830
+// with halves — the round trip, not the pipe, was the tile period).
+constexpr int RS_QN = RS_BN / 2;
+constexpr uint32_t kIdescRs = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(RS_QN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 struct RsGeom {
   int nfull, rem;
@@ -901,15 +907,19 @@ __host__ __device__ constexpr RsGeom rs_geom(int k16) {
                 (uint32_t)((k16 / 4) * RS_BN * 128 + (k16 % 4) * RS_BN * 32)};
 }
 constexpr int kRsBarBytes = 256;
+// second buffer for the K tail of the query tile (the tail is read from shared memory for the whole item, so the next
+// query tile's tail needs its own place when the tile is prefetched early; the full chunks live in tensor memory)
+__host__ __device__ constexpr int rs_tail_bytes(int k16) { return (k16 % 4) * RS_BM * 32; }
 constexpr int kSmemMax = 232448;   // 227 KB per CTA on sm_100
 // candidate staging slots per query that still fit next to the operand buffers (3 at K16 = 9)
 __host__ __device__ constexpr int rs_slots(int k16) {
-  const int left = kSmemMax - 1024 - kRsBarBytes - (int)(rs_geom(k16).a_bytes + kRsStages * rs_geom(k16).b_bytes);
+  const int left = kSmemMax - 1024 - kRsBarBytes - (int)(rs_geom(k16).a_bytes + kRsStages * rs_geom(k16).b_bytes) - rs_tail_bytes(k16);
   const int s = left / (kRsEpiThreads * 12);
   return s > kCandSlots ? kCandSlots : s;
 }
 __host__ __device__ constexpr int rs_smem_bytes(int k16) {
-  return (int)(rs_geom(k16).a_bytes + kRsStages * rs_geom(k16).b_bytes) + 1024 + kRsBarBytes + rs_slots(k16) * kRsEpiThreads * 12;
+  return (int)(rs_geom(k16).a_bytes + kRsStages * rs_geom(k16).b_bytes) + rs_tail_bytes(k16) + 1024 + kRsBarBytes +
+         rs_slots(k16) * kRsEpiThreads * 12;
 }
 static_assert(rs_slots(kRsMaxK16) >= 2 && rs_smem_bytes(kRsMaxK16) <= kSmemMax, "resident kernel does not fit");
 
@@ -938,9 +948,11 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t a_base = base;
   const uint32_t a_rem = a_base + (uint32_t)NFULL * RS_BM * 128;
   const uint32_t b_base = a_base + geo.a_bytes;
-  constexpr uint32_t tiles_bytes = geo.a_bytes + (uint32_t)kRsStages * geo.b_bytes;
+  const uint32_t a_rem2 = b_base + (uint32_t)kRsStages * geo.b_bytes;     // see rs_tail_bytes
+  constexpr uint32_t tiles_bytes = geo.a_bytes + (uint32_t)kRsStages * geo.b_bytes + (uint32_t)rs_tail_bytes(K16);
+  const bool ta = args.a_tmem && NFULL > 0;
   const uint32_t bar0 = base + tiles_bytes;
-  // barriers: 0 a_full, 1 a_empty, 2..3 b_full, 4..5 b_empty, 6..7 tfull[half], 8..9 tempty[half],
+  // barriers: 0 a_full, 1 a_empty, 2..3 b_full, 4..5 b_empty, 20..23 tfull[quarter], 24..27 tempty[quarter],
   // 10..11 sched_full[slot], 12..13 sched_empty[slot]; then the TMEM base and the 2-slot item ring
   auto bar = [&](int i) { return bar0 + 8u * i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + tiles_bytes + 8 * 16);
@@ -961,10 +973,10 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmAt); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBt);
-    mbar_init(bar(0), 1); mbar_init(bar(1), 1);
-    for (int s = 0; s < kRsStages; s++) { mbar_init(bar(2 + s), 1); mbar_init(bar(4 + s), 1); }
-    for (int h = 0; h < 2; h++) { mbar_init(bar(6 + h), 1); mbar_init(bar(8 + h), kRsEpiThreads / 64); }
-    for (int s = 0; s < 2; s++) { mbar_init(bar(10 + s), 1); mbar_init(bar(12 + s), 1 + kRsEpiThreads / 32); }
+    mbar_init(bar(0), 1); mbar_init(bar(1), 2);            // a_empty, b_empty: one commit per issuing warp
+    for (int s = 0; s < kRsStages; s++) { mbar_init(bar(2 + s), 1); mbar_init(bar(4 + s), 2); }
+    for (int q = 0; q < 4; q++) { mbar_init(bar(20 + q), 1); mbar_init(bar(24 + q), kRsEpiThreads / 128); }   // tfull / tempty
+    for (int s = 0; s < 2; s++) { mbar_init(bar(10 + s), 1); mbar_init(bar(12 + s), 2 + kRsEpiThreads / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -991,6 +1003,7 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       long long n_tiles_done = 0, n_items_done = 0;
       int w_static = blockIdx.x;
       int prev_q0 = -1, prev_qn = -1;   // query tile currently resident (consecutive items may share it)
+      int a_loads = 0;                  // query tiles loaded so far (parity selects the tail buffer)
       for (int k = 0;; k++) {
         int w;
         if (w_static < args.n_static) { w = w_static; w_static += gridDim.x; }
@@ -1017,9 +1030,11 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(bar(1), a_phase ^ 1u);
             mbar_expect_tx(bar(0), geo.a_bytes);
             for (int c = 0; c < NFULL; c++) tma_load_2d(a_base + (uint32_t)c * RS_BM * 128, &tmA, bar(0), c * 64, it.q_row0);
+            const uint32_t rem_dst = (ta && (a_loads & 1)) ? a_rem2 : a_rem;
             for (int p = 0; p < REM; p++)
-              tma_load_2d(a_rem + (uint32_t)p * RS_BM * 32, &tmAt, bar(0), NFULL * 64 + p * 16, it.q_row0);
+              tma_load_2d(rem_dst + (uint32_t)p * RS_BM * 32, &tmAt, bar(0), NFULL * 64 + p * 16, it.q_row0);
             a_phase ^= 1u;
+            a_loads++;
           }
           if (t == ntiles) break;
           TL(8);
@@ -1045,16 +1060,21 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    // The whole warp runs this loop (warp-uniform control flow keeps descriptors and barrier
-    // addresses in uniform registers); one elected lane issues tcgen05.mma / commit.  The 2*K16
-    // MMAs of a tile are straight-line code: a single thread's dependent instruction stream costs
-    // ~45 cycles per issue, against 96 cycles of tensor work per M128 x N192 x K16 instruction.
+  } else if (warp == 1 || warp == kRsMmaWarp1) {
+    // ================= MMA issuers: one warp per query half =================
+    // Each warp runs this loop for ITS accumulator half h (warp-uniform control flow keeps descriptors and barrier
+    // addresses in uniform registers); one elected lane issues tcgen05.mma / commit.  The K16 MMAs of a half tile are
+    // straight-line code: a single thread's dependent instruction stream costs ~45 cycles per issue, against 96 cycles
+    // of tensor work per M128 x N192 x K16 instruction.  Two issuing warps instead of one: a half's next tile is
+    // issued as soon as ITS accumulator has been drained, not after the other half's nine MMAs have been pushed
+    // through the (back-pressured) issue queue — the accumulator round trip was the tile period (timeline: 2083 of
+    // 2122 cycles against 1728 of tensor work).
+    const int h = (warp == 1) ? 0 : 1;
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0, t_phase = 0, a_phase = 0;
     int prev_q0 = -1, prev_qn = -1;
+    int a_tiles = -1;                    // index of the resident query tile (parity selects its tail buffer)
     for (int k = 0;; k++) {
       const int w = next_item(k);
       if (w < 0) break;
@@ -1062,47 +1082,52 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ntiles = (it.col1 - it.col0 + RS_BN - 1) / RS_BN;
       if (ntiles <= 0) continue;
       if (it.q_row0 != prev_q0 || it.q_rows != prev_qn) {
-        // a different query tile: release the resident one (free once the MMAs issued so far
-        // retire), then wait for the new one
-        if (prev_qn >= 0 && leader) umma_commit(bar(1));
+        // a different query tile.  A from shared memory: release the resident one (free once the MMAs issued so
+        // far retire), then wait for the new one.  A from tensor memory: the shared-memory copy was released right
+        // after it had been copied (below), so the new tile has normally landed long ago.
+        if (!ta && prev_qn >= 0 && leader) umma_commit(bar(1));
         __syncwarp();
         prev_q0 = it.q_row0; prev_qn = it.q_rows;
         mbar_wait(bar(0), a_phase);
         a_phase ^= 1u;
-        if (args.a_tmem && NFULL > 0) {
+        a_tiles++;
+        if (ta) {
           tc_fence_after();
           if (leader) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
+            for (int c = 0; c < NFULL; c++) {
+              const uint64_t adesc = smem_desc(a_base + (uint32_t)c * RS_BM * 128 + (uint32_t)h * 128 * 128);
 #pragma unroll
-              for (int c = 0; c < NFULL; c++) {
-                const uint64_t adesc = smem_desc(a_base + (uint32_t)c * RS_BM * 128 + (uint32_t)h * 128 * 128);
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                  tmem_cp_128x256b(tmem_base + (uint32_t)(h * 256 + RS_BN + (c * 4 + k) * 8), adesc + 2u * k);
-              }
+              for (int k = 0; k < 4; k++)
+                tmem_cp_128x256b(tmem_base + (uint32_t)(h * 256 + RS_BN + (c * 4 + k) * 8), adesc + 2u * k);
             }
+            // the copies (and every MMA before them) done -> the producer may fetch the NEXT query tile into the
+            // same shared memory while this one is still being used from tensor memory
+            umma_commit(bar(1));
           }
           __syncwarp();
         }
       }
+      const uint32_t a_rem_cur = (ta && (a_tiles & 1)) ? a_rem2 : a_rem;
       for (int t = 0; t < ntiles; t++) {
-        if (leader) TL(0);
+        if (leader && h == 0) TL(0);
         mbar_wait(bar(2 + stage), phase);
-        if (leader) TL(1);
+        if (leader && h == 0) TL(1);
         const uint32_t b_src = b_base + (uint32_t)stage * geo.b_bytes;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          mbar_wait(bar(8 + h), t_phase ^ 1u);   // epilogue has drained half h of the previous tile
+        for (int cq = 0; cq < 2; cq++) {
+          const int q = h * 2 + cq;
+          mbar_wait(bar(24 + q), t_phase ^ 1u);   // the epilogue has drained this quarter of the previous tile
           tc_fence_after();
           if (leader) {
-            TL(2 + 9 * h);   // slots 2 and 11
-            const uint32_t d_tmem = tmem_base + (uint32_t)(h * 256);
-            if (args.a_tmem) {
-              const uint32_t a_t = d_tmem + (uint32_t)RS_BN;
+            if (cq == 0) TL(2 + 9 * h);   // slots 2 and 11
+            const uint32_t d_tmem = tmem_base + (uint32_t)(h * 256 + cq * RS_QN);
+            const uint32_t b_q = b_src + (uint32_t)(cq * RS_QN * 128);            // train rows [96 cq, 96 cq + 96) of a chunk
+            if (ta) {
+              const uint32_t a_t = tmem_base + (uint32_t)(h * 256 + RS_BN);
 #pragma unroll
               for (int c = 0; c < NFULL; c++) {
-                const uint64_t bdesc = smem_desc(b_src + (uint32_t)c * RS_BN * 128);
+                const uint64_t bdesc = smem_desc(b_q + (uint32_t)c * RS_BN * 128);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                   if (c == 0 && k == 0) umma_bf16_ts_first(d_tmem, a_t, bdesc, kIdescRs);
@@ -1113,7 +1138,7 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int c = 0; c < NFULL; c++) {
                 const uint64_t adesc = smem_desc(a_base + (uint32_t)c * RS_BM * 128 + (uint32_t)h * 128 * 128);
-                const uint64_t bdesc = smem_desc(b_src + (uint32_t)c * RS_BN * 128);
+                const uint64_t bdesc = smem_desc(b_q + (uint32_t)c * RS_BN * 128);
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                   if (c == 0 && k == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdescRs);
@@ -1123,14 +1148,16 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
 #pragma unroll
             for (int p = 0; p < REM; p++) {
-              const uint64_t adesc = smem_desc_sw32(a_rem + (uint32_t)p * RS_BM * 32 + (uint32_t)h * 128 * 32);
-              const uint64_t bdesc = smem_desc_sw32(b_src + (uint32_t)(NFULL * RS_BN * 128 + p * RS_BN * 32));
+              const uint64_t adesc = smem_desc_sw32(a_rem_cur + (uint32_t)p * RS_BM * 32 + (uint32_t)h * 128 * 32);
+              const uint64_t bdesc = smem_desc_sw32(b_src + (uint32_t)(NFULL * RS_BN * 128 + p * RS_BN * 32 + cq * RS_QN * 32));
               if (NFULL == 0 && p == 0) umma_bf16_first(d_tmem, adesc, bdesc, kIdescRs);
               else umma_bf16_acc(d_tmem, adesc, bdesc, kIdescRs);
             }
-            umma_commit(bar(6 + h));
-            if (h == 1) umma_commit(bar(4 + stage));
-            TL(3 + 9 * h);   // slots 3 and 12
+            umma_commit(bar(20 + q));
+            if (cq == 1) {
+              umma_commit(bar(4 + stage));       // the train tile is free once BOTH halves' MMAs have retired
+              TL(3 + 9 * h);   // slots 3 and 12
+            }
           }
           __syncwarp();
         }
@@ -1188,7 +1215,7 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       first_item = false;
       for (int t = 0; t < ntiles; t++) {
         if (tl_thread) TL(4);
-        mbar_wait(bar(6 + mhalf), t_phase);
+        mbar_wait(bar(20 + mhalf * 2 + chalf), t_phase);
         if (tl_thread) TL(5);
         tc_fence_after();
         const int tcol = t * RS_BN + chalf * CW;          // first column of this thread, item-relative
@@ -1209,7 +1236,7 @@ pair_rs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // accumulator columns of this warp are in registers: hand them back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(8 + mhalf));
+        if (lane == 0) mbar_arrive(bar(24 + mhalf * 2 + chalf));
         if (tl_thread) TL(6);
         epi_chunk<MODE, EXCL, SLOTS, kRsEpiThreads>(args, st, sh, ra, col_base + 64, partial, dump, row_local, tcol + 64);
         if (MODE == MODE_NN && st.valid_row) {
