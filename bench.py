@@ -93,19 +93,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """the timed region starts now (nvidia-smi takes a few hundred ms to deliver its first row, so the sampler is
+        started before the warm-up and only rows from here on count)"""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        t0 = getattr(self, "t_mark", 0.0) - 0.1          # a row is up to one 100 ms period old when it is read
+        inside = [r for t, r in self.rows if t >= t0]
+        rows = inside if inside else [r for _, r in self.rows][-3:]
+        sm = [float(r[1]) for r in rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "samples_inside_timed_region": len(inside)}
 
 
 def pin_to_gpu_numa_node(gpu_index: int):
@@ -473,15 +481,16 @@ def run_ours(args):
         prof, E.PROFILE = E.PROFILE, None
         return t, prof
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         step_device()
         step_e2e()
         step_e2e_pageable()
         step_eager()
     tm.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     t_dev = tm.timed(step_device, args.steps)
     if plan is not None and plan.speculative:
         # the replayed graph carries no exhaustive-scan launches; it is only valid if no candidate list overflowed
