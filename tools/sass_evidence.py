@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 LIB = os.path.join(ROOT, "simple_tip_b200", "libb200tip.so")
-COLS = ["UTCHMMA", "LDTM", "UTCBAR", "UTMALDG", "SYNCS", "REDUX", "MUFU.EX2", "RED/ATOM", "LD/ST .SYS"]
+COLS = ["UTCHMMA", "UTCCP", "LDTM", "UTCBAR", "UTMALDG", "SYNCS", "REDUX", "MUFU.EX2", "RED/ATOM", "LD/ST .SYS"]
 
 
 def main():
@@ -27,7 +27,7 @@ def main():
             op = m.group(1)
             c = count[cur]
             c["n"] += 1
-            for key in ("UTCHMMA", "LDTM", "UTCBAR", "UTMALDG", "SYNCS", "REDUX", "MUFU.EX2"):
+            for key in ("UTCHMMA", "UTCCP", "LDTM", "UTCBAR", "UTMALDG", "SYNCS", "REDUX", "MUFU.EX2"):
                 if op.startswith(key):
                     c[key] += 1
             if op.startswith("RED") and not op.startswith("REDUX") or op.startswith("ATOM"):
@@ -39,7 +39,7 @@ def main():
         names[k] = re.sub(r"\(.*", "", d).replace("void ", "")
     print("# SASS evidence (`cuobjdump -sass simple_tip_b200/libb200tip.so`, sm_100a), round 2\n")
     print("Per kernel: instruction count and the mnemonics that show tcgen05 / TMEM / TMA use (B200_PROFILING.md: "
-          "`tcgen05.mma` -> UTCHMMA, `tcgen05.ld` -> LDTM, `tcgen05.commit` -> UTCBAR, TMA -> UTMALDG, mbarrier -> SYNCS); "
+          "`tcgen05.mma` -> UTCHMMA, `tcgen05.cp` -> UTCCP, `tcgen05.ld` -> LDTM, `tcgen05.commit` -> UTCBAR, TMA -> UTMALDG, mbarrier -> SYNCS); "
           "`LD/ST .SYS` = system-scope loads / stores (the peer-memory exchange of csrc/shard.cu).  "
           "Regenerate: `python tools/sass_evidence.py`.\n")
     print("| kernel | SASS instr | " + " | ".join(COLS) + " |")
