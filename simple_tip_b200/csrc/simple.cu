@@ -687,21 +687,25 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const unsigned char* _
   }
 }
 
-// out[m x dn] = (x[:, cols] - mu) . w   (fp32 FFMA, 64x64 tiles, 4x4 per thread)
+// out[m x dn] = (x[:, cols] - mu) . w   (fp32 FFMA; 128 x 64 tiles, 8 x 4 outputs per thread, K in steps of 32).
+// The centring happens in double on the way into shared memory (one rounding to float, as a float64 host expression
+// would give); a warp reads 32 consecutive K of one row per load (128 B), the inner loop is 3 x LDS.128 per 32 FFMA.
+constexpr int kWhBM = 128, kWhBN = 64, kWhBK = 32;
 template <typename T>
 __global__ void __launch_bounds__(256) whiten_kernel(const T* __restrict__ x, int64_t m, int64_t d_in,
                                                      const int32_t* __restrict__ cols, int dn,
                                                      const double* __restrict__ mu, const float* __restrict__ w,
                                                      float* __restrict__ out) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int64_t row0 = (int64_t)blockIdx.y * 64;
-  const int col0 = blockIdx.x * 64;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < dn; k0 += 16) {
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-      const int r = i >> 4, k = i & 15;
+  __shared__ __align__(16) float As[kWhBK][kWhBM + 4];
+  __shared__ __align__(16) float Bs[kWhBK][kWhBN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 column groups of 4, 16 row groups of 8
+  const int64_t row0 = (int64_t)blockIdx.y * kWhBM;
+  const int col0 = blockIdx.x * kWhBN;
+  float acc[8][4] = {};
+  for (int k0 = 0; k0 < dn; k0 += kWhBK) {
+#pragma unroll 4
+    for (int i = threadIdx.x; i < kWhBM * kWhBK; i += 256) {
+      const int r = i >> 5, k = i & 31;
       float v = 0.f;
       if (row0 + r < m && k0 + k < dn) {
         const int src_col = cols ? cols[k0 + k] : (k0 + k);
@@ -709,50 +713,76 @@ __global__ void __launch_bounds__(256) whiten_kernel(const T* __restrict__ x, in
       }
       As[k][r] = v;
     }
-    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+#pragma unroll 4
+    for (int i = threadIdx.x; i < kWhBK * kWhBN; i += 256) {
       const int k = i >> 6, c = i & 63;
       Bs[k][c] = (k0 + k < dn && col0 + c < dn) ? w[(int64_t)(k0 + k) * dn + col0 + c] : 0.f;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-      float a[4], b[4];
+    for (int k = 0; k < kWhBK; k++) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = As[k][ty * 4 + i];
+      for (int i = 0; i < 8; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) b[j] = Bs[k][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
-  for (int i = 0; i < 4; i++) {
-    const int64_t r = row0 + ty * 4 + i;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int64_t r = row0 + ty * 8 + i;
     if (r >= m) continue;
-    for (int j = 0; j < 4; j++) {
-      const int c = col0 + tx * 4 + j;
-      if (c < dn) out[r * dn + c] = acc[i][j];
+    const int c = col0 + tx * 4;
+    if (c + 3 < dn && (dn & 3) == 0) {
+      *reinterpret_cast<float4*>(out + r * dn + c) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (c + j < dn) out[r * dn + c + j] = acc[i][j];
     }
   }
 }
 
+// merge of the per-slot (max, sum exp(. - max)) partials of every query: 32 queries x 8 slot groups per block
 __global__ void __launch_bounds__(256) kde_combine_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
                                                           int64_t m, int slots, float* __restrict__ om,
                                                           float* __restrict__ os) {
-  const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (row >= m) return;
-  float mx = -INFINITY;
-  for (int s = 0; s < slots; s++) mx = fmaxf(mx, pm[(int64_t)s * m + row]);
-  float sum = 0.f;
-  if (mx > -INFINITY)
-    for (int s = 0; s < slots; s++) {
+  __shared__ float s_mx[8][32];
+  __shared__ float s_sum[8][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * 32 + lane;
+  float mx = -INFINITY, sum = 0.f;
+  if (row < m) {
+    for (int s = g; s < slots; s += 8) {               // online merge: one pass over this group's slots
       const float v = pm[(int64_t)s * m + row];
-      if (v > -INFINITY) sum += ps[(int64_t)s * m + row] * expf(v - mx);
+      if (v > -INFINITY) {
+        const float p = ps[(int64_t)s * m + row];
+        if (v > mx) { sum = sum * expf(mx - v) + p; mx = v; }   // mx = -inf: sum is 0, expf(-inf) = 0
+        else sum += p * expf(v - mx);
+      }
     }
-  om[row] = mx;
-  os[row] = sum;
+  }
+  s_mx[g][lane] = mx;
+  s_sum[g][lane] = sum;
+  __syncthreads();
+  if (g == 0 && row < m) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 8; q++) M = fmaxf(M, s_mx[q][lane]);
+    float S = 0.f;
+    if (M > -INFINITY) {
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (s_mx[q][lane] > -INFINITY) S += s_sum[q][lane] * expf(s_mx[q][lane] - M);
+    }
+    om[row] = M;
+    os[row] = S;
+  }
 }
 
 // out[row] = sum_k y[row, k]^2 accumulated in double (one warp per row): the squared Mahalanobis distance /
@@ -996,8 +1026,8 @@ extern "C" int tip_whiten(const void* x, int dtype, int64_t m, int64_t d_in, con
   TIP_REQUIRE(m >= 0 && d_in >= 1 && d_out >= 1 && d_out <= 65535 * 64, "shape");
   TIP_REQUIRE(cols != nullptr || d_in >= d_out, "without a column list the input must be at least d_out wide");
   if (m == 0) return TIP_OK;
-  dim3 grid((unsigned)((d_out + 63) / 64), (unsigned)((m + 63) / 64));
-  TIP_REQUIRE((m + 63) / 64 <= 65535, "too many rows for one launch");
+  dim3 grid((unsigned)((d_out + kWhBN - 1) / kWhBN), (unsigned)((m + kWhBM - 1) / kWhBM));
+  TIP_REQUIRE((m + kWhBM - 1) / kWhBM <= 65535, "too many rows for one launch");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == TIP_F32)
     whiten_kernel<float><<<grid, 256, 0, st>>>((const float*)x, m, d_in, cols, (int)d_out, mu, w, out);
@@ -1023,7 +1053,7 @@ extern "C" int tip_kde_combine(const float* pm, const float* ps, int64_t m, int3
   TIP_REQUIRE(pm && ps && om && os, "null pointer");
   TIP_REQUIRE(m >= 0 && slots >= 1, "shape");
   if (m == 0) return TIP_OK;
-  kde_combine_kernel<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pm, ps, m, slots, om, os);
+  kde_combine_kernel<<<(unsigned)((m + 31) / 32), 256, 0, (cudaStream_t)stream>>>(pm, ps, m, slots, om, os);
   TIP_LAUNCH_CHECK();
   return TIP_OK;
 }
