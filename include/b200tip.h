@@ -226,6 +226,7 @@ int tip_nn_filter_tile(int64_t d, int32_t* q_rows, int32_t* t_rows);
  * (128 x 256 tiles; B200TIP_PAIR2=0).  tip_kde_tile_rows: query rows per work item of tip_kde_lse*. */
 int tip_nn_filter_kind(int64_t d);
 int tip_kde_tile_rows(void);
+int tip_kde_slot_parts(void);   /* partial (max, sum) pairs per work-item slot: part_max / part_sum hold slots x this x m */
 
 /* ---- exact re-rank (NumPy-order distances, first-occurrence argmin) -------------------
  * q, t: original-dtype (TIP_F32/TIP_F64) matrices m x d and n x d; train rows are grouped by
@@ -355,9 +356,9 @@ int tip_row_sqnorm(const float* y, int64_t m, int64_t d, double* out, void* stre
 
 /* q_pack / t_pack from tip_pair_prep(segments=3, scale=1, norm_coef=-0.5 on the train side).
  * For every work item writes the partial (max_i a_ij, sum_i exp(a_ij - max)) of
- * a_ij = <p_i, q_j> - |p_i|^2/2 over the item's span into part_max/part_sum[(2*slot+h)*m + row],
- * h = 0/1 for the two 128-column halves of the 256-wide tiles (so 2*slots*m floats each, which
- * the caller initialises to -inf / 0). */
+ * a_ij = <p_i, q_j> - |p_i|^2/2 over the item's span into part_max/part_sum[(P*slot+h)*m + row],
+ * P = tip_kde_slot_parts(), h = 0..P-1 for the column parts of the 256-wide tiles each group of four epilogue
+ * warps reduces (so P*slots*m floats each, which the caller initialises to -inf / 0). */
 int tip_kde_lse(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d,
                 int64_t pitch, const tip_work_item* items, int32_t n_items, float* part_max,
                 float* part_sum, void* stream);

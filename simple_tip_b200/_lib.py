@@ -82,6 +82,7 @@ _SIGNATURES = {
     "tip_nn_filter_tile": (C.c_int, [_i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "tip_nn_filter_kind": (C.c_int, [_i64]),
     "tip_kde_tile_rows": (C.c_int, []),
+    "tip_kde_slot_parts": (C.c_int, []),
     "tip_debug_timeline": (C.c_int, [_vp, _i32]),
     "tip_debug_cta_clock": (C.c_int, [_vp]),
     "tip_pair_probe": (C.c_int, [_vp, _i64, _vp, _i64, _i64, C.c_int, _i64, C.c_int, _vp, _vp]),

@@ -33,6 +33,11 @@ constexpr int kBBytes = BN * BK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kEpiThreads = 256;             // 8 epilogue warps
 constexpr int kThreads = 64 + kEpiThreads;   // + TMA warp + MMA warp
+// epilogue warps of the streaming kernel in log-sum-exp mode (8 or 16, see pair_kernel).  16 was measured at C3 and
+// changes nothing (0.338 ms either way): the K = 272 pass is bound by shared-memory bandwidth — both operands stream
+// through shared memory for every tile (TMA writes 94 B/clk + MMA reads 96 B/clk against a 128 B/clk port = the
+// measured 3400 cycles per 2176-cycle tile), not by the ex2 pipe's latency.
+constexpr int kLseEpiWarps = 8;
 constexpr int kCandSlots = 8;   // per-query staging slots for candidates (MODE_NN)
 constexpr int kCandBytes = kCandSlots * 256 * 12;   // value, chunk start, 32-bit column mask
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kCandBytes;
@@ -401,9 +406,12 @@ __device__ __forceinline__ void epi_chunk(const PairArgs& args, EpiState& st, co
   }
 }
 
-template <int MODE, bool EXCL>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int MODE, bool EXCL, int EW = 8>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PairArgs args) {
+  // EW epilogue warps: 8 = one query row x 128 columns per thread, 16 = one row x 64 columns (kLseEpiWarps)
+  constexpr int PARTS = EW / 4;          // column parts of a tile, one per group of four epilogue warps
+  constexpr int CPT = BN / PARTS;        // columns per thread and tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -421,7 +429,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiThreads / 32); }
+    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -504,14 +512,14 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ================= epilogue =================
-    // 8 warps: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.
-    // One thread = one query row x one 128-column half of every tile; the two halves of a row
+    // EW warps: TMEM lane quadrant = warp % 4 (hardware rule), column part = (warp - 2) / 4.
+    // One thread = one query row x one CPT-column part of every tile; the parts of a row
     // never talk to each other except through row_min_bits (like CTAs on different spans do).
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;    // column part index, 0 .. PARTS-1
     const int row_local = quad * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (BN / 2));
-    const int etid = threadIdx.x - 64;   // 0..255 among the epilogue threads
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * CPT);
+    const int etid = threadIdx.x - 64;   // index among the epilogue threads
     EpiShared sh;
     sh.cand_val = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
     sh.cand_col = reinterpret_cast<int*>(sh.cand_val + kCandSlots * kEpiThreads);
@@ -547,8 +555,8 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int t = 0; t < ntiles; t++) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        const int col_base = it.col0 + t * BN + half * (BN / 2);
-        const bool partial = col_base + BN / 2 > it.col1;
+        const int col_base = it.col0 + t * BN + half * CPT;
+        const bool partial = col_base + CPT > it.col1;
         uint32_t seen_bits = 0x7f800000u;
         if (MODE == MODE_NN && st.valid_row) seen_bits = ld_volatile_u32(args.row_min_bits + st.row);
         const uint32_t taddr = lane_addr + (uint32_t)(acc * BN);
@@ -557,14 +565,14 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr, ra);
 #pragma unroll 1
-        for (int h = 0; h < 2; h++) {   // rolled on purpose: the epilogue has to stay inside the I-cache
+        for (int h = 0; h < CPT / 64; h++) {   // rolled on purpose: the epilogue has to stay inside the I-cache
           tmem_wait_ld();
           tmem_ld32(taddr + 64 * h + 32, rb);
           epi_chunk<MODE, EXCL>(args, st, sh, ra, col_base + 64 * h, partial, w == 0 && t == 0, row_local,
-                          half * (BN / 2) + 64 * h);
+                          half * CPT + 64 * h);
           tmem_wait_ld();
-          if (h == 0) {
-            tmem_ld32(taddr + 64, ra);
+          if (h + 1 < CPT / 64) {
+            tmem_ld32(taddr + 64 * (h + 1), ra);
           } else {
             // accumulator drained into registers: hand the TMEM stage back to the MMA warp early
             tc_fence_before();
@@ -572,7 +580,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
           epi_chunk<MODE, EXCL>(args, st, sh, rb, col_base + 64 * h + 32, partial, w == 0 && t == 0, row_local,
-                          half * (BN / 2) + 64 * h + 32);
+                          half * CPT + 64 * h + 32);
         }
 
         if (MODE == MODE_NN && st.valid_row) {
@@ -610,8 +618,8 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else if (MODE == MODE_LSE) {
         if (st.valid_row) {
-          args.part_max[(int64_t)(it.slot * 2 + half) * args.m + st.row] = st.run_max;
-          args.part_sum[(int64_t)(it.slot * 2 + half) * args.m + st.row] = st.run_sum;
+          args.part_max[(int64_t)(it.slot * PARTS + half) * args.m + st.row] = st.run_max;
+          args.part_sum[(int64_t)(it.slot * PARTS + half) * args.m + st.row] = st.run_sum;
         }
       }
     }
@@ -1342,13 +1350,14 @@ static int launch_pair(const void* q_pack, int64_t m, const void* t_pack, int64_
   if (rc != TIP_OK) return rc;
   rc = make_map(&mb, t_pack, n, pitch, BN);
   if (rc != TIP_OK) return rc;
+  constexpr int EW = MODE == MODE_LSE ? kLseEpiWarps : 8;
   static bool attr_set = false;   // one flag per template instantiation
   if (!attr_set) {
-    TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_kernel<MODE, EXCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_kernel<MODE, EXCL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   const int grid = min(args.n_items, sm_count());
-  pair_kernel<MODE, EXCL><<<grid, kThreads, kSmemBytes, st>>>(ma, mb, args);
+  pair_kernel<MODE, EXCL, EW><<<grid, 64 + 32 * EW, kSmemBytes, st>>>(ma, mb, args);
   TIP_LAUNCH_CHECK();
   return TIP_OK;
 }
@@ -1516,6 +1525,7 @@ extern "C" int tip_nn_filter_kind(int64_t d) {
 }
 
 extern "C" int tip_kde_tile_rows(void) { return use_pair2() ? 2 * BM : BM; }
+extern "C" int tip_kde_slot_parts(void) { return use_pair2() ? 2 : kLseEpiWarps / 4; }
 
 extern "C" int tip_kde_lse(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t d, int64_t pitch,
                            const tip_work_item* items, int32_t n_items, float* part_max, float* part_sum,

@@ -1184,7 +1184,8 @@ class KdeEngine:
             items = span_major(items)
             if len(self._items) > 16:
                 self._items.clear()
-            plan = (torch.from_numpy(items).to(self.dev), items.shape[0], slots * 2)   # one partial per 128-column half
+            # one partial per column part of a tile (tip_kde_slot_parts: 4 x 64 columns)
+            plan = (torch.from_numpy(items).to(self.dev), items.shape[0], slots * int(self.lib.tip_kde_slot_parts()))
             self._items[m] = plan
         return plan
 
