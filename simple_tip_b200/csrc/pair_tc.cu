@@ -31,6 +31,7 @@ constexpr int kStages = 4;
 constexpr int kABytes = BM * BK * 2;
 constexpr int kBBytes = BN * BK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kResAChunks = 5;               // resident-A variant (RESA): query tiles of up to 5 x 64 K elements
 constexpr int kEpiThreads = 256;             // 8 epilogue warps
 constexpr int kThreads = 64 + kEpiThreads;   // + TMA warp + MMA warp
 // epilogue warps of the streaming kernel in log-sum-exp mode (8 or 16, see pair_kernel).  16 was measured at C3 and
@@ -406,7 +407,7 @@ __device__ __forceinline__ void epi_chunk(const PairArgs& args, EpiState& st, co
   }
 }
 
-template <int MODE, bool EXCL, int EW = 8>
+template <int MODE, bool EXCL, int EW = 8, bool RESA = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PairArgs args) {
   // EW epilogue warps: 8 = one query row x 128 columns per thread, 16 = one row x 64 columns (kLseEpiWarps)
@@ -416,12 +417,17 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t bar0 = base + kStages * kStageBytes;
+  // RESA (short K, tip_kde_lse*): the query tile's K chunks stay RESIDENT in shared memory for the whole work item
+  // (kResAChunks x 16 KB at `base`, loaded once per item) and the ring carries train chunks only (kStages x 32 KB
+  // behind it) — re-streaming A for every train tile cost a third of the TMA write traffic of a bandwidth-bound pass.
+  const uint32_t b_ring = base + (RESA ? kResAChunks * kABytes : 0);
+  const uint32_t bar0 = RESA ? b_ring + kStages * kBBytes : base + kStages * kStageBytes;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kStages + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 4));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (bar0 - base) + 8 * (2 * kStages + 4));
+  const uint32_t a_full = bar0 + 8u * (2 * kStages + 6), a_empty = bar0 + 8u * (2 * kStages + 7);   // RESA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -430,6 +436,7 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW); }
+    if (RESA) { mbar_init(a_full, 1); mbar_init(a_empty, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -451,16 +458,28 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t a_phase = 0;
       for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
         const tip_work_item it = args.items[w];
         const int ntiles = (it.col1 - it.col0 + BN - 1) / BN;
+        if (RESA && ntiles > 0) {
+          mbar_wait(a_empty, a_phase ^ 1u);      // the previous item's MMAs have retired (first item: passes at once)
+          mbar_expect_tx(a_full, (uint32_t)nchunks * kABytes);
+          for (int c = 0; c < nchunks; c++) tma_load_2d(base + (uint32_t)c * kABytes, &tmA, a_full, c * BK, it.q_row0);
+          a_phase ^= 1u;
+        }
         for (int t = 0; t < ntiles; t++) {
           for (int c = 0; c < nchunks; c++) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), kStageBytes);
-            const uint32_t a_dst = base + stage * kStageBytes;
-            tma_load_2d(a_dst, &tmA, full_bar(stage), c * BK, it.q_row0);
-            tma_load_2d(a_dst + kABytes, &tmB, full_bar(stage), c * BK, it.col0 + t * BN);
+            if (RESA) {
+              mbar_expect_tx(full_bar(stage), kBBytes);
+              tma_load_2d(b_ring + (uint32_t)stage * kBBytes, &tmB, full_bar(stage), c * BK, it.col0 + t * BN);
+            } else {
+              mbar_expect_tx(full_bar(stage), kStageBytes);
+              const uint32_t a_dst = base + stage * kStageBytes;
+              tma_load_2d(a_dst, &tmA, full_bar(stage), c * BK, it.q_row0);
+              tma_load_2d(a_dst + kABytes, &tmB, full_bar(stage), c * BK, it.col0 + t * BN);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -474,10 +493,15 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool leader = elect_one();
     const uint32_t idesc = args.idesc ? args.idesc : kIdesc;
     int stage = 0, acc = 0;
-    uint32_t phase = 0, acc_phase = 0;
+    uint32_t phase = 0, acc_phase = 0, a_phase = 0;
     for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
       const tip_work_item it = args.items[w];
       const int ntiles = (it.col1 - it.col0 + BN - 1) / BN;
+      if (RESA && ntiles > 0) {
+        mbar_wait(a_full, a_phase);
+        a_phase ^= 1u;
+        tc_fence_after();
+      }
       for (int t = 0; t < ntiles; t++) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
@@ -486,8 +510,8 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = base + stage * kStageBytes;
-          const uint64_t adesc = smem_desc(a_addr);
-          const uint64_t bdesc = smem_desc(a_addr + kABytes);
+          const uint64_t adesc = smem_desc(RESA ? base + (uint32_t)c * kABytes : a_addr);
+          const uint64_t bdesc = smem_desc(RESA ? b_ring + (uint32_t)stage * kBBytes : a_addr + kABytes);
           const int nm = min(4, k16 - 4 * c);
           if (leader) {
             // +32 bytes (one K=16 slice) inside the 128-byte swizzle row = +2 in the >>4 field
@@ -508,6 +532,10 @@ pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
+      }
+      if (RESA && ntiles > 0) {
+        if (leader) umma_commit(a_empty);      // the resident query tile is free once this item's MMAs have retired
+        __syncwarp();
       }
     }
   } else {
@@ -1337,6 +1365,9 @@ static int check_device() {
   return TIP_OK;
 }
 
+constexpr int kResADefault = 1;      // measured at C3: 0.3406 -> 0.3320 ms per step
+static_assert(kResAChunks * kABytes + kStages * kBBytes + 256 + 1024 <= kSmemBytes, "resident-A layout does not fit");
+
 template <int MODE, bool EXCL = false>
 static int launch_pair(const void* q_pack, int64_t m, const void* t_pack, int64_t n, int64_t pitch, PairArgs args,
                        cudaStream_t st) {
@@ -1354,10 +1385,20 @@ static int launch_pair(const void* q_pack, int64_t m, const void* t_pack, int64_
   static bool attr_set = false;   // one flag per template instantiation
   if (!attr_set) {
     TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_kernel<MODE, EXCL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    if (MODE == MODE_LSE)
+      TIP_CHECK_CUDA(cudaFuncSetAttribute(pair_kernel<MODE, EXCL, EW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   const int grid = min(args.n_items, sm_count());
-  pair_kernel<MODE, EXCL, EW><<<grid, 64 + 32 * EW, kSmemBytes, st>>>(ma, mb, args);
+  static int resa = -1;      // B200TIP_RESA=0: the log-sum-exp pass streams the query tile like the candidate search does
+  if (resa < 0) {
+    const char* e = getenv("B200TIP_RESA");
+    resa = e ? (e[0] == '1' ? 1 : 0) : kResADefault;
+  }
+  if (MODE == MODE_LSE && resa && (args.k16 + 3) / 4 <= kResAChunks)
+    pair_kernel<MODE, EXCL, EW, MODE == MODE_LSE><<<grid, 64 + 32 * EW, kSmemBytes, st>>>(ma, mb, args);
+  else
+    pair_kernel<MODE, EXCL, EW><<<grid, 64 + 32 * EW, kSmemBytes, st>>>(ma, mb, args);
   TIP_LAUNCH_CHECK();
   return TIP_OK;
 }
