@@ -438,6 +438,36 @@ def test_lsa_random_vs_oracle(n_train, n_test, d, seed, dt):
     assert np.array_equal(LSA(xtr)(xte), got)            # deterministic across fits and calls
 
 
+def test_lsa_repeated_batch_shapes_replay_a_graph_with_the_same_bits():
+    """A batch shape seen for the second time is captured as one CUDA graph and replayed from then on
+    (stable_kde._DensityPlan): eager first call, capturing second call and replays give the same bits, for NumPy and
+    device-resident inputs, for other data of the same shape, with and without the one-segment fast pass, and for the
+    per-class LSAs of a MultiModalSA (ten plans in flight); a different shape in between does not disturb a plan."""
+    torch = _torch()
+    from src.core.surprise import LSA, MultiModalSA
+
+    for n_train, n_test, d in ((5000, 1500, 256), (3000, 300, 24)):        # with / without the fast pass
+        xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(n_train, n_test, d, 5, seed=41, spread=1.0)
+        xte2 = np.ascontiguousarray(xte[::-1])
+        sa = LSA(xtr)
+        first = sa(xte)
+        _close(first, np_oracle.lsa_oracle(xtr, xte))
+        for _ in range(3):
+            assert np.array_equal(sa(xte), first)
+        assert any(k[0] == n_test for k in sa.kde._plans)                   # the graph path is what ran
+        assert np.array_equal(sa(torch.from_numpy(xte).cuda()), first)
+        other = sa(xte2)                                                    # same shape, other data: same plan
+        assert np.array_equal(other, first[::-1])
+        part = sa(xte[:77])                                                 # another shape in between (batches under 1024
+        _close(part, first[:77])                                            # inputs never try the one-segment pass)
+        assert np.array_equal(sa(xte[:77]), part)
+        assert np.array_equal(sa(xte), first)
+        mm = MultiModalSA.build_by_class(xtr, ytr, lambda x, y: LSA(x))
+        want = mm(xte, pte)
+        for _ in range(3):
+            assert np.array_equal(mm(xte, pte), want, equal_nan=True)
+
+
 def test_lsa_bf16_stored_traces_config3_shape():
     """BASELINE config 3 shape at reduced N: traces stored in bf16; both sides see the same
     bf16-rounded values."""
