@@ -20,8 +20,11 @@ Every line also carries (so that the driver records them, not only the builder):
       N x the measured tensor peak, time of one exchange, and `parity_ok`: sampled inputs checked bit
       for bit against the CPU oracle on a host copy of the traces;
   `parity_ok` (N > 1)  C2 through the N_train-sharded DSA class vs the NumPy oracle, bit for bit;
-  `other_configs` (N = 1)  C1 DeepGini, C3 LSA (+ per-class LSA), C4 KMNC: device ms, e2e, roofline and
-      cpu_baseline each (also selectable alone with --workload).
+  `other_configs` (N = 1)  C1 DeepGini, C3 LSA (+ per-class LSA, `device_call_graph_ms` = the CUDA-graph replay of a
+      whole scoring call's device work), C4 KMNC, CAM: device ms, e2e, roofline and cpu_baseline each (also selectable
+      alone with --workload);
+  `fit_time_table` (N = 1)  the opt-in extension DSA.fit_other_class_table() — not what `value` measures;
+  `stall_retries`  how many timed measurements were repeated because one step contained a host stall (Timer.timed).
 
 `value` times the device-resident path (test traces already in HBM, result left in HBM); `e2e` times
 the reference-facing call `DSA.__call__(numpy, numpy) -> numpy` from pinned host memory, host<->device

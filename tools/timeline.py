@@ -1,4 +1,6 @@
-"""Per-tile timeline of block 0 of the resident-query filter kernel (bring-up tool)."""
+"""Per-tile timeline of block 0 of the resident-query filter kernel (bring-up tool).
+Since the quarter-accumulator rewrite the two MMA warps stamp their own half: "issue half h" spans both quarters of
+that half (wait for the second quarter's accumulator included), "wait TMEM half h empty" is the first quarter's wait."""
 import ctypes as C
 import os
 import sys
