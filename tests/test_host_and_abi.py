@@ -373,3 +373,28 @@ def test_winner_keys_order_like_numpy_argmin():
     assert (none > keys.max()).all()
     nd, ng = E.unpack_winner_keys(none)
     assert np.isnan(nd.numpy()).all() and (ng.numpy() == -1).all()
+
+
+def test_bench_clock_sampler_reports_rows_of_the_timed_region():
+    """bench.py's nvidia-smi sampler: rows from before the timed region are ignored once rows inside exist, throttle
+    reasons are collected, and a run whose sampler delivered nothing inside still reports the latest rows."""
+    import time
+
+    import bench
+
+    s = bench.ClockSampler(0)
+    s.proc = type("P", (), {"terminate": lambda self: None})()
+    now = time.perf_counter()
+    row = lambda sm, cap: ["0", str(sm), "1965", "500.0", "Not Active", "Not Active", "Not Active", cap]
+    s.rows = [(now - 5.0, row(210, "Not Active")), (now - 4.9, row(1500, "Not Active"))]
+    s.t_mark = now - 1.0
+    s.rows += [(now - 0.5, row(1965, "Active")), (now - 0.4, row(1950, "Not Active")), (now - 0.3, row(1965, "Not Active"))]
+    out = s.stop()
+    assert out["samples_inside_timed_region"] == 3 and out["samples"] == 3
+    assert out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    s2 = bench.ClockSampler(0)
+    s2.proc = type("P", (), {"terminate": lambda self: None})()
+    s2.rows = [(now - 5.0, row(1800, "Not Active"))]
+    s2.t_mark = now
+    out2 = s2.stop()
+    assert out2["samples_inside_timed_region"] == 0 and out2["samples"] == 1 and out2["sm_mhz"] == 1800.0
