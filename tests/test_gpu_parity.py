@@ -1005,6 +1005,25 @@ def test_lsa_fast_pass_is_verified_and_falls_back():
     _close(res[5:][sub[sub >= 5] - 5], np_oracle.lsa_oracle(xtr, far[5:][sub[sub >= 5] - 5]))
 
 
+def test_dsa_nan_test_trace_is_contained():
+    """NaN traces are unsupported inputs, but one bad row must neither crash the call nor disturb the
+    other rows: their scores stay bit-identical to the reference's, on the eager first call, on the captured plan (which
+    counts the row's empty candidate list and repeats the call eagerly) and on later calls."""
+    from src.core.surprise import DSA
+
+    xtr, ytr, xte, pte, _ = np_oracle.synth_clusters(4000, 300, 64, 4, seed=71)
+    bad = xte.copy()
+    bad[17, 5] = np.nan
+    want = np_oracle.dsa_oracle(xtr, ytr, xte, pte)["dsa"]
+    sa = DSA(xtr, ytr)
+    keep = np.ones(300, dtype=bool)
+    keep[17] = False
+    for _ in range(4):
+        got = sa(bad, pte)
+        assert got.shape == (300,) and np.array_equal(got[keep], want[keep])
+    assert np.array_equal(sa(xte, pte), want)            # and a clean batch of the same shape afterwards
+
+
 def test_dsa_mixed_dtypes_follow_numpy_promotion():
     """float64 test traces against float32 training traces: NumPy promotes the difference to float64
     (surprise.py:638) — same bits here; float16 traces are widened and scored in float32 (documented)."""
